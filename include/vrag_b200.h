@@ -1,0 +1,160 @@
+/*
+ * libvrag_b200 -- C ABI of the B200-native verbatim-rag hot path.
+ *
+ * The reference (KRLabsOrg/verbatim-rag) is pure Python and has NO FFI of its own; the drop-in
+ * boundary is its three plugin ABCs.  Each entry point below replaces the third-party call that
+ * the reference makes at the cited line; the Python plugin classes in verbatim_rag_b200/ bind these
+ * through ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ *   vrag_span_forward        <- ModelSpanExtractor._extract_highlighter -> model.process()
+ *                               packages/core/verbatim_core/extractors.py:203-228 (forward part)
+ *   vrag_spans_from_probs    <- same call, span post-processing part (threshold / merge / min length)
+ *   vrag_encoder_create      <- ModelSpanExtractor._init_highlighter   extractors.py:151-157
+ *                               SpladeProvider._load_model              verbatim_rag/embedding_providers.py:125-136
+ *   vrag_splade_forward      <- SpladeProvider.embed_batch / embed_text -> SparseEncoder.encode
+ *                               verbatim_rag/embedding_providers.py:138-166
+ *   vrag_dense_forward       <- SentenceTransformersProvider.embed_batch embedding_providers.py:73-77
+ *   vrag_index_create        <- LocalMilvusStore._setup_client          verbatim_rag/vector_stores/milvus_local.py:58-125
+ *   vrag_index_add_*         <- BaseMilvusStore.add_vectors -> client.insert   milvus_base.py:90-127
+ *   vrag_index_search_dense  <- BaseMilvusStore.query dense branch -> client.search  milvus_base.py:239-248
+ *   vrag_index_search_sparse <- BaseMilvusStore.query sparse branch -> client.search milvus_base.py:250-259
+ *   vrag_index_mark_deleted  <- BaseMilvusStore.delete -> client.delete         milvus_base.py:461-470
+ *   vrag_topk_merge          <- (new) merge of per-shard top-k after the NCCL all-gather
+ *
+ * Conventions: every call returns an int status (0 = VRAG_OK); vrag_last_error() gives the message.
+ * The CALLER owns all data buffers; the library owns only handles, weights, corpora and workspaces.
+ * `on_device` != 0 means the data pointers are device pointers on the context's GPU (inputs already
+ * resident in HBM); 0 means host pointers and the call performs the H2D / D2H copies itself.
+ * No exception crosses the ABI.  All work is issued on the context's stream; calls that return data
+ * to host pointers are synchronous, device-pointer calls are asynchronous until vrag_sync().
+ * There is no CPU fallback: without a CUDA device vrag_ctx_create fails with VRAG_ERR_CUDA.
+ */
+#ifndef VRAG_B200_H
+#define VRAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRAG_OK 0
+#define VRAG_ERR_CUDA 1      /* CUDA runtime / driver failure (incl. no device) */
+#define VRAG_ERR_ARG 2       /* invalid argument */
+#define VRAG_ERR_CAPACITY 3  /* caller's output buffer too small; *needed says how much */
+#define VRAG_ERR_WEIGHTS 4   /* missing / mis-shaped tensor in the weight set */
+#define VRAG_ERR_INTERNAL 5
+
+#define VRAG_ENC_MODERNBERT_TOKCLS 0 /* ModernBERT encoder + token-classification head (span extractor) */
+#define VRAG_ENC_BERT_MLM 1          /* BERT encoder + MLM head + SPLADE pooling (sparse provider) */
+#define VRAG_ENC_BERT_DENSE 2        /* BERT encoder + mean/CLS pooling (dense provider) */
+
+#define VRAG_INDEX_DENSE_COSINE 0
+#define VRAG_INDEX_SPARSE_IP 1
+
+#define VRAG_POOL_MEAN 0
+#define VRAG_POOL_CLS 1
+
+typedef struct vrag_ctx vrag_ctx;
+typedef struct vrag_encoder vrag_encoder;
+typedef struct vrag_index vrag_index;
+
+/* One named fp32 host tensor of a checkpoint (HuggingFace parameter name, row-major). */
+typedef struct vrag_tensor {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} vrag_tensor;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int vrag_ctx_create(int device, vrag_ctx** out);
+void vrag_ctx_destroy(vrag_ctx* ctx);
+const char* vrag_last_error(vrag_ctx* ctx); /* ctx may be NULL: last error of a failed vrag_ctx_create */
+int vrag_sync(vrag_ctx* ctx);
+void* vrag_stream(vrag_ctx* ctx);            /* the cudaStream_t all kernels are launched on */
+uint64_t vrag_launch_count(vrag_ctx* ctx);   /* kernels launched so far through this context */
+const char* vrag_version(void);
+
+/* ---- encoders ------------------------------------------------------------------------------ */
+/* Uploads + repacks the checkpoint (fp32 host tensors -> fp16 tensor-core operands, fp32 norms/biases).
+ * max_tokens bounds the tokens processed per internal pass (workspace size). */
+int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
+                        const vrag_tensor* tensors, int num_tensors, vrag_encoder** out);
+void vrag_encoder_destroy(vrag_encoder* enc);
+
+/* Token-classification forward over `nseq` unpadded sequences packed back to back:
+ * ids[cu_seqlens[i] .. cu_seqlens[i+1]) is sequence i; cu_seqlens is always a HOST array [nseq+1].
+ * probs_out[t]  = softmax(logits[t])[1]  (P(relevant), fp32)      [total_tokens]
+ * logits_out    = raw logits [total_tokens, 2] or NULL. */
+int vrag_span_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq, float* probs_out,
+                      float* logits_out, int on_device);
+
+/* SPLADE forward: per sequence max over tokens of log1p(relu(mlm_logits)), returned as CSR with
+ * entries > min_abs (0.0 reproduces embed_batch's np.nonzero, 1e-6 embed_text's filter).
+ * indptr_out [nseq+1], indices_out/values_out [cap] are HOST buffers; on VRAG_ERR_CAPACITY *nnz_out is
+ * the required capacity.  dense_out (nullable) receives the dense [nseq, vocab] fp32 vectors
+ * (host or device per on_device; `ids` follows on_device too). */
+int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq, float min_abs,
+                        int64_t* indptr_out, int32_t* indices_out, float* values_out, int64_t cap, int64_t* nnz_out,
+                        float* dense_out, int on_device);
+
+/* Dense sentence embedding: encoder -> mean / CLS pooling -> optional L2 normalisation.  out [nseq, hidden]. */
+int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq, int pooling,
+                       int normalize, float* out, int on_device);
+
+/* Debug / test hook: run the tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (fp16 operands, fp32 accumulate) against
+ * an in-library SIMT reference GEMM on random data and return the max |diff| (device-side self check). */
+int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff, double* ref_abs_max);
+
+/* Debug hook (tests): vrag_span_forward with host buffers that also returns the fp32 residual stream after
+ * the embedding and after every layer, hidden_out [num_layers + 1, total_tokens, 768]; single pass only. */
+int vrag_debug_span_hidden(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,
+                           float* probs_out, float* logits_out, float* hidden_out);
+
+/* ---- span post-processing (host, integer logic) -------------------------------------------- */
+/* For context c, its tokens are [ctx_indptr[c], ctx_indptr[c+1]) in probs / tok_char_start / tok_char_end.
+ * keep = p > threshold; maximal runs -> char spans; merge gaps <= merge_gap_chars; drop spans shorter than
+ * min_span_chars.  Outputs (capacity cap): span_ctx, span_char_start, span_char_end, span_score (mean kept p),
+ * span_tok_start, span_tok_end (token indices relative to the context).  *nspans_out = number produced / needed. */
+int vrag_spans_from_probs(const float* probs, const int32_t* tok_char_start, const int32_t* tok_char_end,
+                          const int64_t* ctx_indptr, int nctx, float threshold, int min_span_chars,
+                          int merge_gap_chars, int32_t* span_ctx, int32_t* span_char_start, int32_t* span_char_end,
+                          float* span_score, int32_t* span_tok_start, int32_t* span_tok_end, int64_t cap,
+                          int64_t* nspans_out);
+
+/* ---- exact top-k index --------------------------------------------------------------------- */
+int vrag_index_create(vrag_ctx* ctx, int kind, int dim, vrag_index** out);
+void vrag_index_destroy(vrag_index* idx);
+int64_t vrag_index_size(vrag_index* idx);
+/* Append n fp32 rows [n, dim] (not normalised; the index caches 1/||row|| computed in fp64). */
+int vrag_index_add_dense(vrag_index* idx, const float* rows, int64_t n, int on_device);
+/* Append n sparse rows given as host CSR (indptr [n+1] relative to this call, indices ascending per row). */
+int vrag_index_add_sparse(vrag_index* idx, const int64_t* indptr, const int32_t* indices, const float* values,
+                          int64_t n);
+/* Global id of this shard's row 0: added to the row numbers reported by the searches (corpus row-sharded
+ * across GPUs). */
+int vrag_index_set_id_base(vrag_index* idx, int64_t base);
+/* Tombstone rows (deleted rows never appear in results). rows: host array of row numbers. */
+int vrag_index_mark_deleted(vrag_index* idx, const int64_t* rows, int64_t n);
+
+/* Exact top-k.  Order: score descending, row index ascending; score evaluated in fp64 from the stored fp32
+ * values and reported both as fp32 (scores_out) and fp64 (scores64_out, nullable).  Results [nq, k]; when the
+ * index holds fewer than k live rows the tail is filled with id -1 / score -inf.
+ * queries [nq, dim] fp32 (host/device per on_device); outputs follow on_device too. */
+int vrag_index_search_dense(vrag_index* idx, const float* queries, int nq, int k, int64_t* ids_out, float* scores_out,
+                            double* scores64_out, int on_device);
+/* Sparse queries as host CSR; outputs are host buffers. */
+int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr, const int32_t* q_indices,
+                             const float* q_values, int nq, int k, int64_t* ids_out, float* scores_out,
+                             double* scores64_out);
+
+/* Merge m candidate (score64, id) pairs per query (e.g. the all-gathered per-shard top-k of all ranks) into the
+ * global top-k with the same order.  Device buffers on ctx's GPU. */
+int vrag_topk_merge(vrag_ctx* ctx, const double* scores64, const int64_t* ids, int nq, int m, int k, int64_t* ids_out,
+                    float* scores_out, double* scores64_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRAG_B200_H */

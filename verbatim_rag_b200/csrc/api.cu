@@ -1,0 +1,236 @@
+// Context management, TMA descriptor encode, host span post-processing and the GEMM self test.
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+#include <random>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+using namespace vrag;
+
+static thread_local std::string g_create_error;
+
+void* vrag_ctx::pinned_reserve(size_t n) {
+  if (n <= pinned_bytes) return pinned;
+  if (pinned) cudaFreeHost(pinned);
+  pinned = nullptr;
+  pinned_bytes = 0;
+  VRAG_CUDA(cudaMallocHost(&pinned, n));
+  pinned_bytes = n;
+  return pinned;
+}
+
+namespace vrag {
+
+CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt, size_t elem_bytes, uint64_t rows,
+                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_elems * elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  VRAG_CHECK(box_cols * elem_bytes == 128, VRAG_ERR_INTERNAL, "tensor map: inner box must span 128 bytes");
+  VRAG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (gstride[0] & 15) == 0, VRAG_ERR_INTERNAL,
+             "tensor map: base / stride not 16-byte aligned");
+  CUresult r = ctx->encode_tiled(&m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(VRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return m;
+}
+
+}  // namespace vrag
+
+extern "C" const char* vrag_version(void) { return "vrag_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int vrag_ctx_create(int device, vrag_ctx** out) {
+  if (!out) return VRAG_ERR_ARG;
+  *out = nullptr;
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw Error(VRAG_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                     "); libvrag_b200 has no CPU fallback");
+    VRAG_CHECK(device >= 0 && device < count, VRAG_ERR_ARG, "ctx_create: device index out of range");
+    VRAG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VRAG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw Error(VRAG_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                     std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only");
+    std::unique_ptr<vrag_ctx> c(new vrag_ctx());
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    VRAG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VRAG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) throw Error(VRAG_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    c->encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    *out = c.release();
+    return VRAG_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return VRAG_ERR_INTERNAL;
+  }
+}
+
+extern "C" void vrag_ctx_destroy(vrag_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+}
+
+extern "C" const char* vrag_last_error(vrag_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+extern "C" int vrag_sync(vrag_ctx* ctx) {
+  if (!ctx) return VRAG_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("stream synchronize: ") + cudaGetErrorString(e);
+    return VRAG_ERR_CUDA;
+  }
+  return VRAG_OK;
+}
+
+extern "C" void* vrag_stream(vrag_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+extern "C" uint64_t vrag_launch_count(vrag_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Span post-processing: the integer half of the highlighter contract (oracle/highlighter.py steps 4-8;
+// reference call site packages/core/verbatim_core/extractors.py:213-224).
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrag_spans_from_probs(const float* probs, const int32_t* tcs, const int32_t* tce,
+                                     const int64_t* ctx_indptr, int nctx, float threshold, int min_span_chars,
+                                     int merge_gap_chars, int32_t* span_ctx, int32_t* span_cs, int32_t* span_ce,
+                                     float* span_score, int32_t* span_ts, int32_t* span_te, int64_t cap,
+                                     int64_t* nspans_out) {
+  if (!probs || !tcs || !tce || !ctx_indptr || !nspans_out || nctx < 0) return VRAG_ERR_ARG;
+  int64_t count = 0;
+  for (int c = 0; c < nctx; ++c) {
+    const int64_t a = ctx_indptr[c], b = ctx_indptr[c + 1];
+    bool open = false;
+    int32_t cs = 0, ce = 0, ts = 0, te = 0, cnt = 0;
+    double acc = 0.0;
+    auto flush = [&]() {
+      if (open && ce - cs >= min_span_chars) {
+        if (count < cap) {
+          span_ctx[count] = c;
+          span_cs[count] = cs;
+          span_ce[count] = ce;
+          span_score[count] = static_cast<float>(acc / cnt);
+          span_ts[count] = ts;
+          span_te[count] = te;
+        }
+        ++count;
+      }
+      open = false;
+    };
+    int64_t i = a;
+    while (i < b) {
+      if (!(probs[i] > threshold)) { ++i; continue; }
+      int64_t j = i;
+      double racc = 0.0;
+      while (j < b && probs[j] > threshold) { racc += static_cast<double>(probs[j]); ++j; }
+      const int32_t rs = tcs[i], re = tce[j - 1];
+      if (open && rs - ce <= merge_gap_chars) {  // merge into the open span
+        ce = re;
+        te = static_cast<int32_t>(j - a);
+        acc += racc;
+        cnt += static_cast<int32_t>(j - i);
+      } else {
+        flush();
+        open = true;
+        cs = rs; ce = re;
+        ts = static_cast<int32_t>(i - a); te = static_cast<int32_t>(j - a);
+        acc = racc;
+        cnt = static_cast<int32_t>(j - i);
+      }
+      i = j;
+    }
+    flush();
+  }
+  *nspans_out = count;
+  return count <= cap ? VRAG_OK : VRAG_ERR_CAPACITY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM self test: tcgen05 path vs the SIMT reference path, same epilogue (EPI_F32 or EPI_F16), on the device.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void fill_half_kernel(__half* p, size_t n, uint32_t seed, float scale) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = static_cast<uint32_t>(i) * 2654435761u + seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  p[i] = __float2half_rn((static_cast<float>(x & 0xffff) / 32768.0f - 1.0f) * scale);
+}
+__global__ void diff_kernel(const float* a, const float* b, size_t n, float* out /*[2]: max diff, max |b|*/) {
+  float d = 0.f, m = 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float x = fabsf(a[i] - b[i]);
+    if (!(x == x)) x = INFINITY;  // NaN (e.g. an output the kernel never wrote) must not hide behind fmaxf
+    d = fmaxf(d, x);
+    m = fmaxf(m, fabsf(b[i]));
+  }
+  atomicMax(reinterpret_cast<int*>(out), __float_as_int(d));
+  atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(m));
+}
+}  // namespace
+
+extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff,
+                                  double* ref_abs_max) {
+  if (!ctx || !max_abs_diff) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  try {
+    VRAG_CUDA(cudaSetDevice(ctx->device));
+    VRAG_CHECK(epilogue == EPI_F32, VRAG_ERR_ARG, "selftest_gemm: only the plain fp32 epilogue (10) is supported");
+    DevBuf A, W, C0, C1, R;
+    A.reserve(static_cast<size_t>(M) * K * 2);
+    W.reserve(static_cast<size_t>(N) * K * 2);
+    C0.reserve(static_cast<size_t>(M) * N * 4);
+    C1.reserve(static_cast<size_t>(M) * N * 4);
+    R.reserve(8);
+    fill_half_kernel<<<static_cast<unsigned>((static_cast<size_t>(M) * K + 255) / 256), 256, 0, ctx->stream>>>(
+        A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
+    fill_half_kernel<<<static_cast<unsigned>((static_cast<size_t>(N) * K + 255) / 256), 256, 0, ctx->stream>>>(
+        W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
+    VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, static_cast<size_t>(M) * N * 4, ctx->stream));
+    VRAG_CUDA(cudaMemsetAsync(C1.p, 0, static_cast<size_t>(M) * N * 4, ctx->stream));
+    VRAG_CUDA(cudaMemsetAsync(R.p, 0, 8, ctx->stream));
+    GemmEpiParams p;
+    p.M = M; p.ld32 = N;
+    p.out32 = C0.as<float>();
+    launch_gemm(ctx, EPI_F32, A.as<__half>(), W.as<__half>(), M, N, K, p, 0);
+    p.out32 = C1.as<float>();
+    launch_gemm(ctx, EPI_F32, A.as<__half>(), W.as<__half>(), M, N, K, p, 1);
+    diff_kernel<<<256, 256, 0, ctx->stream>>>(C0.as<float>(), C1.as<float>(), static_cast<size_t>(M) * N, R.as<float>());
+    float h[2];
+    VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
+    if (ref_abs_max) *ref_abs_max = h[1];
+    A.release(); W.release(); C0.release(); C1.release(); R.release();
+    return VRAG_OK;
+  } catch (const Error& e) {
+    ctx->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->last_error = e.what();
+    return VRAG_ERR_INTERNAL;
+  }
+}

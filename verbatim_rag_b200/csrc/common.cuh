@@ -1,0 +1,89 @@
+// Shared host-side plumbing of libvrag_b200: context, error reporting, TMA descriptor encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vrag_b200.h"
+
+namespace vrag {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define VRAG_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw ::vrag::Error(VRAG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + \
+                                             __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
+  } while (0)
+
+#define VRAG_CHECK(cond, code, msg)                       \
+  do {                                                    \
+    if (!(cond)) throw ::vrag::Error((code), (msg));      \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Device buffer owned by the library (workspaces, weights, corpora).
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    VRAG_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace vrag
+
+// The context behind the opaque C handle.
+struct vrag_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  vrag::PFN_encodeTiled encode_tiled = nullptr;
+  std::string last_error;
+  std::mutex mu;           // one call at a time per context (plugin objects are shared across threads)
+  uint64_t launches = 0;   // kernels launched through this context (bench.py's gpu_launches)
+  // pinned staging for the *_host entry points
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* pinned_reserve(size_t n);
+};
+
+namespace vrag {
+
+// 2D row-major tensor map, 128-byte swizzle, box = {box_cols (128 bytes worth), box_rows}.
+CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt, size_t elem_bytes, uint64_t rows,
+                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
+struct StreamGuard {
+  vrag_ctx* c;
+  explicit StreamGuard(vrag_ctx* ctx) : c(ctx) { VRAG_CUDA(cudaSetDevice(ctx->device)); }
+};
+
+}  // namespace vrag

@@ -1,0 +1,510 @@
+// Encoder handles: checkpoint repack (fp32 host tensors -> device operands) and the forward schedules
+// (ModernBERT token classifier, BERT MLM + SPLADE pooling, BERT dense pooling).
+//
+// Data layout in HBM (per pass of <= max_tokens tokens, sequences packed back to back, no padding):
+//   x32   [T, 768] fp32   residual stream            h16  [T, 768]  fp16  LayerNorm output = GEMM A operand
+//   qkv16 [T, 2304] fp16  q|k|v (RoPE applied)       o16  [T, 768]  fp16  attention output
+//   w16   [T, 1152|3072] fp16  GeGLU / FFN activation  buf32 [T, 768] fp32 head pre-norm
+// Weights: every Linear as fp16 [N, K] row-major (K-major tensor-core operand), norms / biases / embeddings fp32.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+
+#include "encoder.cuh"
+
+using namespace vrag;
+
+struct vrag_encoder {
+  vrag_ctx* ctx = nullptr;
+  int kind = 0, layers = 0, vocab = 0, vocab_pad = 0, max_tokens = 0, max_seqs = 0, max_pos = 0;
+  int ffn = 0;  // GeGLU width (1152) or FFN width (3072)
+  bool use_reference_gemm = false;
+  std::vector<DevBuf*> owned;
+  // shared
+  float *emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  // ModernBERT
+  struct MLayer { float* attn_g; __half* wqkv; __half* wo; float* mlp_g; __half* wi; __half* wo2; };
+  std::vector<MLayer> ml;
+  float *final_g = nullptr, *head_g = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  __half* head_w = nullptr;
+  float *cos_g = nullptr, *sin_g = nullptr, *cos_l = nullptr, *sin_l = nullptr;
+  // BERT
+  struct BLayer {
+    __half* wqkv; float* bqkv; __half* wo; float* bo; float *g1, *b1; __half* wi; float* bi; __half* wo2; float* bo2;
+    float *g2, *b2;
+  };
+  std::vector<BLayer> bl;
+  float *pos_emb = nullptr, *type_emb = nullptr;
+  __half *mlm_w = nullptr, *dec_w = nullptr;
+  float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
+  // workspace
+  DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
+      pooled;
+
+  ~vrag_encoder() {
+    for (auto* b : owned) { b->release(); delete b; }
+    for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled})
+      b->release();
+  }
+  template <typename T>
+  T* alloc(size_t n) {
+    DevBuf* b = new DevBuf();
+    owned.push_back(b);
+    b->reserve(n * sizeof(T));
+    return b->as<T>();
+  }
+};
+
+namespace {
+
+struct WeightSet {
+  std::map<std::string, const vrag_tensor*> m;
+  WeightSet(const vrag_tensor* t, int n) {
+    for (int i = 0; i < n; ++i) m[t[i].name] = &t[i];
+  }
+  const float* get(const std::string& name, int64_t numel) const {
+    auto it = m.find(name);
+    if (it == m.end()) throw Error(VRAG_ERR_WEIGHTS, "missing tensor '" + name + "'");
+    if (it->second->numel != numel)
+      throw Error(VRAG_ERR_WEIGHTS, "tensor '" + name + "' has " + std::to_string(it->second->numel) +
+                                        " elements, expected " + std::to_string(numel));
+    return it->second->data;
+  }
+};
+
+float* upload_f32(vrag_encoder* e, const float* host, size_t n, size_t n_alloc = 0) {
+  float* d = e->alloc<float>(n_alloc ? n_alloc : n);
+  if (n_alloc > n) VRAG_CUDA(cudaMemsetAsync(d, 0, n_alloc * sizeof(float), e->ctx->stream));
+  VRAG_CUDA(cudaMemcpyAsync(d, host, n * sizeof(float), cudaMemcpyHostToDevice, e->ctx->stream));
+  return d;
+}
+
+// fp32 host [rows, cols] -> fp16 device [rows_alloc, cols] (extra rows zero)
+__half* upload_f16(vrag_encoder* e, DevBuf& staging, const float* host, size_t rows, size_t cols,
+                   size_t rows_alloc = 0) {
+  if (!rows_alloc) rows_alloc = rows;
+  __half* d = e->alloc<__half>(rows_alloc * cols);
+  if (rows_alloc > rows) VRAG_CUDA(cudaMemsetAsync(d, 0, rows_alloc * cols * sizeof(__half), e->ctx->stream));
+  staging.reserve(rows * cols * sizeof(float));
+  VRAG_CUDA(cudaMemcpyAsync(staging.p, host, rows * cols * sizeof(float), cudaMemcpyHostToDevice, e->ctx->stream));
+  launch_f32_to_f16(e->ctx, staging.as<float>(), d, rows * cols);
+  VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // staging is reused by the next tensor
+  return d;
+}
+
+void make_rope(vrag_encoder* e, double theta, int max_pos, float** cos_out, float** sin_out) {
+  // cos/sin of pos * inv_freq[j], inv_freq[j] = theta^(-2j/64), fp32 like modeling_modernbert.py:138-172
+  std::vector<float> c(static_cast<size_t>(max_pos) * 32), s(c.size());
+  for (int j = 0; j < 32; ++j) {
+    const float inv = 1.0f / powf(static_cast<float>(theta), static_cast<float>(2 * j) / 64.0f);
+    for (int p = 0; p < max_pos; ++p) {
+      const float f = static_cast<float>(p) * inv;
+      c[static_cast<size_t>(p) * 32 + j] = static_cast<float>(cos(static_cast<double>(f)));
+      s[static_cast<size_t>(p) * 32 + j] = static_cast<float>(sin(static_cast<double>(f)));
+    }
+  }
+  *cos_out = upload_f32(e, c.data(), c.size());
+  *sin_out = upload_f32(e, s.data(), s.size());
+  VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
+}
+
+void build_modernbert(vrag_encoder* e, const WeightSet& w) {
+  const int H = HIDDEN, I = 1152;
+  e->ffn = I;
+  e->max_pos = 8192;
+  DevBuf staging;
+  e->emb = upload_f32(e, w.get("model.embeddings.tok_embeddings.weight", (int64_t)e->vocab * H), (size_t)e->vocab * H);
+  e->emb_g = upload_f32(e, w.get("model.embeddings.norm.weight", H), H);
+  std::vector<float> wi_perm(static_cast<size_t>(2 * I) * H);
+  for (int i = 0; i < e->layers; ++i) {
+    const std::string p = "model.layers." + std::to_string(i) + ".";
+    vrag_encoder::MLayer L{};
+    L.attn_g = i > 0 ? upload_f32(e, w.get(p + "attn_norm.weight", H), H) : nullptr;
+    L.wqkv = upload_f16(e, staging, w.get(p + "attn.Wqkv.weight", 3LL * H * H), 3 * H, H);
+    L.wo = upload_f16(e, staging, w.get(p + "attn.Wo.weight", (int64_t)H * H), H, H);
+    L.mlp_g = upload_f32(e, w.get(p + "mlp_norm.weight", H), H);
+    // GeGLU: Wi = [input rows 0..I) | gate rows I..2I).  Interleave per 128 so one 256-wide GEMM tile holds
+    // input[128t..128t+128) and gate[128t..128t+128) -> act(input)*gate is tile-local (EPI_GEGLU).
+    const float* wi = w.get(p + "mlp.Wi.weight", 2LL * I * H);
+    for (int t = 0; t < I / 128; ++t) {
+      memcpy(&wi_perm[static_cast<size_t>(t * 256) * H], wi + static_cast<size_t>(t * 128) * H, sizeof(float) * 128 * H);
+      memcpy(&wi_perm[static_cast<size_t>(t * 256 + 128) * H], wi + static_cast<size_t>(I + t * 128) * H,
+             sizeof(float) * 128 * H);
+    }
+    L.wi = upload_f16(e, staging, wi_perm.data(), 2 * I, H);
+    L.wo2 = upload_f16(e, staging, w.get(p + "mlp.Wo.weight", (int64_t)H * I), H, I);
+    e->ml.push_back(L);
+  }
+  e->final_g = upload_f32(e, w.get("model.final_norm.weight", H), H);
+  e->head_w = upload_f16(e, staging, w.get("head.dense.weight", (int64_t)H * H), H, H);
+  e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
+  e->cls_w = upload_f32(e, w.get("classifier.weight", 2LL * H), 2 * H);
+  e->cls_b = upload_f32(e, w.get("classifier.bias", 2), 2);
+  make_rope(e, 160000.0, e->max_pos, &e->cos_g, &e->sin_g);
+  make_rope(e, 10000.0, e->max_pos, &e->cos_l, &e->sin_l);
+  staging.release();
+}
+
+void build_bert(vrag_encoder* e, const WeightSet& w) {
+  const int H = HIDDEN, I = 3072;
+  e->ffn = I;
+  e->max_pos = 512;
+  DevBuf staging;
+  const std::string em = "bert.embeddings.";
+  const float* wemb = w.get(em + "word_embeddings.weight", (int64_t)e->vocab * H);
+  e->emb = upload_f32(e, wemb, (size_t)e->vocab * H);
+  e->pos_emb = upload_f32(e, w.get(em + "position_embeddings.weight", (int64_t)e->max_pos * H), (size_t)e->max_pos * H);
+  e->type_emb = upload_f32(e, w.get(em + "token_type_embeddings.weight", 2LL * H), 2 * H);
+  e->emb_g = upload_f32(e, w.get(em + "LayerNorm.weight", H), H);
+  e->emb_b = upload_f32(e, w.get(em + "LayerNorm.bias", H), H);
+  std::vector<float> cat(static_cast<size_t>(3 * H) * H), bcat(3 * H);
+  for (int i = 0; i < e->layers; ++i) {
+    const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
+    vrag_encoder::BLayer L{};
+    const char* nm[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      memcpy(&cat[static_cast<size_t>(j) * H * H], w.get(p + "attention.self." + nm[j] + ".weight", (int64_t)H * H),
+             sizeof(float) * H * H);
+      memcpy(&bcat[static_cast<size_t>(j) * H], w.get(p + "attention.self." + nm[j] + ".bias", H), sizeof(float) * H);
+    }
+    L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H);
+    L.bqkv = upload_f32(e, bcat.data(), 3 * H);
+    VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // bcat reused next layer
+    L.wo = upload_f16(e, staging, w.get(p + "attention.output.dense.weight", (int64_t)H * H), H, H);
+    L.bo = upload_f32(e, w.get(p + "attention.output.dense.bias", H), H);
+    L.g1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.weight", H), H);
+    L.b1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.bias", H), H);
+    L.wi = upload_f16(e, staging, w.get(p + "intermediate.dense.weight", (int64_t)I * H), I, H);
+    L.bi = upload_f32(e, w.get(p + "intermediate.dense.bias", I), I);
+    L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I);
+    L.bo2 = upload_f32(e, w.get(p + "output.dense.bias", H), H);
+    L.g2 = upload_f32(e, w.get(p + "output.LayerNorm.weight", H), H);
+    L.b2 = upload_f32(e, w.get(p + "output.LayerNorm.bias", H), H);
+    e->bl.push_back(L);
+  }
+  if (e->kind == VRAG_ENC_BERT_MLM) {
+    const std::string c = "cls.predictions.";
+    e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H);
+    e->mlm_b = upload_f32(e, w.get(c + "transform.dense.bias", H), H);
+    e->mlm_g = upload_f32(e, w.get(c + "transform.LayerNorm.weight", H), H);
+    e->mlm_beta = upload_f32(e, w.get(c + "transform.LayerNorm.bias", H), H);
+    // decoder is tied to the word embeddings (modeling_bert.py:471-511); pad the vocabulary to a tile multiple
+    e->dec_w = upload_f16(e, staging, wemb, e->vocab, H, e->vocab_pad);
+    e->dec_b = upload_f32(e, w.get(c + "bias", e->vocab), e->vocab, e->vocab_pad);
+  }
+  VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  staging.release();
+}
+
+void reserve_workspace(vrag_encoder* e) {
+  const size_t T = e->max_tokens, H = HIDDEN;
+  e->ids.reserve(T * 4);
+  e->pos.reserve(T * 4);
+  e->seqrow.reserve(T * 4);
+  e->cu.reserve((static_cast<size_t>(e->max_seqs) + 1) * 4);
+  e->x32.reserve(T * H * 4);
+  e->h16.reserve(T * H * 2);
+  e->qkv16.reserve(T * 3 * H * 2);
+  e->o16.reserve(T * H * 2);
+  e->w16.reserve(T * e->ffn * 2);
+  e->buf32.reserve(T * H * 4);
+  e->probs.reserve(T * 4);
+  e->logits.reserve(T * 8);
+}
+
+struct Pass { int s0, s1, t0, t1, max_len; };
+
+std::vector<Pass> plan_passes(const int32_t* cu, int nseq, int max_tokens, int max_seqs) {
+  std::vector<Pass> out;
+  int s = 0;
+  while (s < nseq) {
+    int e = s, ml = 0;
+    while (e < nseq && cu[e + 1] - cu[s] <= max_tokens && e - s < max_seqs) {
+      ml = std::max(ml, cu[e + 1] - cu[e]);
+      ++e;
+    }
+    VRAG_CHECK(e > s, VRAG_ERR_ARG, "a sequence is longer than the encoder's max_tokens");
+    out.push_back({s, e, cu[s], cu[e], ml});
+    s = e;
+  }
+  return out;
+}
+
+// Stage one pass' ids + cu_seqlens on the device, build pos / seq_of_row.
+void stage_pass(vrag_encoder* e, const Pass& ps, const int32_t* ids, const int32_t* cu, int on_device) {
+  vrag_ctx* ctx = e->ctx;
+  const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0;
+  VRAG_CUDA(cudaMemcpyAsync(e->ids.p, ids + ps.t0, static_cast<size_t>(T) * 4,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  int32_t* cu_h = static_cast<int32_t*>(ctx->pinned_reserve((static_cast<size_t>(ns) + 1) * 4));
+  for (int i = 0; i <= ns; ++i) cu_h[i] = cu[ps.s0 + i] - ps.t0;
+  VRAG_CUDA(cudaMemcpyAsync(e->cu.p, cu_h, (static_cast<size_t>(ns) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VRAG_CUDA(cudaStreamSynchronize(ctx->stream));  // cu_h (pinned scratch) is reused by the next pass
+  launch_token_meta(ctx, e->cu.as<int32_t>(), ns, T, e->pos.as<int32_t>(), e->seqrow.as<int32_t>());
+}
+
+void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
+  vrag_ctx* ctx = e->ctx;
+  const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0, H = HIDDEN, I = e->ffn;
+  const int ref = e->use_reference_gemm ? 1 : 0;
+  float* x32 = e->x32.as<float>();
+  __half *h16 = e->h16.as<__half>(), *qkv = e->qkv16.as<__half>(), *o16 = e->o16.as<__half>(), *g16 = e->w16.as<__half>();
+  auto dump = [&](int slot) {
+    if (hidden_dbg_host)
+      VRAG_CUDA(cudaMemcpyAsync(hidden_dbg_host + static_cast<size_t>(slot) * T * H, x32,
+                                static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  };
+  launch_embed_ln(ctx, e->ids.as<int32_t>(), T, e->vocab, e->emb, e->emb_g, 1e-5f, x32, h16);
+  dump(0);
+  for (int i = 0; i < e->layers; ++i) {
+    const auto& L = e->ml[i];
+    const bool global = (i % 3) == 0;
+    if (i > 0) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false);
+    GemmEpiParams p;
+    p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.hidden = H; p.pos = e->pos.as<int32_t>();
+    p.rope_cos = global ? e->cos_g : e->cos_l;
+    p.rope_sin = global ? e->sin_g : e->sin_l;
+    launch_gemm(ctx, EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
+    launch_attention(ctx, qkv, o16, e->cu.as<int32_t>(), ns, ps.max_len, 12, H, global ? -1 : 64);
+    GemmEpiParams r;
+    r.M = T; r.out32 = x32; r.ld32 = H;
+    launch_gemm(ctx, EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
+    launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
+    GemmEpiParams g;
+    g.M = T; g.out16 = g16; g.ld16 = I;
+    launch_gemm(ctx, EPI_GEGLU, h16, L.wi, T, 2 * I, H, g, ref);
+    launch_gemm(ctx, EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
+    dump(i + 1);
+  }
+  launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false);
+  GemmEpiParams hd;
+  hd.M = T; hd.out32 = e->buf32.as<float>(); hd.ld32 = H;
+  launch_gemm(ctx, EPI_GELU_F32, h16, e->head_w, T, H, H, hd, ref);
+  launch_head_final(ctx, e->buf32.as<float>(), T, e->head_g, 1e-5f, e->cls_w, e->cls_b, e->logits.as<float>(),
+                    e->probs.as<float>());
+}
+
+// BERT encoder stack: leaves the post-LN final hidden states in x32 (fp32) and h16 (fp16).
+void bert_stack(vrag_encoder* e, const Pass& ps) {
+  vrag_ctx* ctx = e->ctx;
+  const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0, H = HIDDEN, I = e->ffn;
+  const int ref = e->use_reference_gemm ? 1 : 0;
+  float* x32 = e->x32.as<float>();
+  __half *h16 = e->h16.as<__half>(), *qkv = e->qkv16.as<__half>(), *o16 = e->o16.as<__half>(), *f16 = e->w16.as<__half>();
+  launch_bert_embed_ln(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
+                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16);
+  for (int i = 0; i < e->layers; ++i) {
+    const auto& L = e->bl[i];
+    GemmEpiParams p;
+    p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.bias = L.bqkv;
+    launch_gemm(ctx, EPI_BIAS_F16, h16, L.wqkv, T, 3 * H, H, p, ref);
+    launch_attention(ctx, qkv, o16, e->cu.as<int32_t>(), ns, ps.max_len, 12, H, -1);
+    GemmEpiParams r;
+    r.M = T; r.out32 = x32; r.ld32 = H; r.bias = L.bo;
+    launch_gemm(ctx, EPI_BIAS_RESID_F32, o16, L.wo, T, H, H, r, ref);
+    launch_layernorm(ctx, x32, T, L.g1, L.b1, 1e-12f, h16, true);
+    GemmEpiParams f;
+    f.M = T; f.out16 = f16; f.ld16 = I; f.bias = L.bi;
+    launch_gemm(ctx, EPI_BIAS_GELU_F16, h16, L.wi, T, I, H, f, ref);
+    GemmEpiParams r2;
+    r2.M = T; r2.out32 = x32; r2.ld32 = H; r2.bias = L.bo2;
+    launch_gemm(ctx, EPI_BIAS_RESID_F32, f16, L.wo2, T, H, I, r2, ref);
+    launch_layernorm(ctx, x32, T, L.g2, L.b2, 1e-12f, h16, true);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define VRAG_API_BEGIN(ctxp)                 \
+  vrag_ctx* _ctx = (ctxp);                   \
+  std::lock_guard<std::mutex> _lk(_ctx->mu); \
+  try {                                      \
+    VRAG_CUDA(cudaSetDevice(_ctx->device));
+#define VRAG_API_END()                                    \
+    return VRAG_OK;                                       \
+  } catch (const vrag::Error& e) {                        \
+    _ctx->last_error = e.what();                          \
+    return e.code;                                        \
+  } catch (const std::exception& e) {                     \
+    _ctx->last_error = e.what();                          \
+    return VRAG_ERR_INTERNAL;                             \
+  }
+
+extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
+                                   const vrag_tensor* tensors, int num_tensors, vrag_encoder** out) {
+  if (!ctx || !out) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(ctx)
+  VRAG_CHECK(kind >= 0 && kind <= 2 && num_layers > 0 && vocab_size > 0 && max_tokens >= 128, VRAG_ERR_ARG,
+             "encoder_create: bad kind / num_layers / vocab_size / max_tokens");
+  std::unique_ptr<vrag_encoder> e(new vrag_encoder());
+  e->ctx = ctx;
+  e->kind = kind;
+  e->layers = num_layers;
+  e->vocab = vocab_size;
+  e->vocab_pad = (vocab_size + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+  e->max_tokens = max_tokens;
+  e->max_seqs = std::max(64, max_tokens / 8);
+  const char* dbg = getenv("VRAG_GEMM_REFERENCE");
+  e->use_reference_gemm = dbg && dbg[0] == '1';
+  WeightSet w(tensors, num_tensors);
+  if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
+  else build_bert(e.get(), w);
+  reserve_workspace(e.get());
+  VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = e.release();
+  VRAG_API_END()
+}
+
+extern "C" void vrag_encoder_destroy(vrag_encoder* enc) {
+  if (!enc) return;
+  cudaSetDevice(enc->ctx->device);
+  cudaStreamSynchronize(enc->ctx->stream);
+  delete enc;
+}
+
+static int span_forward_impl(vrag_encoder* enc, const int32_t* ids, const int32_t* cu, int nseq, float* probs_out,
+                             float* logits_out, int on_device, float* hidden_dbg) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_MODERNBERT_TOKCLS, VRAG_ERR_ARG, "span_forward needs a MODERNBERT_TOKCLS encoder");
+  VRAG_CHECK(ids && cu && probs_out && nseq >= 0, VRAG_ERR_ARG, "span_forward: null argument");
+  if (nseq == 0) return VRAG_OK;
+  for (int i = 0; i < nseq; ++i) {
+    VRAG_CHECK(cu[i + 1] > cu[i], VRAG_ERR_ARG, "span_forward: empty sequence");
+    VRAG_CHECK(cu[i + 1] - cu[i] <= enc->max_pos, VRAG_ERR_ARG, "span_forward: sequence longer than 8192 tokens");
+  }
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, enc->max_seqs);
+  VRAG_CHECK(!hidden_dbg || passes.size() == 1, VRAG_ERR_ARG, "debug hidden dump needs a single pass");
+  const cudaMemcpyKind back = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (const Pass& ps : passes) {
+    stage_pass(enc, ps, ids, cu, on_device);
+    modernbert_pass(enc, ps, hidden_dbg);
+    const size_t T = ps.t1 - ps.t0;
+    VRAG_CUDA(cudaMemcpyAsync(probs_out + ps.t0, enc->probs.p, T * 4, back, _ctx->stream));
+    if (logits_out) VRAG_CUDA(cudaMemcpyAsync(logits_out + 2 * static_cast<size_t>(ps.t0), enc->logits.p, T * 8, back, _ctx->stream));
+    if (!on_device) VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  }
+  VRAG_API_END()
+}
+
+extern "C" int vrag_span_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,
+                                 float* probs_out, float* logits_out, int on_device) {
+  return span_forward_impl(enc, ids, cu_seqlens, nseq, probs_out, logits_out, on_device, nullptr);
+}
+
+// Debug hook (tests only): host ids, also returns the fp32 residual stream after the embedding and after each
+// layer, hidden_out [layers + 1, T, 768] host.
+extern "C" int vrag_debug_span_hidden(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,
+                                      float* probs_out, float* logits_out, float* hidden_out) {
+  return span_forward_impl(enc, ids, cu_seqlens, nseq, probs_out, logits_out, 0, hidden_out);
+}
+
+extern "C" int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu, int nseq, float min_abs,
+                                   int64_t* indptr_out, int32_t* indices_out, float* values_out, int64_t cap,
+                                   int64_t* nnz_out, float* dense_out, int on_device) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_BERT_MLM, VRAG_ERR_ARG, "splade_forward needs a BERT_MLM encoder");
+  VRAG_CHECK(ids && cu && nseq >= 0 && nnz_out, VRAG_ERR_ARG, "splade_forward: null argument");
+  const bool want_csr = indptr_out != nullptr;
+  VRAG_CHECK(!want_csr || (indices_out && values_out) || cap == 0, VRAG_ERR_ARG, "splade_forward: null CSR buffers");
+  *nnz_out = 0;
+  if (want_csr) indptr_out[0] = 0;
+  if (nseq == 0) return VRAG_OK;
+  for (int i = 0; i < nseq; ++i) {
+    VRAG_CHECK(cu[i + 1] > cu[i], VRAG_ERR_ARG, "splade_forward: empty sequence");
+    VRAG_CHECK(cu[i + 1] - cu[i] <= enc->max_pos, VRAG_ERR_ARG, "splade_forward: sequence longer than 512 tokens");
+  }
+  const int H = HIDDEN, V = enc->vocab, VP = enc->vocab_pad;
+  const int ref = enc->use_reference_gemm ? 1 : 0;
+  // the dense pooled buffer is [seqs_per_pass, VP] fp32: bound sequences per pass to 512 (60 MB)
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, std::min(enc->max_seqs, 512));
+  int64_t nnz_total = 0;
+  bool overflow = false;
+  for (const Pass& ps : passes) {
+    const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0;
+    stage_pass(enc, ps, ids, cu, on_device);
+    bert_stack(enc, ps);
+    GemmEpiParams t;
+    t.M = T; t.out32 = enc->buf32.as<float>(); t.ld32 = H; t.bias = enc->mlm_b;
+    launch_gemm(_ctx, EPI_BIAS_GELU_F32, enc->h16.as<__half>(), enc->mlm_w, T, H, H, t, ref);
+    launch_layernorm(_ctx, enc->buf32.as<float>(), T, enc->mlm_g, enc->mlm_beta, 1e-12f, enc->h16.as<__half>(), false);
+    enc->splade.reserve(static_cast<size_t>(ns) * VP * 4);
+    VRAG_CUDA(cudaMemsetAsync(enc->splade.p, 0, static_cast<size_t>(ns) * VP * 4, _ctx->stream));
+    GemmEpiParams sp;
+    sp.M = T; sp.bias = enc->dec_b; sp.seq_of_row = enc->seqrow.as<int32_t>(); sp.splade_out = enc->splade.as<float>();
+    sp.splade_ld = VP; sp.n_valid = V;
+    launch_gemm(_ctx, EPI_SPLADE, enc->h16.as<__half>(), enc->dec_w, T, VP, H, sp, ref);
+    if (dense_out)
+      VRAG_CUDA(cudaMemcpy2DAsync(dense_out + static_cast<size_t>(ps.s0) * V, static_cast<size_t>(V) * 4, enc->splade.p,
+                                  static_cast<size_t>(VP) * 4, static_cast<size_t>(V) * 4, ns,
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, _ctx->stream));
+    if (want_csr) {
+      enc->counts.reserve(static_cast<size_t>(ns) * 4);
+      enc->indptr.reserve((static_cast<size_t>(ns) + 1) * 8);
+      launch_splade_count(_ctx, enc->splade.as<float>(), ns, VP, V, min_abs, enc->counts.as<int32_t>());
+      std::vector<int32_t> cnt(ns);
+      VRAG_CUDA(cudaMemcpyAsync(cnt.data(), enc->counts.p, static_cast<size_t>(ns) * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+      VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+      std::vector<int64_t> ip(ns + 1);
+      ip[0] = 0;
+      for (int i = 0; i < ns; ++i) ip[i + 1] = ip[i] + cnt[i];
+      for (int i = 0; i < ns; ++i) indptr_out[ps.s0 + i + 1] = nnz_total + ip[i + 1];
+      const int64_t n_here = ip[ns];
+      if (!overflow && nnz_total + n_here <= cap) {
+        if (n_here > 0) {
+          enc->sp_idx.reserve(static_cast<size_t>(n_here) * 4);
+          enc->sp_val.reserve(static_cast<size_t>(n_here) * 4);
+          VRAG_CUDA(cudaMemcpyAsync(enc->indptr.p, ip.data(), (static_cast<size_t>(ns) + 1) * 8, cudaMemcpyHostToDevice, _ctx->stream));
+          launch_splade_fill(_ctx, enc->splade.as<float>(), ns, VP, V, min_abs, enc->indptr.as<int64_t>(),
+                             enc->sp_idx.as<int32_t>(), enc->sp_val.as<float>());
+          VRAG_CUDA(cudaMemcpyAsync(indices_out + nnz_total, enc->sp_idx.p, static_cast<size_t>(n_here) * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+          VRAG_CUDA(cudaMemcpyAsync(values_out + nnz_total, enc->sp_val.p, static_cast<size_t>(n_here) * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+        }
+      } else {
+        overflow = true;
+      }
+      nnz_total += n_here;
+    }
+    VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  }
+  *nnz_out = nnz_total;
+  if (overflow) throw Error(VRAG_ERR_CAPACITY, "splade_forward: CSR capacity too small; see *nnz_out");
+  VRAG_API_END()
+}
+
+extern "C" int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu, int nseq, int pooling,
+                                  int normalize, float* out, int on_device) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_BERT_DENSE || enc->kind == VRAG_ENC_BERT_MLM, VRAG_ERR_ARG,
+             "dense_forward needs a BERT encoder");
+  VRAG_CHECK(ids && cu && out && nseq >= 0, VRAG_ERR_ARG, "dense_forward: null argument");
+  VRAG_CHECK(pooling == VRAG_POOL_MEAN || pooling == VRAG_POOL_CLS, VRAG_ERR_ARG, "dense_forward: bad pooling");
+  if (nseq == 0) return VRAG_OK;
+  for (int i = 0; i < nseq; ++i) {
+    VRAG_CHECK(cu[i + 1] > cu[i], VRAG_ERR_ARG, "dense_forward: empty sequence");
+    VRAG_CHECK(cu[i + 1] - cu[i] <= enc->max_pos, VRAG_ERR_ARG, "dense_forward: sequence longer than 512 tokens");
+  }
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, enc->max_seqs);
+  for (const Pass& ps : passes) {
+    const int ns = ps.s1 - ps.s0;
+    stage_pass(enc, ps, ids, cu, on_device);
+    bert_stack(enc, ps);
+    enc->pooled.reserve(static_cast<size_t>(ns) * HIDDEN * 4);
+    launch_pool(_ctx, enc->x32.as<float>(), enc->cu.as<int32_t>(), ns, pooling, normalize, enc->pooled.as<float>());
+    VRAG_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(ps.s0) * HIDDEN, enc->pooled.p, static_cast<size_t>(ns) * HIDDEN * 4,
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, _ctx->stream));
+    VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  }
+  VRAG_API_END()
+}

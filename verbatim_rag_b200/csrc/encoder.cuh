@@ -1,0 +1,37 @@
+// Internal kernels + launchers of the encoder forward passes (ModernBERT token classifier, BERT MLM/SPLADE, BERT dense).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace vrag {
+
+constexpr int HIDDEN = 768;  // all supported encoders are *-base: H = 768, 12 heads x 64
+
+// attention.cu
+void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev, int nseq,
+                      int max_len, int heads, int hidden, int window);
+
+// rowops.cu  (one warp per token row, H = 768)
+void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, int total, int32_t* pos,
+                       int32_t* seq_of_row);
+void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
+                     float eps, float* x32, __half* h16);
+void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
+                          const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
+                          const float* beta, float eps, float* x32, __half* h16);
+// h16 = LN(x32) * gamma (+ beta); if write_back, x32 is overwritten with the normalised row too (post-LN residual).
+void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps,
+                      __half* h16, bool write_back);
+// ModernBERT head tail: LN(buf32) * gamma -> classifier (2 x 768) + bias -> logits, P(class 1).
+void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
+                       const float* cls_b, float* logits /*nullable*/, float* probs);
+// SPLADE CSR extraction from the dense [nseq, ld] buffer.
+void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
+                         int32_t* counts);
+void launch_splade_fill(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
+                        const int64_t* indptr_dev, int32_t* indices, float* values);
+void launch_pool(vrag_ctx* ctx, const float* x32, const int32_t* cu_seqlens_dev, int nseq, int pooling,
+                 int normalize, float* out);
+void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n);
+
+}  // namespace vrag

@@ -1,0 +1,367 @@
+// tcgen05 GEMM for sm_100a: persistent, warp-specialised.
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes into a 4-stage smem ring)
+//   warp 1      : MMA issuer     (one lane issues tcgen05.mma 128x256x16, fp32 accumulators in TMEM)
+//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> fused tail -> global)
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Tiles are walked n-fastest so concurrently running CTAs share the same A rows (L2 reuse); W is L2 resident.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace vrag {
+
+namespace {
+
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+    d[i] = u;
+  }
+}
+__device__ __forceinline__ void store_float32(float* dst, const float (&v)[32]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// Accumulator source for one thread's row: chunk c = columns [32c, 32c+32) of the 256-wide tile.
+struct TmemLoader {
+  uint32_t taddr;  // lane quarter + accumulator stage column base
+  __device__ __forceinline__ void load(int chunk, float (&v)[32]) const {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + chunk * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  }
+};
+struct ReferenceLoader {  // SIMT dot products (debug / self test)
+  const __half* a_row;    // nullptr for rows >= M
+  const __half* w_tile;   // W + n_tile*256*K
+  int K;
+  __device__ __forceinline__ void load(int chunk, float (&v)[32]) const {
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      float acc = 0.f;
+      if (a_row) {
+        const __half* w = w_tile + static_cast<size_t>(chunk * 32 + j) * K;
+        for (int k = 0; k < K; ++k) acc = fmaf(__half2float(a_row[k]), __half2float(w[k]), acc);
+      }
+      v[j] = acc;
+    }
+  }
+};
+
+// The fused tail for one thread == one output row of one 128x256 tile.  All 32 lanes of a warp call this together.
+template <int EPI, typename Loader>
+__device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, int n_tile, const Loader& ld) {
+  const bool valid = row < p.M;
+  const int col0 = n_tile * BN;
+  float v[32];
+  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      ld.load(c, v);
+      if constexpr (EPI != EPI_F16) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 b = __ldg(b4 + i);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (valid) store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32, v);
+    }
+  } else if constexpr (EPI == EPI_F32 || EPI == EPI_GELU_F32 || EPI == EPI_BIAS_GELU_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      ld.load(c, v);
+      if constexpr (EPI == EPI_BIAS_GELU_F32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col0 + c * 32 + i);
+      }
+      if constexpr (EPI != EPI_F32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (valid) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32, v);
+    }
+  } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      ld.load(c, v);
+      if (valid) {
+        float4* x4 = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 x = x4[i];
+          x.x += v[4 * i]; x.y += v[4 * i + 1]; x.z += v[4 * i + 2]; x.w += v[4 * i + 3];
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32) + i);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          x4[i] = x;
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_ROPE_QKV) {
+    // 4 heads of 64 per tile.  x1 = dims [0,32), x2 = dims [32,64): out1 = x1*cos - x2*sin, out2 = x2*cos + x1*sin
+    // (rotate_half convention, fp32, modeling_modernbert.py:197-228).
+    float w2[32];
+    const int pos = valid ? __ldg(p.pos + row) : 0;
+    const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<size_t>(pos) * 32);
+    const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<size_t>(pos) * 32);
+#pragma unroll 1
+    for (int h = 0; h < BN / 64; ++h) {
+      ld.load(2 * h, v);
+      ld.load(2 * h + 1, w2);
+      const int gcol = col0 + h * 64;
+      if (gcol < 2 * p.hidden) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 c = __ldg(cs4 + i), s = __ldg(sn4 + i);
+          float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x1 = v[4 * i + e], x2 = w2[4 * i + e];
+            v[4 * i + e] = x1 * cc[e] - x2 * ss[e];
+            w2[4 * i + e] = x2 * cc[e] + x1 * ss[e];
+          }
+        }
+      }
+      if (valid) {
+        __half* o = p.out16 + static_cast<size_t>(row) * p.ld16 + gcol;
+        store_half32(o, v);
+        store_half32(o + 32, w2);
+      }
+    }
+  } else if constexpr (EPI == EPI_GEGLU) {
+    float g[32];
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      ld.load(c, v);
+      ld.load(4 + c, g);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]) * g[i];
+      if (valid) store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + n_tile * 128 + c * 32, v);
+    }
+  } else if constexpr (EPI == EPI_SPLADE) {
+    // log1p(relu(x + b)) is >= 0, so its float bits order like ints: max-pool with integer max.
+    const int seq = valid ? __ldg(p.seq_of_row + row) : -1;
+    const int seq0 = __shfl_sync(0xffffffffu, seq, 0);
+    const bool uniform = __all_sync(0xffffffffu, seq == seq0) && seq0 >= 0;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      ld.load(c, v);
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.n_valid) continue;  // warp-uniform
+      int mine = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = v[i] + __ldg(p.bias + cbase + i);
+        float a = x > 0.f ? log1pf(x) : 0.f;
+        int bits = __float_as_int(a);
+        if (uniform) {
+          int m = __reduce_max_sync(0xffffffffu, bits);
+          if (lane == i) mine = m;
+        } else if (valid && bits > 0 && cbase + i < p.n_valid) {
+          atomicMax(reinterpret_cast<int*>(p.splade_out + static_cast<size_t>(seq) * p.splade_ld + cbase + i), bits);
+        }
+      }
+      if (uniform && mine > 0 && cbase + lane < p.n_valid)
+        atomicMax(reinterpret_cast<int*>(p.splade_out + static_cast<size_t>(seq0) * p.splade_ld + cbase + lane), mine);
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m_tiles,
+                    int n_tiles, int k_blocks, GemmEpiParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tfull = bar_empty + STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s, 1);
+      mbar_init(bar_empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + a, 1);
+      mbar_init(bar_tempty + a, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_idx = tile / n_tiles, n_idx = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(bar_empty + stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + stage, STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, bar_full + stage, kb * BK, m_idx * BM);
+          tma_load_2d(sa + A_BYTES, &tmB, bar_full + stage, kb * BK, n_idx * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(bar_full + stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + stage);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + acc);      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_idx = tile / n_tiles, n_idx = tile % n_tiles;
+      mbar_wait(bar_tfull + acc, acc_phase);
+      tc_fence_after();
+      TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
+      epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(128)
+gemm_reference_kernel(const __half* __restrict__ A, const __half* __restrict__ W, int K, int n_tiles,
+                      GemmEpiParams p) {
+  const int m_idx = blockIdx.x / n_tiles, n_idx = blockIdx.x % n_tiles;
+  const int row = m_idx * BM + threadIdx.x;
+  ReferenceLoader ld{row < p.M ? A + static_cast<size_t>(row) * K : nullptr,
+                     W + static_cast<size_t>(n_idx) * BN * K, K};
+  epilogue_row<EPI>(p, row, n_idx, ld);
+}
+
+template <int EPI>
+void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int K, const GemmEpiParams& p,
+              int use_reference) {
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
+  if (use_reference) {
+    gemm_reference_kernel<EPI><<<m_tiles * n_tiles, 128, 0, ctx->stream>>>(A, W, K, n_tiles, p);
+  } else {
+    CUtensorMap tmA = make_tmap_2d(ctx, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, K, BM, BK);
+    CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN, BK);
+    static bool attr_set[16] = {};
+    if (!attr_set[EPI]) {
+      VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SMEM_BYTES));
+      attr_set[EPI] = true;
+    }
+    const int total = m_tiles * n_tiles;
+    const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+    gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, m_tiles, n_tiles, k_blocks, p);
+  }
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+}  // namespace
+
+void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M, int N, int K,
+                 const GemmEpiParams& p, int use_reference) {
+  VRAG_CHECK(M > 0 && N % BN == 0 && K % BK == 0, VRAG_ERR_ARG, "gemm: need M > 0, N % 256 == 0, K % 64 == 0");
+  switch (epi) {
+#define VRAG_CASE(E) case E: launch_t<E>(ctx, A, W, M, N, K, p, use_reference); break;
+    VRAG_CASE(EPI_F16)
+    VRAG_CASE(EPI_ROPE_QKV)
+    VRAG_CASE(EPI_RESID_F32)
+    VRAG_CASE(EPI_GEGLU)
+    VRAG_CASE(EPI_BIAS_F16)
+    VRAG_CASE(EPI_BIAS_GELU_F16)
+    VRAG_CASE(EPI_BIAS_RESID_F32)
+    VRAG_CASE(EPI_SPLADE)
+    VRAG_CASE(EPI_GELU_F32)
+    VRAG_CASE(EPI_BIAS_GELU_F32)
+    VRAG_CASE(EPI_F32)
+#undef VRAG_CASE
+    default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
+  }
+}
+
+}  // namespace vrag

@@ -1,0 +1,48 @@
+// Tensor-core GEMM of the encoder blocks:  C[M,N] = A[M,K] * W[N,K]^T, fp16 operands, fp32 accumulate in TMEM,
+// with the layer's element-wise tail fused into the epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace vrag {
+
+enum GemmEpi : int {
+  EPI_F16 = 0,            // out16 = acc
+  EPI_ROPE_QKV = 1,       // ModernBERT Wqkv: rotate q/k heads by the token position, v as is -> out16 [M, 3*H]
+  EPI_RESID_F32 = 2,      // out32 += acc                       (Wo / mlp.Wo onto the fp32 residual stream)
+  EPI_GEGLU = 3,          // out16[:, 128t+j] = gelu(acc[j]) * acc[128+j]   (Wi rows interleaved per 128)
+  EPI_BIAS_F16 = 4,       // out16 = acc + bias                 (BERT fused q|k|v)
+  EPI_BIAS_GELU_F16 = 5,  // out16 = gelu(acc + bias)           (BERT intermediate)
+  EPI_BIAS_RESID_F32 = 6, // out32 += acc + bias                (BERT attention.output / output dense)
+  EPI_SPLADE = 7,         // splade[seq(row), col] = max(., log1p(relu(acc + bias)))   (MLM decoder, never stores logits)
+  EPI_GELU_F32 = 8,       // out32 = gelu(acc)                  (ModernBERT head.dense)
+  EPI_BIAS_GELU_F32 = 9,  // out32 = gelu(acc + bias)           (BERT MLM transform.dense)
+  EPI_F32 = 10,           // out32 = acc                        (self test)
+};
+
+struct GemmEpiParams {
+  __half* out16 = nullptr;
+  int ld16 = 0;
+  float* out32 = nullptr;
+  int ld32 = 0;
+  const float* bias = nullptr;
+  const int32_t* pos = nullptr;       // [M] position of each token inside its sequence
+  const float* rope_cos = nullptr;    // [max_pos, 32]
+  const float* rope_sin = nullptr;
+  int hidden = 768;                   // H: q = cols [0,H), k = [H,2H), v = [2H,3H)
+  const int32_t* seq_of_row = nullptr;  // [M] sequence index of each token (SPLADE pooling)
+  float* splade_out = nullptr;        // [nseq, splade_ld], zero-initialised
+  int splade_ld = 0;
+  int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail)
+  int M = 0;                          // valid rows
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BK = 64;
+
+// A: [M, K] fp16 row-major (lda = K).  W: [N, K] fp16 row-major.  N % 256 == 0, K % 64 == 0.
+// use_reference != 0 runs the SIMT reference kernel with the same epilogue (debug / self test only).
+void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M, int N, int K,
+                 const GemmEpiParams& p, int use_reference);
+
+}  // namespace vrag

@@ -1,0 +1,307 @@
+// Row-wise (per token) kernels of the encoders: embedding gather + LayerNorm, LayerNorm, classifier tail,
+// SPLADE CSR extraction, sentence pooling.  One warp per 768-wide row, 128-bit loads, fp32 statistics.
+// These are HBM-streaming kernels: ~3 KB read + 1.5-4.5 KB written per token.
+#include "encoder.cuh"
+#include "ptx.cuh"
+
+namespace vrag {
+
+namespace {
+
+constexpr int H = HIDDEN;
+constexpr int VEC = H / 128;  // float4 per lane = 6
+constexpr int ROWS_PER_BLOCK = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Normalise the row held as v[VEC] float4 per lane (element index = (i*32 + lane)*4 + e).
+__device__ __forceinline__ void ln_row(float4 (&v)[VEC], const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    v[i].x *= rstd * g.x; v[i].y *= rstd * g.y; v[i].z *= rstd * g.z; v[i].w *= rstd * g.w;
+    if (beta) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+      v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row, __half* h16_row, int lane) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (x32_row) reinterpret_cast<float4*>(x32_row)[i * 32 + lane] = v[i];
+    if (h16_row) {
+      uint2 u;
+      u.x = pack_half2(v[i].x, v[i].y);
+      u.y = pack_half2(v[i].z, v[i].w);
+      reinterpret_cast<uint2*>(h16_row)[i * 32 + lane] = u;
+    }
+  }
+}
+
+__global__ void token_meta_kernel(const int32_t* __restrict__ cu, int nseq, int32_t* __restrict__ pos,
+                                  int32_t* __restrict__ seq_of_row) {
+  const int s = blockIdx.x;
+  if (s >= nseq) return;
+  const int a = cu[s], b = cu[s + 1];
+  for (int t = a + threadIdx.x; t < b; t += blockDim.x) {
+    pos[t] = t - a;
+    seq_of_row[t] = s;
+  }
+}
+
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
+embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* __restrict__ emb,
+                const float* __restrict__ gamma, float eps, float* __restrict__ x32, __half* __restrict__ h16) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4* e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(id) * H);
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = __ldg(e + i * 32 + lane);
+  ln_row(v, gamma, nullptr, eps, lane);
+  store_row(v, x32 + static_cast<size_t>(row) * H, h16 + static_cast<size_t>(row) * H, lane);
+}
+
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
+bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int T, int vocab, int max_pos,
+                     const float* __restrict__ wemb, const float* __restrict__ pemb, const float* __restrict__ temb0,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     float* __restrict__ x32, __half* __restrict__ h16) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int p = pos[row];
+  p = p >= max_pos ? max_pos - 1 : p;
+  const float4* e = reinterpret_cast<const float4*>(wemb + static_cast<size_t>(id) * H);
+  const float4* pe = reinterpret_cast<const float4*>(pemb + static_cast<size_t>(p) * H);
+  const float4* te = reinterpret_cast<const float4*>(temb0);
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 a = __ldg(e + i * 32 + lane), b = __ldg(pe + i * 32 + lane), c = __ldg(te + i * 32 + lane);
+    v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+  }
+  ln_row(v, gamma, beta, eps, lane);
+  store_row(v, x32 + static_cast<size_t>(row) * H, h16 + static_cast<size_t>(row) * H, lane);
+}
+
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
+layernorm_kernel(float* __restrict__ x32, int T, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, __half* __restrict__ h16, int write_back) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  float* xr = x32 + static_cast<size_t>(row) * H;
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = reinterpret_cast<const float4*>(xr)[i * 32 + lane];
+  ln_row(v, gamma, beta, eps, lane);
+  store_row(v, write_back ? xr : nullptr, h16 ? h16 + static_cast<size_t>(row) * H : nullptr, lane);
+}
+
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
+head_final_kernel(const float* __restrict__ buf32, int T, const float* __restrict__ gamma, float eps,
+                  const float* __restrict__ cw, const float* __restrict__ cb, float* __restrict__ logits,
+                  float* __restrict__ probs) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(buf32 + static_cast<size_t>(row) * H);
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = xr[i * 32 + lane];
+  ln_row(v, gamma, nullptr, eps, lane);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(cw) + i * 32 + lane);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(cw + H) + i * 32 + lane);
+    d0 += (v[i].x * w0.x + v[i].y * w0.y) + (v[i].z * w0.z + v[i].w * w0.w);
+    d1 += (v[i].x * w1.x + v[i].y * w1.y) + (v[i].z * w1.z + v[i].w * w1.w);
+  }
+  d0 = warp_sum(d0) + cb[0];
+  d1 = warp_sum(d1) + cb[1];
+  if (lane == 0) {
+    if (logits) {
+      logits[2 * static_cast<size_t>(row)] = d0;
+      logits[2 * static_cast<size_t>(row) + 1] = d1;
+    }
+    // softmax([d0, d1])[1] in fp32, max-subtracted like torch.softmax
+    const float m = fmaxf(d0, d1);
+    const float e0 = expf(d0 - m), e1 = expf(d1 - m);
+    probs[row] = e1 / (e0 + e1);
+  }
+}
+
+// ---- SPLADE: dense [nseq, ld] -> CSR, entries > min_abs, ascending vocabulary index ----
+__global__ void splade_count_kernel(const float* __restrict__ dense, int ld, int vocab, float min_abs,
+                                    int32_t* __restrict__ counts) {
+  const float* r = dense + static_cast<size_t>(blockIdx.x) * ld;
+  int c = 0;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) c += r[i] > min_abs;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += part[w];
+    counts[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+splade_fill_kernel(const float* __restrict__ dense, int ld, int vocab, float min_abs,
+                   const int64_t* __restrict__ indptr, int32_t* __restrict__ indices, float* __restrict__ values) {
+  const float* r = dense + static_cast<size_t>(blockIdx.x) * ld;
+  int64_t base = indptr[blockIdx.x];
+  __shared__ int wcount[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < vocab; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    const float x = i < vocab ? r[i] : 0.f;
+    const bool keep = i < vocab && x > min_abs;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) off += wcount[w];
+      tot += wcount[w];
+    }
+    if (keep) {
+      const int64_t o = base + off + __popc(m & ((1u << lane) - 1));
+      indices[o] = i;
+      values[o] = x;
+    }
+    base += tot;
+    __syncthreads();
+  }
+}
+
+// ---- sentence pooling over the fp32 final hidden states ----
+__global__ void __launch_bounds__(256)
+pool_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int pooling, int normalize,
+            float* __restrict__ out) {
+  const int s = blockIdx.x;
+  const int a = cu[s], b = cu[s + 1];
+  __shared__ float red[256];
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < 3; ++j) {
+    const int c = threadIdx.x + j * 256;
+    if (pooling == VRAG_POOL_CLS) {
+      acc[j] = b > a ? x32[static_cast<size_t>(a) * H + c] : 0.f;
+    } else {
+      float t = 0.f;
+      for (int r = a; r < b; ++r) t += x32[static_cast<size_t>(r) * H + c];
+      acc[j] = b > a ? t / static_cast<float>(b - a) : 0.f;
+    }
+  }
+  float scale = 1.f;
+  if (normalize) {
+    red[threadIdx.x] = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    scale = 1.f / fmaxf(sqrtf(red[0]), 1e-12f);
+  }
+  for (int j = 0; j < 3; ++j) out[static_cast<size_t>(s) * H + threadIdx.x + j * 256] = acc[j] * scale;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 u;
+    u.x = pack_half2(v.x, v.y);
+    u.y = pack_half2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = u;
+  } else {
+    for (; i < n; ++i) dst[i] = __float2half_rn(src[i]);
+  }
+}
+
+inline int row_blocks(int T) { return (T + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK; }
+
+}  // namespace
+
+#define VRAG_LAUNCHED(ctx)            \
+  do {                                \
+    VRAG_CUDA(cudaGetLastError());    \
+    (ctx)->launches++;                \
+  } while (0)
+
+void launch_token_meta(vrag_ctx* ctx, const int32_t* cu, int nseq, int total, int32_t* pos, int32_t* seq_of_row) {
+  (void)total;
+  token_meta_kernel<<<nseq, 128, 0, ctx->stream>>>(cu, nseq, pos, seq_of_row);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
+                     float eps, float* x32, __half* h16) {
+  embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, T, vocab, tok_emb, gamma, eps, x32, h16);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
+                          const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
+                          const float* beta, float eps, float* x32, __half* h16) {
+  bert_embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
+                                                                                pos_emb, type_emb0, gamma, beta, eps,
+                                                                                x32, h16);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps, __half* h16,
+                      bool write_back) {
+  layernorm_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
+                                                                            write_back ? 1 : 0);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
+                       const float* cls_b, float* logits, float* probs) {
+  head_final_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(buf32, T, gamma, eps, cls_w, cls_b, logits,
+                                                                             probs);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
+                         int32_t* counts) {
+  splade_count_kernel<<<nseq, 256, 0, ctx->stream>>>(dense, ld, vocab, min_abs, counts);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_splade_fill(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
+                        const int64_t* indptr_dev, int32_t* indices, float* values) {
+  splade_fill_kernel<<<nseq, 256, 0, ctx->stream>>>(dense, ld, vocab, min_abs, indptr_dev, indices, values);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_pool(vrag_ctx* ctx, const float* x32, const int32_t* cu, int nseq, int pooling, int normalize,
+                 float* out) {
+  pool_kernel<<<nseq, 256, 0, ctx->stream>>>(x32, cu, pooling, normalize, out);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n) {
+  const size_t threads = (n + 3) / 4;
+  f32_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(src, dst, n);
+  VRAG_LAUNCHED(ctx);
+}
+
+}  // namespace vrag

@@ -1,0 +1,723 @@
+// Exact top-k similarity scan behind the vector store (dense COSINE, sparse IP).
+//
+// Pipeline per query tile (<= 8 queries per corpus pass):
+//   1. scan     : stream the corpus once from HBM, fp32 FMA dot products -> scores[q][row]       (HBM-bound)
+//   2. select   : per query, threshold-filtered warp top-k' lists over 64-bit keys
+//                 key = (ordered(score) << 32) | ~row   => order (score desc, row asc); two levels
+//   3. rescore  : the k' = k + margin candidates are re-evaluated in fp64 from the stored fp32 values
+//   4. rank     : exact order (score64 desc, row asc) -> ids (global), fp32 + fp64 scores
+// The fp64 rescoring makes results independent of the summation order of pass 1 and identical across shard
+// counts, which is what lets the sharded multi-GPU search be bit-identical to the 1-GPU search.
+#include <math.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+using namespace vrag;
+
+namespace {
+
+constexpr int QT = 8;          // queries per corpus pass
+constexpr int MARGIN = 16;     // extra candidates kept for the fp64 re-ranking
+constexpr int MAX_K = 1024;
+constexpr int SEL_WARPS = 8;
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t ord32(float f) {  // monotone float -> uint
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return (static_cast<uint64_t>(ord32(score)) << 32) | static_cast<uint64_t>(~row);
+}
+__device__ __forceinline__ uint32_t key_row(uint64_t key) { return ~static_cast<uint32_t>(key); }
+
+// ---------------------------------------------------------------------------------- dense: norms
+__global__ void __launch_bounds__(256)
+dense_norm_kernel(const float* __restrict__ rows, int64_t n, int dim, double* __restrict__ norm64,
+                  float* __restrict__ inv_norm32) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* r = rows + row * dim;
+  double s = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const double v = static_cast<double>(r[i]);
+    s += v * v;
+  }
+  s = warp_sum_d(s);
+  if (lane == 0) {
+    const double nrm = sqrt(s);
+    norm64[row] = nrm;
+    inv_norm32[row] = nrm > 0.0 ? static_cast<float>(1.0 / nrm) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------- dense: scan
+// One warp streams 4 rows at a time (24 independent 16-byte loads per lane in flight); queries live in smem.
+template <int VEC>  // dim = VEC * 128
+__global__ void __launch_bounds__(256)
+dense_scan_kernel(const float* __restrict__ rows, int64_t n, const float* __restrict__ queries, int nq,
+                  const float* __restrict__ inv_norm_d, const float* __restrict__ inv_norm_q,
+                  const uint8_t* __restrict__ deleted, float* __restrict__ scores) {
+  constexpr int DIM = VEC * 128;
+  __shared__ float4 sq[QT][VEC * 32];
+  for (int i = threadIdx.x; i < QT * VEC * 32; i += blockDim.x) {
+    const int qi = i / (VEC * 32), c = i % (VEC * 32);
+    sq[qi][c] = qi < nq ? reinterpret_cast<const float4*>(queries + static_cast<size_t>(qi) * DIM)[c]
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t r0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * 4; r0 < n; r0 += nwarps * 4) {
+    float4 d[4][VEC];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t row = min(r0 + r, n - 1);
+      const float4* p = reinterpret_cast<const float4*>(rows + row * DIM);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) d[r][i] = ldg_stream(p + i * 32 + lane);
+    }
+    float acc[4][QT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi) acc[r][qi] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi) {
+        const float4 qv = sq[qi][i * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          acc[r][qi] += (d[r][i].x * qv.x + d[r][i].y * qv.y) + (d[r][i].z * qv.z + d[r][i].w * qv.w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi) acc[r][qi] = warp_sum(acc[r][qi]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t row = r0 + r;
+        if (row < n) {
+          const float inv = inv_norm_d[row];
+          const bool dead = deleted[row] != 0;
+#pragma unroll
+          for (int qi = 0; qi < QT; ++qi)
+            if (qi < nq) scores[static_cast<size_t>(qi) * n + row] = dead ? -INFINITY : acc[r][qi] * inv * inv_norm_q[qi];
+        }
+      }
+    }
+  }
+}
+
+// generic dimension (dim % 4 == 0): one warp per row, queries read from global/L1
+__global__ void __launch_bounds__(256)
+dense_scan_generic_kernel(const float* __restrict__ rows, int64_t n, int dim, const float* __restrict__ queries,
+                          int nq, const float* __restrict__ inv_norm_d, const float* __restrict__ inv_norm_q,
+                          const uint8_t* __restrict__ deleted, float* __restrict__ scores) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < n; row += nwarps) {
+    float acc[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) acc[qi] = 0.f;
+    const float4* p = reinterpret_cast<const float4*>(rows + row * dim);
+    for (int c = lane; c < dim / 4; c += 32) {
+      const float4 dv = ldg_stream(p + c);
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi) {
+        if (qi < nq) {
+          const float4 qv = __ldg(reinterpret_cast<const float4*>(queries + static_cast<size_t>(qi) * dim) + c);
+          acc[qi] += (dv.x * qv.x + dv.y * qv.y) + (dv.z * qv.z + dv.w * qv.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) acc[qi] = warp_sum(acc[qi]);
+    if (lane == 0) {
+      const float inv = inv_norm_d[row];
+      const bool dead = deleted[row] != 0;
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi)
+        if (qi < nq) scores[static_cast<size_t>(qi) * n + row] = dead ? -INFINITY : acc[qi] * inv * inv_norm_q[qi];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- sparse: scan
+// qT: dense query block [dim][QT] (row = vocabulary id, QT consecutive floats = one 32-byte sector per gather).
+__global__ void sparse_scatter_query_kernel(const int64_t* __restrict__ q_indptr, const int32_t* __restrict__ q_idx,
+                                            const float* __restrict__ q_val, int nq, int dim, float* __restrict__ qT) {
+  const int qi = blockIdx.x;
+  if (qi >= nq) return;
+  for (int64_t j = q_indptr[qi] + threadIdx.x; j < q_indptr[qi + 1]; j += blockDim.x) {
+    const int t = q_idx[j];
+    if (t >= 0 && t < dim) qT[static_cast<size_t>(t) * QT + qi] = q_val[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sparse_scan_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const float* __restrict__ values, int64_t n, const float* __restrict__ qT, int nq,
+                   const uint8_t* __restrict__ deleted, float* __restrict__ scores) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < n; row += nwarps) {
+    const int64_t a = indptr[row], b = indptr[row + 1];
+    float acc[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) acc[qi] = 0.f;
+    for (int64_t j = a + lane; j < b; j += 32) {
+      const int t = __ldg(indices + j);
+      const float v = __ldg(values + j);
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * QT));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * QT) + 1);
+      acc[0] += v * q0.x; acc[1] += v * q0.y; acc[2] += v * q0.z; acc[3] += v * q0.w;
+      acc[4] += v * q1.x; acc[5] += v * q1.y; acc[6] += v * q1.z; acc[7] += v * q1.w;
+    }
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) acc[qi] = warp_sum(acc[qi]);
+    if (lane == 0) {
+      const bool dead = deleted[row] != 0;
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi)
+        if (qi < nq) scores[static_cast<size_t>(qi) * n + row] = dead ? -INFINITY : acc[qi];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- select
+// Sorted (descending) list of kp keys per warp in smem; a key enters only if it beats the current kp-th best.
+__device__ __forceinline__ void list_insert(uint64_t* L, int kp, uint64_t x, int lane) {
+  int cnt = 0;
+  for (int j = lane; j < kp; j += 32) cnt += L[j] > x;
+  const int pos = __reduce_add_sync(0xffffffffu, cnt);
+  // shift [pos, kp-1) right by one: read everything first, then write
+  uint64_t tmp[(MAX_K + MARGIN + 31) / 32];
+  int c = 0;
+  for (int j = lane; j < kp; j += 32, ++c) tmp[c] = (j > pos) ? L[j - 1] : 0;
+  __syncwarp();
+  c = 0;
+  for (int j = lane; j < kp; j += 32, ++c) {
+    if (j > pos) L[j] = tmp[c];
+    else if (j == pos) L[j] = x;
+  }
+  __syncwarp();
+}
+
+template <bool FROM_SCORES>
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+select_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int kp,
+              uint64_t* __restrict__ keys_out /* [nq][gridDim.x][kp] */) {
+  extern __shared__ uint64_t lists[];  // [SEL_WARPS][kp]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.y;
+  uint64_t* L = lists + static_cast<size_t>(warp) * kp;
+  for (int j = lane; j < kp; j += 32) L[j] = 0;
+  __syncwarp();
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = per_block * blockIdx.x, b1 = min(n, b0 + per_block);
+  const int64_t per_warp = (b1 - b0 + SEL_WARPS - 1) / SEL_WARPS;
+  const int64_t w0 = b0 + per_warp * warp, w1 = min(b1, w0 + per_warp);
+  uint64_t thr = 0;
+  for (int64_t i0 = w0; i0 < w1; i0 += 32) {
+    const int64_t i = i0 + lane;
+    uint64_t key = 0;
+    if (i < w1) {
+      if (FROM_SCORES) {
+        const float s = scores[static_cast<size_t>(q) * n + i];
+        key = (s == -INFINITY) ? 0 : make_key(s, static_cast<uint32_t>(i));
+      } else {
+        key = keys_in[static_cast<size_t>(q) * n + i];
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, key > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t x = __shfl_sync(0xffffffffu, key, src);
+      if (x > thr) {
+        list_insert(L, kp, x, lane);
+        thr = L[kp - 1];
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < SEL_WARPS; ++w) {
+      const uint64_t* O = lists + static_cast<size_t>(w) * kp;
+      for (int j = 0; j < kp; ++j) {
+        const uint64_t x = O[j];
+        if (x <= thr) break;  // O is sorted descending
+        list_insert(L, kp, x, lane);
+        thr = L[kp - 1];
+      }
+    }
+    uint64_t* out = keys_out + (static_cast<size_t>(q) * gridDim.x + blockIdx.x) * kp;
+    for (int j = lane; j < kp; j += 32) out[j] = L[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------- rescore (fp64)
+__global__ void __launch_bounds__(256)
+dense_rescore_kernel(const float* __restrict__ rows, int dim, const double* __restrict__ norm64,
+                     const float* __restrict__ queries, const uint64_t* __restrict__ cand, int kp,
+                     double* __restrict__ score64, int64_t* __restrict__ cand_row) {
+  const int q = blockIdx.y;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= kp) return;
+  const uint64_t key = cand[static_cast<size_t>(q) * kp + c];
+  const size_t o = static_cast<size_t>(q) * kp + c;
+  if (key == 0) {
+    if (lane == 0) { score64[o] = -INFINITY; cand_row[o] = -1; }
+    return;
+  }
+  const int64_t row = key_row(key);
+  const float* r = rows + row * dim;
+  const float* qv = queries + static_cast<size_t>(q) * dim;
+  double dot = 0.0, qq = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const double a = static_cast<double>(r[i]), b = static_cast<double>(qv[i]);
+    dot += a * b;
+    qq += b * b;
+  }
+  dot = warp_sum_d(dot);
+  qq = warp_sum_d(qq);
+  if (lane == 0) {
+    const double den = sqrt(qq) * norm64[row];
+    score64[o] = den > 0.0 ? dot / den : 0.0;
+    cand_row[o] = row;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sparse_rescore_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      const float* __restrict__ values, const float* __restrict__ qT, int qslot,
+                      const uint64_t* __restrict__ cand, int kp, double* __restrict__ score64,
+                      int64_t* __restrict__ cand_row) {
+  // grid.y = query within the tile; qslot = -1 means "slot = blockIdx.y"
+  const int q = blockIdx.y;
+  const int slot = qslot < 0 ? q : qslot;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= kp) return;
+  const size_t o = static_cast<size_t>(q) * kp + c;
+  const uint64_t key = cand[o];
+  if (key == 0) {
+    if (lane == 0) { score64[o] = -INFINITY; cand_row[o] = -1; }
+    return;
+  }
+  const int64_t row = key_row(key);
+  double dot = 0.0;
+  for (int64_t j = indptr[row] + lane; j < indptr[row + 1]; j += 32)
+    dot += static_cast<double>(values[j]) * static_cast<double>(qT[static_cast<size_t>(indices[j]) * QT + slot]);
+  dot = warp_sum_d(dot);
+  if (lane == 0) { score64[o] = dot; cand_row[o] = row; }
+}
+
+// ---------------------------------------------------------------------------------- final rank
+// m candidates (score64, id) per query -> best k by (score desc, id asc).  id < 0 = empty slot.
+__global__ void __launch_bounds__(256)
+rank_kernel(const double* __restrict__ score64, const int64_t* __restrict__ ids, int m, int k, int64_t id_base,
+            int64_t* __restrict__ ids_out, float* __restrict__ scores_out, double* __restrict__ scores64_out) {
+  const int q = blockIdx.x;
+  const double* s = score64 + static_cast<size_t>(q) * m;
+  const int64_t* id = ids + static_cast<size_t>(q) * m;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {  // default fill
+    ids_out[static_cast<size_t>(q) * k + j] = -1;
+    scores_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+    if (scores64_out) scores64_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int64_t idi = id[i];
+    if (idi < 0) continue;
+    const double si = s[i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const int64_t idj = id[j];
+      if (idj < 0 || j == i) continue;
+      const double sj = s[j];
+      rank += (sj > si) || (sj == si && (idj < idi || (idj == idi && j < i)));
+    }
+    if (rank < k) {
+      ids_out[static_cast<size_t>(q) * k + rank] = idi + id_base;
+      scores_out[static_cast<size_t>(q) * k + rank] = static_cast<float>(si);
+      if (scores64_out) scores64_out[static_cast<size_t>(q) * k + rank] = si;
+    }
+  }
+}
+
+__global__ void query_norm_kernel(const float* __restrict__ queries, int dim, float* __restrict__ inv_norm_q) {
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x;
+  double s = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const double v = static_cast<double>(queries[static_cast<size_t>(q) * dim + i]);
+    s += v * v;
+  }
+  s = warp_sum_d(s);
+  if (lane == 0) inv_norm_q[q] = s > 0.0 ? static_cast<float>(1.0 / sqrt(s)) : 0.f;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct vrag_index {
+  vrag_ctx* ctx = nullptr;
+  int kind = 0, dim = 0;
+  int64_t n = 0, cap = 0;
+  int64_t id_base = 0;  // added to row numbers in results (global id of this shard's row 0)
+  DevBuf rows, norm64, inv32, deleted;
+  // sparse
+  DevBuf indptr, indices, values;
+  int64_t nnz = 0, nnz_cap = 0;
+  // work
+  DevBuf scores, keys0, keys1, s64, crow, qdev, qnorm, qT, qip, qidx, qval, out_ids, out_s32, out_s64;
+  ~vrag_index() {
+    for (DevBuf* b : {&rows, &norm64, &inv32, &deleted, &indptr, &indices, &values, &scores, &keys0, &keys1, &s64,
+                      &crow, &qdev, &qnorm, &qT, &qip, &qidx, &qval, &out_ids, &out_s32, &out_s64})
+      b->release();
+  }
+};
+
+namespace {
+
+void grow(vrag_ctx* ctx, DevBuf& b, size_t used_bytes, size_t need_bytes) {
+  if (need_bytes <= b.bytes) return;
+  size_t nb = std::max(need_bytes, b.bytes + b.bytes / 2);
+  void* np = nullptr;
+  VRAG_CUDA(cudaMalloc(&np, nb));
+  if (used_bytes) VRAG_CUDA(cudaMemcpyAsync(np, b.p, used_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (b.p) cudaFree(b.p);
+  b.p = np;
+  b.bytes = nb;
+}
+
+// scores [nq_tile][n] on device -> final top-k for the tile written at out offsets
+void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float* queries_dev /*dense*/,
+                     int64_t* ids_out, float* s32_out, double* s64_out /*device, tile offset applied*/) {
+  vrag_ctx* ctx = ix->ctx;
+  const int64_t n = ix->n;
+  const int kp = static_cast<int>(std::min<int64_t>(k + MARGIN, std::max<int64_t>(n, 1)));
+  const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, ctx->num_sms * 4)));
+  const size_t smem = static_cast<size_t>(SEL_WARPS) * kp * 8;
+  static bool smem_attr = false;
+  if (!smem_attr) {
+    VRAG_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    VRAG_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    smem_attr = true;
+  }
+  ix->keys0.reserve(static_cast<size_t>(nq_tile) * nblk0 * kp * 8);
+  ix->keys1.reserve(static_cast<size_t>(nq_tile) * kp * 8);
+  select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
+      ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  const uint64_t* final_keys = ix->keys0.as<uint64_t>();
+  if (nblk0 > 1) {
+    select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
+        nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
+    VRAG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    final_keys = ix->keys1.as<uint64_t>();
+  }
+  ix->s64.reserve(static_cast<size_t>(nq_tile) * kp * 8);
+  ix->crow.reserve(static_cast<size_t>(nq_tile) * kp * 8);
+  dim3 g((kp + 7) / 8, nq_tile);
+  if (dense)
+    dense_rescore_kernel<<<g, 256, 0, ctx->stream>>>(ix->rows.as<float>(), ix->dim, ix->norm64.as<double>(),
+                                                      queries_dev, final_keys, kp, ix->s64.as<double>(),
+                                                      ix->crow.as<int64_t>());
+  else
+    sparse_rescore_kernel<<<g, 256, 0, ctx->stream>>>(ix->indptr.as<int64_t>(), ix->indices.as<int32_t>(),
+                                                       ix->values.as<float>(), ix->qT.as<float>(), -1, final_keys, kp,
+                                                       ix->s64.as<double>(), ix->crow.as<int64_t>());
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  rank_kernel<<<nq_tile, 256, 0, ctx->stream>>>(ix->s64.as<double>(), ix->crow.as<int64_t>(), kp, k, ix->id_base,
+                                                ids_out, s32_out, s64_out);
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void fill_empty(vrag_ctx* ctx, int nq, int k, int64_t* ids, float* s32, double* s64, bool on_device) {
+  std::vector<int64_t> hi(static_cast<size_t>(nq) * k, -1);
+  std::vector<float> hs(static_cast<size_t>(nq) * k, -INFINITY);
+  std::vector<double> hd(static_cast<size_t>(nq) * k, -INFINITY);
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+  VRAG_CUDA(cudaMemcpy(ids, hi.data(), hi.size() * 8, kind));
+  VRAG_CUDA(cudaMemcpy(s32, hs.data(), hs.size() * 4, kind));
+  if (s64) VRAG_CUDA(cudaMemcpy(s64, hd.data(), hd.size() * 8, kind));
+  (void)ctx;
+}
+
+}  // namespace
+
+#define VRAG_API_BEGIN(ctxp)                 \
+  vrag_ctx* _ctx = (ctxp);                   \
+  std::lock_guard<std::mutex> _lk(_ctx->mu); \
+  try {                                      \
+    VRAG_CUDA(cudaSetDevice(_ctx->device));
+#define VRAG_API_END()                                    \
+    return VRAG_OK;                                       \
+  } catch (const vrag::Error& e) {                        \
+    _ctx->last_error = e.what();                          \
+    return e.code;                                        \
+  } catch (const std::exception& e) {                     \
+    _ctx->last_error = e.what();                          \
+    return VRAG_ERR_INTERNAL;                             \
+  }
+
+extern "C" int vrag_index_create(vrag_ctx* ctx, int kind, int dim, vrag_index** out) {
+  if (!ctx || !out) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(ctx)
+  VRAG_CHECK(kind == VRAG_INDEX_DENSE_COSINE || kind == VRAG_INDEX_SPARSE_IP, VRAG_ERR_ARG, "index_create: bad kind");
+  VRAG_CHECK(dim > 0 && (kind == VRAG_INDEX_SPARSE_IP || dim % 4 == 0), VRAG_ERR_ARG,
+             "index_create: dense dim must be a positive multiple of 4");
+  vrag_index* ix = new vrag_index();
+  ix->ctx = ctx;
+  ix->kind = kind;
+  ix->dim = dim;
+  if (kind == VRAG_INDEX_SPARSE_IP) {
+    ix->indptr.reserve(8);
+    VRAG_CUDA(cudaMemsetAsync(ix->indptr.p, 0, 8, ctx->stream));
+    ix->qT.reserve(static_cast<size_t>(dim) * QT * 4);
+    VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = ix;
+  VRAG_API_END()
+}
+
+extern "C" void vrag_index_destroy(vrag_index* idx) {
+  if (!idx) return;
+  cudaSetDevice(idx->ctx->device);
+  cudaStreamSynchronize(idx->ctx->stream);
+  delete idx;
+}
+
+extern "C" int64_t vrag_index_size(vrag_index* idx) { return idx ? idx->n : -1; }
+
+extern "C" int vrag_index_set_id_base(vrag_index* idx, int64_t base) {
+  if (!idx) return VRAG_ERR_ARG;
+  idx->id_base = base;
+  return VRAG_OK;
+}
+
+extern "C" int vrag_index_add_dense(vrag_index* idx, const float* rows, int64_t n, int on_device) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  VRAG_CHECK(idx->kind == VRAG_INDEX_DENSE_COSINE, VRAG_ERR_ARG, "add_dense on a sparse index");
+  VRAG_CHECK(n >= 0 && (rows || n == 0), VRAG_ERR_ARG, "add_dense: null rows");
+  if (n == 0) return VRAG_OK;
+  VRAG_CHECK(idx->n + n < (1LL << 32) - 1, VRAG_ERR_ARG, "add_dense: more than 2^32-2 rows per shard");
+  const size_t rb = static_cast<size_t>(idx->dim) * 4;
+  grow(_ctx, idx->rows, idx->n * rb, (idx->n + n) * rb);
+  grow(_ctx, idx->norm64, idx->n * 8, (idx->n + n) * 8);
+  grow(_ctx, idx->inv32, idx->n * 4, (idx->n + n) * 4);
+  grow(_ctx, idx->deleted, idx->n, idx->n + n);
+  float* dst = idx->rows.as<float>() + idx->n * idx->dim;
+  VRAG_CUDA(cudaMemcpyAsync(dst, rows, n * rb, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, _ctx->stream));
+  VRAG_CUDA(cudaMemsetAsync(idx->deleted.as<uint8_t>() + idx->n, 0, n, _ctx->stream));
+  dense_norm_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, _ctx->stream>>>(
+      dst, n, idx->dim, idx->norm64.as<double>() + idx->n, idx->inv32.as<float>() + idx->n);
+  VRAG_CUDA(cudaGetLastError());
+  _ctx->launches++;
+  VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  idx->n += n;
+  VRAG_API_END()
+}
+
+extern "C" int vrag_index_add_sparse(vrag_index* idx, const int64_t* indptr, const int32_t* indices,
+                                     const float* values, int64_t n) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  VRAG_CHECK(idx->kind == VRAG_INDEX_SPARSE_IP, VRAG_ERR_ARG, "add_sparse on a dense index");
+  VRAG_CHECK(n >= 0 && (indptr || n == 0), VRAG_ERR_ARG, "add_sparse: null indptr");
+  if (n == 0) return VRAG_OK;
+  VRAG_CHECK(idx->n + n < (1LL << 32) - 1, VRAG_ERR_ARG, "add_sparse: more than 2^32-2 rows per shard");
+  const int64_t add_nnz = indptr[n] - indptr[0];
+  VRAG_CHECK(add_nnz >= 0 && (add_nnz == 0 || (indices && values)), VRAG_ERR_ARG, "add_sparse: bad CSR");
+  for (int64_t j = 0; j < add_nnz; ++j)
+    VRAG_CHECK(indices[indptr[0] + j] >= 0 && indices[indptr[0] + j] < idx->dim, VRAG_ERR_ARG,
+               "add_sparse: term id outside [0, dim)");
+  std::vector<int64_t> ip(n);
+  for (int64_t i = 0; i < n; ++i) {
+    VRAG_CHECK(indptr[i + 1] >= indptr[i], VRAG_ERR_ARG, "add_sparse: indptr not monotone");
+    ip[i] = idx->nnz + (indptr[i + 1] - indptr[0]);
+  }
+  grow(_ctx, idx->indptr, (idx->n + 1) * 8, (idx->n + n + 1) * 8);
+  grow(_ctx, idx->indices, idx->nnz * 4, (idx->nnz + add_nnz) * 4);
+  grow(_ctx, idx->values, idx->nnz * 4, (idx->nnz + add_nnz) * 4);
+  grow(_ctx, idx->deleted, idx->n, idx->n + n);
+  VRAG_CUDA(cudaMemcpyAsync(idx->indptr.as<int64_t>() + idx->n + 1, ip.data(), n * 8, cudaMemcpyHostToDevice, _ctx->stream));
+  if (add_nnz) {
+    VRAG_CUDA(cudaMemcpyAsync(idx->indices.as<int32_t>() + idx->nnz, indices + indptr[0], add_nnz * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(idx->values.as<float>() + idx->nnz, values + indptr[0], add_nnz * 4, cudaMemcpyHostToDevice, _ctx->stream));
+  }
+  VRAG_CUDA(cudaMemsetAsync(idx->deleted.as<uint8_t>() + idx->n, 0, n, _ctx->stream));
+  VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  idx->n += n;
+  idx->nnz += add_nnz;
+  VRAG_API_END()
+}
+
+extern "C" int vrag_index_mark_deleted(vrag_index* idx, const int64_t* rows, int64_t n) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  VRAG_CHECK(n >= 0 && (rows || n == 0), VRAG_ERR_ARG, "mark_deleted: null rows");
+  const uint8_t one = 1;
+  for (int64_t i = 0; i < n; ++i) {
+    VRAG_CHECK(rows[i] >= 0 && rows[i] < idx->n, VRAG_ERR_ARG, "mark_deleted: row out of range");
+    VRAG_CUDA(cudaMemcpyAsync(idx->deleted.as<uint8_t>() + rows[i], &one, 1, cudaMemcpyHostToDevice, _ctx->stream));
+  }
+  VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  VRAG_API_END()
+}
+
+extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, int nq, int k, int64_t* ids_out,
+                                       float* scores_out, double* scores64_out, int on_device) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  VRAG_CHECK(idx->kind == VRAG_INDEX_DENSE_COSINE, VRAG_ERR_ARG, "search_dense on a sparse index");
+  VRAG_CHECK(nq >= 0 && k > 0 && k <= MAX_K, VRAG_ERR_ARG, "search_dense: need nq >= 0 and 1 <= k <= 1024");
+  VRAG_CHECK(nq == 0 || (queries && ids_out && scores_out), VRAG_ERR_ARG, "search_dense: null argument");
+  if (nq == 0) return VRAG_OK;
+  if (idx->n == 0) { fill_empty(_ctx, nq, k, ids_out, scores_out, scores64_out, on_device); return VRAG_OK; }
+  const int dim = idx->dim;
+  const int64_t n = idx->n;
+  const float* qd = queries;
+  if (!on_device) {
+    idx->qdev.reserve(static_cast<size_t>(nq) * dim * 4);
+    VRAG_CUDA(cudaMemcpyAsync(idx->qdev.p, queries, static_cast<size_t>(nq) * dim * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    qd = idx->qdev.as<float>();
+    idx->out_ids.reserve(static_cast<size_t>(nq) * k * 8);
+    idx->out_s32.reserve(static_cast<size_t>(nq) * k * 4);
+    idx->out_s64.reserve(static_cast<size_t>(nq) * k * 8);
+  }
+  int64_t* d_ids = on_device ? ids_out : idx->out_ids.as<int64_t>();
+  float* d_s32 = on_device ? scores_out : idx->out_s32.as<float>();
+  double* d_s64 = on_device ? scores64_out : idx->out_s64.as<double>();
+  idx->qnorm.reserve(static_cast<size_t>(nq) * 4);
+  query_norm_kernel<<<nq, 32, 0, _ctx->stream>>>(qd, dim, idx->qnorm.as<float>());
+  VRAG_CUDA(cudaGetLastError());
+  _ctx->launches++;
+  idx->scores.reserve(static_cast<size_t>(QT) * n * 4);
+  const int grid = static_cast<int>(std::min<int64_t>((n + 31) / 32, static_cast<int64_t>(_ctx->num_sms) * 2));
+  for (int q0 = 0; q0 < nq; q0 += QT) {
+    const int nt = std::min(QT, nq - q0);
+    const float* qt = qd + static_cast<size_t>(q0) * dim;
+    const float* qn = idx->qnorm.as<float>() + q0;
+#define VRAG_SCAN(V)                                                                                            \
+  dense_scan_kernel<V><<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, qt, nt, idx->inv32.as<float>(), \
+                                                        qn, idx->deleted.as<uint8_t>(), idx->scores.as<float>())
+    if (dim == 768) VRAG_SCAN(6);
+    else if (dim == 384) VRAG_SCAN(3);
+    else if (dim == 1024) VRAG_SCAN(8);
+    else
+      dense_scan_generic_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, dim, qt, nt,
+                                                                idx->inv32.as<float>(), qn,
+                                                                idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+#undef VRAG_SCAN
+    VRAG_CUDA(cudaGetLastError());
+    _ctx->launches++;
+    select_and_rank(idx, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
+                    d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
+  }
+  if (!on_device) {
+    VRAG_CUDA(cudaMemcpyAsync(ids_out, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(scores_out, d_s32, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+    if (scores64_out)
+      VRAG_CUDA(cudaMemcpyAsync(scores64_out, d_s64, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  }
+  VRAG_API_END()
+}
+
+extern "C" int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr, const int32_t* q_indices,
+                                        const float* q_values, int nq, int k, int64_t* ids_out, float* scores_out,
+                                        double* scores64_out) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  VRAG_CHECK(idx->kind == VRAG_INDEX_SPARSE_IP, VRAG_ERR_ARG, "search_sparse on a dense index");
+  VRAG_CHECK(nq >= 0 && k > 0 && k <= MAX_K, VRAG_ERR_ARG, "search_sparse: need nq >= 0 and 1 <= k <= 1024");
+  VRAG_CHECK(nq == 0 || (q_indptr && ids_out && scores_out), VRAG_ERR_ARG, "search_sparse: null argument");
+  if (nq == 0) return VRAG_OK;
+  if (idx->n == 0) { fill_empty(_ctx, nq, k, ids_out, scores_out, scores64_out, false); return VRAG_OK; }
+  const int64_t n = idx->n;
+  const int64_t qnnz = q_indptr[nq] - q_indptr[0];
+  std::vector<int64_t> ip(nq + 1);
+  for (int i = 0; i <= nq; ++i) ip[i] = q_indptr[i] - q_indptr[0];
+  idx->qip.reserve((static_cast<size_t>(nq) + 1) * 8);
+  idx->qidx.reserve(std::max<size_t>(4, static_cast<size_t>(qnnz) * 4));
+  idx->qval.reserve(std::max<size_t>(4, static_cast<size_t>(qnnz) * 4));
+  VRAG_CUDA(cudaMemcpyAsync(idx->qip.p, ip.data(), (static_cast<size_t>(nq) + 1) * 8, cudaMemcpyHostToDevice, _ctx->stream));
+  if (qnnz) {
+    VRAG_CUDA(cudaMemcpyAsync(idx->qidx.p, q_indices + q_indptr[0], static_cast<size_t>(qnnz) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(idx->qval.p, q_values + q_indptr[0], static_cast<size_t>(qnnz) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+  }
+  idx->out_ids.reserve(static_cast<size_t>(nq) * k * 8);
+  idx->out_s32.reserve(static_cast<size_t>(nq) * k * 4);
+  idx->out_s64.reserve(static_cast<size_t>(nq) * k * 8);
+  idx->scores.reserve(static_cast<size_t>(QT) * n * 4);
+  const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(_ctx->num_sms) * 8));
+  for (int q0 = 0; q0 < nq; q0 += QT) {
+    const int nt = std::min(QT, nq - q0);
+    VRAG_CUDA(cudaMemsetAsync(idx->qT.p, 0, static_cast<size_t>(idx->dim) * QT * 4, _ctx->stream));
+    sparse_scatter_query_kernel<<<nt, 128, 0, _ctx->stream>>>(idx->qip.as<int64_t>() + q0, idx->qidx.as<int32_t>(),
+                                                               idx->qval.as<float>(), nt, idx->dim, idx->qT.as<float>());
+    VRAG_CUDA(cudaGetLastError());
+    _ctx->launches++;
+    sparse_scan_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->indptr.as<int64_t>(), idx->indices.as<int32_t>(),
+                                                        idx->values.as<float>(), n, idx->qT.as<float>(), nt,
+                                                        idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+    VRAG_CUDA(cudaGetLastError());
+    _ctx->launches++;
+    select_and_rank(idx, nt, k, false, nullptr, idx->out_ids.as<int64_t>() + static_cast<size_t>(q0) * k,
+                    idx->out_s32.as<float>() + static_cast<size_t>(q0) * k,
+                    idx->out_s64.as<double>() + static_cast<size_t>(q0) * k);
+  }
+  VRAG_CUDA(cudaMemcpyAsync(ids_out, idx->out_ids.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+  VRAG_CUDA(cudaMemcpyAsync(scores_out, idx->out_s32.p, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+  if (scores64_out)
+    VRAG_CUDA(cudaMemcpyAsync(scores64_out, idx->out_s64.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+  VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  VRAG_API_END()
+}
+
+extern "C" int vrag_topk_merge(vrag_ctx* ctx, const double* scores64, const int64_t* ids, int nq, int m, int k,
+                               int64_t* ids_out, float* scores_out, double* scores64_out) {
+  if (!ctx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(ctx)
+  VRAG_CHECK(nq >= 0 && m > 0 && k > 0 && scores64 && ids && ids_out && scores_out, VRAG_ERR_ARG, "topk_merge: bad argument");
+  if (nq == 0) return VRAG_OK;
+  rank_kernel<<<nq, 256, 0, ctx->stream>>>(scores64, ids, m, k, 0, ids_out, scores_out, scores64_out);
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  VRAG_API_END()
+}
