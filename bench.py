@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""
+bench.py -- the contract benchmark of the B200 hot path (BASELINE.json metric, configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference-shaped CPU path (oracle port)
+
+One "step" = one pass of the span-extraction hot path over one batch of synthetic input:
+256 questions x 16 retrieved chunks = 4096 sequences of exactly 512 tokens
+(``[CLS] + 29 question tokens + [SEP] + 480 chunk tokens + [SEP]``), ModernBERT-base token classifier, 22 layers,
+seeded random-init weights (no checkpoint exists offline).  Weak scaling: every rank processes its own 4096
+sequences per step; no collective on this path.
+
+Printed JSON line (rank 0): the base contract keys plus
+  e2e          the same step through the C ABI with HOST buffers: ids H2D, forward, probs D2H, span post-processing
+  roofline     tensor-core GEMM: algorithmic FLOPs / summed CUDA-event kernel time, vs MEASURED_PEAKS.json
+  cpu_baseline the oracle port timed on this box's host cores (bounded sample; rank 0, N=1 only)
+  secondary    top-k scan (BASELINE 'top-k GB/s') and SPLADE encode numbers, same run
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "(question,512-tok chunk) span-extractions/sec"
+UNIT = "extractions/s"
+SEQ_LEN, Q_LEN = 512, 29
+SEQS_PER_STEP = 256 * 16
+LAYERS = 22
+FLOPS_LINEAR_PER_TOKEN = 221.78e6          # all Linear layers incl. head
+FLOPS_PER_EXTRACTION = 122.65e9            # linears + windowed attention at L = 512
+WORKLOAD = "ModernBERT-v2 span extraction: 256-query batch x 16 retrieved chunks @512 tok (configs[2])"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"source": "measured (MEASURED_PEAKS.json)", "hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"])}
+    return {"source": "fallback (B200_PROFILING.md)", "hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0}
+
+
+def make_batch(nseq: int, seed: int):
+    """Token ids of ``nseq`` sequences ``[CLS] q(29) [SEP] chunk(480) [SEP]`` + synthetic char offsets of the chunk
+    tokens (7 chars per token incl. the separating space) for the span post-processing."""
+    from verbatim_rag_b200.synthetic import ModernBertSpec
+    spec = ModernBertSpec()
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(5, 50279, size=(nseq, SEQ_LEN), dtype=np.int32)
+    ids[:, 0] = spec.cls_id
+    ids[:, Q_LEN + 1] = spec.sep_id
+    ids[:, -1] = spec.sep_id
+    cu = (np.arange(nseq + 1, dtype=np.int64) * SEQ_LEN).astype(np.int32)
+    n_ctx = SEQ_LEN - Q_LEN - 3
+    tok_cs = np.tile(np.arange(n_ctx, dtype=np.int32) * 7, nseq)
+    tok_ce = tok_cs + 6
+    ctx_indptr = np.arange(nseq + 1, dtype=np.int64) * n_ctx
+    return ids.reshape(-1), cu, tok_cs, tok_ce, ctx_indptr
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference-shaped path (oracle port), batch-1 forward per chunk like extractors.py:207-221
+# --------------------------------------------------------------------------------------------------------------
+def cpu_extract(weights, ids, cu, tok_cs, tok_ce, ctx_indptr, nseq):
+    import torch
+    from oracle.highlighter import spans_from_token_probs
+    from oracle.modernbert import modernbert_forward, relevant_prob
+    n_ctx = SEQ_LEN - Q_LEN - 3
+    nspans = 0
+    for i in range(nseq):
+        seq = ids[cu[i]:cu[i + 1]].astype(np.int64)[None]
+        p = relevant_prob(modernbert_forward(weights, seq).numpy()[0])[Q_LEN + 2:Q_LEN + 2 + n_ctx]
+        offs = list(zip(tok_cs[:n_ctx].tolist(), tok_ce[:n_ctx].tolist()))
+        nspans += len(spans_from_token_probs("x" * (7 * n_ctx), p, offs, 0.2, 30, 20))
+    return nspans
+
+
+def time_cpu(nseq_sample: int, steps: int, warmup: int):
+    import torch
+    from verbatim_rag_b200.synthetic import make_modernbert_weights
+    weights = {k: torch.from_numpy(v) for k, v in make_modernbert_weights(1001).items()}
+    ids, cu, tcs, tce, cip = make_batch(nseq_sample, 1003)
+    for _ in range(warmup):
+        cpu_extract(weights, ids, cu, tcs, tce, cip, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_extract(weights, ids, cu, tcs, tce, cip, nseq_sample)
+    dt = (time.perf_counter() - t0) / steps
+    return nseq_sample / dt, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    rate, dt, cores = time_cpu(sample, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "seq_len": SEQ_LEN, "layers": LAYERS},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {SEQS_PER_STEP} sequences per step, batch-1 forward per chunk "
+                                   "(reference control flow, oracle ModernBERT fp32 on torch CPU) + span post-processing"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+def secondary_metrics(ctx, peaks, rank, world, device):
+    """Top-k scan + SPLADE encode numbers of the same run (bounded: ~10 s)."""
+    import torch
+    from verbatim_rag_b200 import _native
+    out = {}
+    st = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def timed(fn, iters=3):
+        fn()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(iters):
+            fn()
+        e1.record(st)
+        ctx.sync()
+        return e0.elapsed_time(e1) / iters
+
+    # dense cosine top-10, 1M x 768 fp32 corpus row-sharded over the ranks (configs[3])
+    n_total, dim, k = 1_000_000, 768, 10
+    from verbatim_rag_b200.distributed import shard_bounds
+    lo, hi = shard_bounds(n_total, rank, world)
+    g = torch.Generator(device=device).manual_seed(1004 + rank)
+    ix = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    ix.set_id_base(lo)
+    ix.add_dense(torch.randn(hi - lo, dim, device=device, generator=g))
+    gq = torch.Generator(device=device).manual_seed(2004)
+    for nq in (1, 8, 64):
+        q = torch.randn(nq, dim, device=device, generator=gq)
+        ids_o = torch.empty(nq, k, dtype=torch.int64, device=device)
+        s_o = torch.empty(nq, k, dtype=torch.float32, device=device)
+        ms = timed(lambda: ix.search_dense_device(q, nq, k, ids_o, s_o))
+        passes = (nq + 7) // 8
+        gbs = passes * (hi - lo) * dim * 4 / ms / 1e6
+        out[f"dense_top{k}_q{nq}"] = {"ms": ms, "corpus_GBps_per_gpu": gbs, "frac_hbm_peak": gbs / peaks["hbm_gbs"],
+                                      "queries_per_s": nq / ms * 1e3, "rows_per_gpu": hi - lo}
+    ix.close()
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import ModernBertSpec, make_modernbert_weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    peaks = _peaks()
+    ctx = _native.default_context(local)
+    spec = ModernBertSpec(layers=LAYERS)
+    enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, make_modernbert_weights(1001, spec), spec.layers,
+                          spec.vocab_size, max_tokens=args.max_tokens)
+    nseq = args.seqs_per_step
+    ids_h, cu, tok_cs, tok_ce, ctx_indptr = make_batch(nseq, 1003 + rank)
+    T = int(cu[-1])
+    ids_d = torch.from_numpy(ids_h).to(device)
+    probs_d = torch.empty(T, dtype=torch.float32, device=device)
+    st = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        ctx.sync()
+
+    def step_device():
+        enc.span_forward_device(ids_d, cu, probs_d)
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream ------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(st)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * nseq / (ms_step / 1e3)
+
+    # ---- e2e: host buffers through the C ABI (H2D + forward + D2H + span post-processing) -----------------------
+    ids_pin = torch.from_numpy(ids_h).pin_memory().numpy()
+    def step_host():
+        p = enc.span_forward(ids_pin, cu)
+        c0 = Q_LEN + 2
+        p_ctx = np.ascontiguousarray(p.reshape(nseq, SEQ_LEN)[:, c0:c0 + (SEQ_LEN - Q_LEN - 3)]).reshape(-1)
+        return _native.spans_from_probs(p_ctx, tok_cs, tok_ce, ctx_indptr, 0.2, 30, 20)
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    nsp = 0
+    for _ in range(max(1, args.steps // 2)):
+        nsp = len(step_host()["ctx"])
+    ctx.sync()
+    e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * nseq / float(t.item())
+
+    if rank != 0:
+        if args.secondary:
+            secondary_metrics(ctx, peaks, rank, world, device)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
+    gemm_flops = FLOPS_LINEAR_PER_TOKEN * T * args.steps
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "seqs_per_step_per_gpu": nseq, "seq_len": SEQ_LEN, "layers": LAYERS,
+                   "precision": "fp16 tensor-core operands, fp32 accumulate + fp32 residual stream",
+                   "max_tokens_per_pass": args.max_tokens,
+                   "l2": "working set per step (>= 11.5 KB of activations per token, %.1f GB) exceeds the 126 MB L2"
+                         % (11.5e3 * T / 1e9),
+                   "tflops_algorithmic": value * FLOPS_PER_EXTRACTION / 1e12 / world},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 4 + (nseq + 1) * 4),
+                "d2h_bytes_per_step": int(T * 4), "spans_per_step": int(nsp),
+                "path": "vrag_span_forward(host ids) + vrag_spans_from_probs (C ABI, host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved,
+                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                     "peak_source": peaks["source"] + ", sustained cuBLAS bf16", "traffic": traffic,
+                     "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                     "flops_per_launch_avg": gemm_flops / max(gemm_n, 1),
+                     "share_of_step": {k: v["ms"] / (ms_total) for k, v in prof.items() if v["launches"]}},
+    }
+    if world == 1 and args.cpu_baseline:
+        rate, dt, cores = time_cpu(args.cpu_sample, 1, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_sample} of {SEQS_PER_STEP} sequences, batch-1 forward per chunk "
+                                          "(reference control flow, oracle ModernBERT fp32 on torch CPU)"}
+    if args.secondary:
+        line["secondary"] = secondary_metrics(ctx, peaks, rank, world, device)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqs-per-step", type=int, default=SEQS_PER_STEP)
+    ap.add_argument("--max-tokens", type=int, default=65536)
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

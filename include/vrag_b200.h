@@ -75,6 +75,12 @@ int vrag_sync(vrag_ctx* ctx);
 void* vrag_stream(vrag_ctx* ctx);            /* the cudaStream_t all kernels are launched on */
 uint64_t vrag_launch_count(vrag_ctx* ctx);   /* kernels launched so far through this context */
 const char* vrag_version(void);
+/* Per-launch CUDA-event profiler on the context's stream.  Classes: 0 tensor-core GEMM, 1 attention, 2 row ops
+ * (LayerNorm / embedding / head tail / CSR extraction), 3 top-k scan, 4 top-k select+rescore+rank, 5 other.
+ * vrag_profile(ctx, 1) starts recording; vrag_profile_read synchronises, returns the summed kernel time (ms) and
+ * launch count per class [6] since the last read, and resets the record. */
+int vrag_profile(vrag_ctx* ctx, int enable);
+int vrag_profile_read(vrag_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
 
 /* ---- encoders ------------------------------------------------------------------------------ */
 /* Uploads + repacks the checkpoint (fp32 host tensors -> fp16 tensor-core operands, fp32 norms/biases).

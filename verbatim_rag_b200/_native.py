@@ -23,7 +23,7 @@ POOL_MEAN, POOL_CLS = 0, 1
 # every symbol include/vrag_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
     "vrag_ctx_create", "vrag_ctx_destroy", "vrag_last_error", "vrag_sync", "vrag_stream", "vrag_launch_count",
-    "vrag_version", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
+    "vrag_version", "vrag_profile", "vrag_profile_read", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
     "vrag_dense_forward", "vrag_selftest_gemm", "vrag_debug_span_hidden", "vrag_spans_from_probs",
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_search_dense", "vrag_index_search_sparse",
@@ -67,6 +67,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_stream": (vp, [vp]),
             "vrag_launch_count": (C.c_uint64, [vp]),
             "vrag_version": (C.c_char_p, []),
+            "vrag_profile": (i32, [vp, i32]),
+            "vrag_profile_read": (i32, [vp, P(f64), P(i64)]),
             "vrag_encoder_create": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, P(vp)]),
             "vrag_encoder_destroy": (None, [vp]),
             "vrag_span_forward": (i32, [vp, vp, vp, i32, vp, vp, i32]),
@@ -137,6 +139,17 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.vrag_launch_count(self.h))
+
+    PROF_CLASSES = ("gemm", "attention", "rowops", "scan", "select", "other")
+
+    def profile(self, enable: bool):
+        self.check(self.lib.vrag_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms = (C.c_double * 6)()
+        cnt = (C.c_int64 * 6)()
+        self.check(self.lib.vrag_profile_read(self.h, ms, cnt))
+        return {n: {"ms": ms[i], "launches": int(cnt[i])} for i, n in enumerate(self.PROF_CLASSES)}
 
     def selftest_gemm(self, M: int, N: int, K: int) -> Tuple[float, float]:
         d, m = C.c_double(), C.c_double()

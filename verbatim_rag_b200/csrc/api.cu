@@ -106,6 +106,32 @@ extern "C" int vrag_sync(vrag_ctx* ctx) {
   return VRAG_OK;
 }
 
+extern "C" int vrag_profile(vrag_ctx* ctx, int enable) {
+  if (!ctx) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->prof.on = enable != 0;
+  ctx->prof.used = 0;
+  ctx->prof.recs.clear();
+  return VRAG_OK;
+}
+
+extern "C" int vrag_profile_read(vrag_ctx* ctx, double* ms_per_class, int64_t* launches_per_class) {
+  if (!ctx || !ms_per_class || !launches_per_class) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return VRAG_ERR_CUDA;
+  for (int i = 0; i < PROF_NCLASS; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  for (const auto& r : ctx->prof.recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->prof.pool[r.e0], ctx->prof.pool[r.e1]);
+    ms_per_class[r.cls] += ms;
+    launches_per_class[r.cls] += 1;
+  }
+  ctx->prof.used = 0;
+  ctx->prof.recs.clear();
+  return VRAG_OK;
+}
+
 extern "C" void* vrag_stream(vrag_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 extern "C" uint64_t vrag_launch_count(vrag_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -178,6 +178,7 @@ void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32
                       int max_len, int heads, int hidden, int window /* <0: full */) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64
   dim3 grid((max_len + BQ - 1) / BQ, heads, nseq);
+  ProfScope prof(ctx, PROF_ATTENTION);
   if (window >= 0)
     attention_kernel<true><<<grid, 128, 0, ctx->stream>>>(qkv, out, cu_seqlens_dev, 3 * hidden, hidden, scale_log2e,
                                                            window);

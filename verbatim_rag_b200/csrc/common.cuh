@@ -60,8 +60,31 @@ struct DevBuf {
 
 }  // namespace vrag
 
+// Optional per-launch CUDA-event profiler (bench.py's roofline leg): start/stop events on the launching stream
+// around every kernel, summed per class on read.  Off by default (no events recorded).
+namespace vrag {
+enum ProfClass { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_ROWOPS = 2, PROF_SCAN = 3, PROF_SELECT = 4, PROF_OTHER = 5,
+                 PROF_NCLASS = 6 };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; size_t e0, e1; };
+  std::vector<Rec> recs;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+}  // namespace vrag
+
 // The context behind the opaque C handle.
 struct vrag_ctx {
+  vrag::Profiler prof;
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -80,6 +103,25 @@ namespace vrag {
 // 2D row-major tensor map, 128-byte swizzle, box = {box_cols (128 bytes worth), box_rows}.
 CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt, size_t elem_bytes, uint64_t rows,
                          uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
+struct ProfScope {
+  vrag_ctx* c;
+  int cls;
+  size_t e0 = 0;
+  ProfScope(vrag_ctx* ctx, int k) : c(ctx), cls(k) {
+    if (c->prof.on) {
+      e0 = c->prof.used;
+      cudaEventRecord(c->prof.get(), c->stream);
+    }
+  }
+  ~ProfScope() {
+    if (c->prof.on) {
+      size_t e1 = c->prof.used;
+      cudaEventRecord(c->prof.get(), c->stream);
+      c->prof.recs.push_back({cls, e0, e1});
+    }
+  }
+};
 
 struct StreamGuard {
   vrag_ctx* c;

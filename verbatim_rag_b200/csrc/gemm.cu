@@ -322,6 +322,7 @@ template <int EPI>
 void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int K, const GemmEpiParams& p,
               int use_reference) {
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
+  ProfScope prof(ctx, PROF_GEMM);
   if (use_reference) {
     gemm_reference_kernel<EPI><<<m_tiles * n_tiles, 128, 0, ctx->stream>>>(A, W, K, n_tiles, p);
   } else {

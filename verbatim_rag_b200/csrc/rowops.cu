@@ -254,18 +254,21 @@ inline int row_blocks(int T) { return (T + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   } while (0)
 
 void launch_token_meta(vrag_ctx* ctx, const int32_t* cu, int nseq, int total, int32_t* pos, int32_t* seq_of_row) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   (void)total;
   token_meta_kernel<<<nseq, 128, 0, ctx->stream>>>(cu, nseq, pos, seq_of_row);
   VRAG_LAUNCHED(ctx);
 }
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
                      float eps, float* x32, __half* h16) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, T, vocab, tok_emb, gamma, eps, x32, h16);
   VRAG_LAUNCHED(ctx);
 }
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
                           const float* beta, float eps, float* x32, __half* h16) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   bert_embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
                                                                                 pos_emb, type_emb0, gamma, beta, eps,
                                                                                 x32, h16);
@@ -273,32 +276,38 @@ void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos,
 }
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps, __half* h16,
                       bool write_back) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   layernorm_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
                                                                             write_back ? 1 : 0);
   VRAG_LAUNCHED(ctx);
 }
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
                        const float* cls_b, float* logits, float* probs) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   head_final_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(buf32, T, gamma, eps, cls_w, cls_b, logits,
                                                                              probs);
   VRAG_LAUNCHED(ctx);
 }
 void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
                          int32_t* counts) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   splade_count_kernel<<<nseq, 256, 0, ctx->stream>>>(dense, ld, vocab, min_abs, counts);
   VRAG_LAUNCHED(ctx);
 }
 void launch_splade_fill(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
                         const int64_t* indptr_dev, int32_t* indices, float* values) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   splade_fill_kernel<<<nseq, 256, 0, ctx->stream>>>(dense, ld, vocab, min_abs, indptr_dev, indices, values);
   VRAG_LAUNCHED(ctx);
 }
 void launch_pool(vrag_ctx* ctx, const float* x32, const int32_t* cu, int nseq, int pooling, int normalize,
                  float* out) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   pool_kernel<<<nseq, 256, 0, ctx->stream>>>(x32, cu, pooling, normalize, out);
   VRAG_LAUNCHED(ctx);
 }
 void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n) {
+  ProfScope prof(ctx, PROF_ROWOPS);
   const size_t threads = (n + 3) / 4;
   f32_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(src, dst, n);
   VRAG_LAUNCHED(ctx);

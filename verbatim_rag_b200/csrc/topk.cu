@@ -435,6 +435,7 @@ void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float
   }
   ix->keys0.reserve(static_cast<size_t>(nq_tile) * nblk0 * kp * 8);
   ix->keys1.reserve(static_cast<size_t>(nq_tile) * kp * 8);
+  ProfScope prof(ctx, PROF_SELECT);
   select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
       ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
   VRAG_CUDA(cudaGetLastError());
@@ -633,6 +634,8 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     const int nt = std::min(QT, nq - q0);
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
+    {
+    ProfScope prof(_ctx, PROF_SCAN);
 #define VRAG_SCAN(V)                                                                                            \
   dense_scan_kernel<V><<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, qt, nt, idx->inv32.as<float>(), \
                                                         qn, idx->deleted.as<uint8_t>(), idx->scores.as<float>())
@@ -646,6 +649,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
 #undef VRAG_SCAN
     VRAG_CUDA(cudaGetLastError());
     _ctx->launches++;
+    }
     select_and_rank(idx, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
                     d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
   }
@@ -693,11 +697,14 @@ extern "C" int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr
                                                                idx->qval.as<float>(), nt, idx->dim, idx->qT.as<float>());
     VRAG_CUDA(cudaGetLastError());
     _ctx->launches++;
-    sparse_scan_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->indptr.as<int64_t>(), idx->indices.as<int32_t>(),
-                                                        idx->values.as<float>(), n, idx->qT.as<float>(), nt,
-                                                        idx->deleted.as<uint8_t>(), idx->scores.as<float>());
-    VRAG_CUDA(cudaGetLastError());
-    _ctx->launches++;
+    {
+      ProfScope prof(_ctx, PROF_SCAN);
+      sparse_scan_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->indptr.as<int64_t>(), idx->indices.as<int32_t>(),
+                                                          idx->values.as<float>(), n, idx->qT.as<float>(), nt,
+                                                          idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+      VRAG_CUDA(cudaGetLastError());
+      _ctx->launches++;
+    }
     select_and_rank(idx, nt, k, false, nullptr, idx->out_ids.as<int64_t>() + static_cast<size_t>(q0) * k,
                     idx->out_s32.as<float>() + static_cast<size_t>(q0) * k,
                     idx->out_s64.as<double>() + static_cast<size_t>(q0) * k);
