@@ -1,0 +1,71 @@
+"""Generate the committed golden fixtures from the CPU oracle (run in the build container):
+
+    PYTHONPATH=/root/repo python tests/golden/make_golden.py
+
+Inputs are re-derived from seeds at test time (``cases.py``); the fixtures hold only the oracle's OUTPUTS plus a hash
+of the inputs, so generator drift is detected.  Library versions are recorded in ``versions.json``.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cases  # noqa: E402
+from oracle import bert_splade, flat_topk, highlighter, modernbert  # noqa: E402
+
+
+def main():
+    import torch
+    import transformers
+    out = {}
+
+    # ---- config 1: 4 questions x 8 chunks @128 tokens, full 22-layer model -------------------------------------
+    c = cases.span_cfg1()
+    logits = modernbert.modernbert_forward_varlen(c["weights"], c["seqs"], c["spec"], batch=8)
+    probs = [modernbert.relevant_prob(lg) for lg in logits]
+    spans = []
+    margin = 1.0
+    for pi, ((q, ctx), lg, pr, nq, off) in enumerate(zip(c["pairs"], logits, probs, c["n_q"], c["ctx_offsets"])):
+        p_ctx = pr[nq + 2: nq + 2 + len(off)]
+        margin = min(margin, float(np.abs(p_ctx - np.float32(0.2)).min()))
+        for sp in highlighter.spans_from_token_probs(ctx, p_ctx, off, 0.2, 30, 20):
+            spans.append((pi, sp["start"], sp["end"], sp["tok_start"], sp["tok_end"], sp["score"]))
+    sp_arr = np.asarray([s[:5] for s in spans], dtype=np.int64).reshape(-1, 5)
+    np.savez_compressed(os.path.join(HERE, "span_cfg1.npz"),
+                        logits=np.concatenate(logits, axis=0).astype(np.float32),
+                        cu=np.cumsum([0] + [len(s) for s in c["seqs"]]).astype(np.int64),
+                        spans=sp_arr, span_scores=np.asarray([s[5] for s in spans], dtype=np.float64),
+                        min_margin_to_threshold=np.float64(margin), input_hash=np.bytes_(c["hash"].encode()))
+    out["span_cfg1"] = {"pairs": len(c["pairs"]), "spans": len(spans), "min_margin_to_threshold": margin,
+                        "frac_tokens_kept": float(np.mean(np.concatenate(probs) > 0.2))}
+
+    # ---- SPLADE: 12 texts, full 12-layer BERT-MLM ---------------------------------------------------------------
+    s = cases.splade_small()
+    dense = bert_splade.splade_encode(s["weights"], s["seqs"], s["spec"])
+    ip, idx, val = flat_topk.dicts_to_csr(bert_splade.to_dicts_embed_batch(dense))
+    np.savez_compressed(os.path.join(HERE, "splade_small.npz"), indptr=ip, indices=idx, values=val,
+                        input_hash=np.bytes_(s["hash"].encode()))
+    out["splade_small"] = {"texts": len(s["seqs"]), "nnz": np.diff(ip).tolist()}
+
+    # ---- top-k ----------------------------------------------------------------------------------------------------
+    d = cases.topk_dense()
+    ids, sc = flat_topk.dense_cosine_topk(d["corpus"], d["queries"], d["k"])
+    np.savez_compressed(os.path.join(HERE, "topk_dense.npz"), ids=ids, scores=sc)
+    t = cases.topk_sparse()
+    ids2, sc2 = flat_topk.sparse_ip_topk(*t["corpus"], 30522, t["query_dicts"], t["k"])
+    np.savez_compressed(os.path.join(HERE, "topk_sparse.npz"), ids=ids2, scores=sc2)
+    out["topk"] = {"dense": list(ids.shape), "sparse": list(ids2.shape)}
+
+    json.dump({"torch": torch.__version__, "transformers": transformers.__version__, "numpy": np.__version__,
+               "summary": out}, open(os.path.join(HERE, "versions.json"), "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

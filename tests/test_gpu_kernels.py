@@ -33,6 +33,17 @@ def test_tcgen05_gemm_matches_simt_reference(ctx, M, N, K):
     assert diff <= 1e-3 * max(ref_max, 1.0), (diff, ref_max)
 
 
+@pytest.mark.parametrize("epi,name", [(0, "f16"), (1, "rope_qkv"), (2, "resid_f32"), (3, "geglu")])
+@pytest.mark.parametrize("M", [128, 300, 5000])
+def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
+    """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel."""
+    N, K = 2304, 768
+    diff, ref_max = ctx.selftest_gemm(M, N, K, epi)
+    _diag(test="gemm_epilogue_selftest", epilogue=name, M=M, max_abs_diff=diff, ref_abs_max=ref_max)
+    tol = 2e-3 if epi != 2 else 1e-4   # fp16 outputs: one rounding of slightly different fp32 sums
+    assert diff <= tol * max(ref_max, 1.0), (name, diff, ref_max)
+
+
 # ------------------------------------------------------------------------------------------ ModernBERT
 def _modernbert_case(layers, lens, seed):
     from verbatim_rag_b200.synthetic import ModernBertSpec, make_modernbert_weights
@@ -48,16 +59,14 @@ def _modernbert_case(layers, lens, seed):
     return spec, w, seqs
 
 
-@pytest.mark.parametrize("use_ref_gemm", [True, False])
-def test_modernbert_forward_vs_oracle(ctx, use_ref_gemm, monkeypatch):
+@pytest.mark.parametrize("use_ref_gemm,legacy_attn", [(True, True), (False, True), (False, False)])
+def test_modernbert_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
     from verbatim_rag_b200 import _native
     from oracle.modernbert import modernbert_forward, modernbert_forward_varlen, relevant_prob
-    lens = [150, 200, 333, 512, 64, 129, 7, 1]
+    lens = [150, 200, 333, 512, 64, 129, 7, 1, 700]
     spec, w, seqs = _modernbert_case(4, lens, 1001)
-    if use_ref_gemm:
-        monkeypatch.setenv("VRAG_GEMM_REFERENCE", "1")
-    else:
-        monkeypatch.delenv("VRAG_GEMM_REFERENCE", raising=False)
+    monkeypatch.setenv("VRAG_GEMM_REFERENCE", "1" if use_ref_gemm else "0")
+    monkeypatch.setenv("VRAG_ATTENTION_LEGACY", "1" if legacy_attn else "0")
     enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, w, spec.layers, spec.vocab_size, max_tokens=4096)
     ids, cu = _native.Encoder._pack(seqs)
     probs, logits, hidden = enc.debug_span_hidden(ids, cu)
@@ -69,7 +78,7 @@ def test_modernbert_forward_vs_oracle(ctx, use_ref_gemm, monkeypatch):
     a, b = cu[i3], cu[i3 + 1]
     layer_err = [float(np.abs(hidden[l, a:b] - hid3[l][0].numpy()).max()) for l in range(spec.layers + 1)]
     perr = np.abs(probs - relevant_prob(ref_logits))
-    _diag(test="modernbert_vs_oracle", use_ref_gemm=use_ref_gemm, logit_max_err=float(err.max()),
+    _diag(test="modernbert_vs_oracle", use_ref_gemm=use_ref_gemm, legacy_attn=legacy_attn, logit_max_err=float(err.max()),
           logit_rms_err=float(np.sqrt((err ** 2).mean())), prob_max_err=float(perr.max()), layer_max_err=layer_err,
           logit_std=float(ref_logits.std()),
           per_seq_err=[float(err[cu[i]:cu[i + 1]].max()) for i in range(len(lens))])
@@ -94,8 +103,8 @@ def test_modernbert_multi_pass_equals_single_pass(ctx):
 
 
 # ------------------------------------------------------------------------------------------ SPLADE
-@pytest.mark.parametrize("use_ref_gemm", [True, False])
-def test_splade_forward_vs_oracle(ctx, use_ref_gemm, monkeypatch):
+@pytest.mark.parametrize("use_ref_gemm,legacy_attn", [(True, True), (False, False)])
+def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
     from verbatim_rag_b200 import _native
     from verbatim_rag_b200.synthetic import BertSpec, make_bert_mlm_weights
     from oracle.bert_splade import splade_encode
@@ -107,10 +116,8 @@ def test_splade_forward_vs_oracle(ctx, use_ref_gemm, monkeypatch):
         s = rng.integers(1000, spec.vocab_size, size=L)
         s[0], s[-1] = spec.cls_id, spec.sep_id
         seqs.append(s.astype(np.int64))
-    if use_ref_gemm:
-        monkeypatch.setenv("VRAG_GEMM_REFERENCE", "1")
-    else:
-        monkeypatch.delenv("VRAG_GEMM_REFERENCE", raising=False)
+    monkeypatch.setenv("VRAG_GEMM_REFERENCE", "1" if use_ref_gemm else "0")
+    monkeypatch.setenv("VRAG_ATTENTION_LEGACY", "1" if legacy_attn else "0")
     enc = _native.Encoder(ctx, _native.ENC_BERT_MLM, w, spec.layers, spec.vocab_size, max_tokens=2048)
     ids, cu = _native.Encoder._pack(seqs)
     out = enc.splade_forward(ids, cu, min_abs=0.0, want_dense=True)

@@ -151,9 +151,11 @@ class Context:
         self.check(self.lib.vrag_profile_read(self.h, ms, cnt))
         return {n: {"ms": ms[i], "launches": int(cnt[i])} for i, n in enumerate(self.PROF_CLASSES)}
 
-    def selftest_gemm(self, M: int, N: int, K: int) -> Tuple[float, float]:
+    def selftest_gemm(self, M: int, N: int, K: int, epilogue: int = 10) -> Tuple[float, float]:
+        """tcgen05 GEMM vs the SIMT reference GEMM on the device; epilogue 10 = fp32, 0 = fp16, 1 = RoPE-QKV,
+        2 = fp32 residual add, 3 = GeGLU."""
         d, m = C.c_double(), C.c_double()
-        self.check(self.lib.vrag_selftest_gemm(self.h, M, N, K, 10, C.byref(d), C.byref(m)))
+        self.check(self.lib.vrag_selftest_gemm(self.h, M, N, K, epilogue, C.byref(d), C.byref(m)))
         return d.value, m.value
 
     def topk_merge(self, scores64, ids, nq: int, m: int, k: int, ids_out, scores_out, scores64_out=None):

@@ -194,28 +194,43 @@ extern "C" int vrag_spans_from_probs(const float* probs, const int32_t* tcs, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEMM self test: tcgen05 path vs the SIMT reference path, same epilogue (EPI_F32 or EPI_F16), on the device.
+// GEMM self test: tcgen05 path (staged TMA epilogues) vs the SIMT reference path (direct thread-per-row epilogue)
+// on identical random operands, for the epilogues F32(10), F16(0), ROPE_QKV(1), RESID_F32(2), GEGLU(3).
 // ------------------------------------------------------------------------------------------------
 namespace {
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
 __global__ void fill_half_kernel(__half* p, size_t n, uint32_t seed, float scale) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t x = static_cast<uint32_t>(i) * 2654435761u + seed;
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  p[i] = __float2half_rn((static_cast<float>(x & 0xffff) / 32768.0f - 1.0f) * scale);
+  p[i] = __float2half_rn((static_cast<float>(hash_u32(static_cast<uint32_t>(i) * 2654435761u + seed) & 0xffff) / 32768.0f - 1.0f) * scale);
 }
-__global__ void diff_kernel(const float* a, const float* b, size_t n, float* out /*[2]: max diff, max |b|*/) {
+__global__ void fill_float_kernel(float* p, size_t n, uint32_t seed, float scale) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = (static_cast<float>(hash_u32(static_cast<uint32_t>(i) * 2654435761u + seed) & 0xffff) / 32768.0f - 1.0f) * scale;
+}
+__global__ void fill_pos_kernel(int32_t* p, size_t n, int max_pos) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = static_cast<int32_t>(hash_u32(static_cast<uint32_t>(i) + 7u) % max_pos);
+}
+template <typename T>
+__global__ void diff_kernel(const T* a, const T* b, size_t n, float* out /*[2]: max diff, max |b|*/) {
   float d = 0.f, m = 0.f;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float x = fabsf(a[i] - b[i]);
+    const float fa = static_cast<float>(a[i]), fb = static_cast<float>(b[i]);
+    float x = fabsf(fa - fb);
     if (!(x == x)) x = INFINITY;  // NaN (e.g. an output the kernel never wrote) must not hide behind fmaxf
     d = fmaxf(d, x);
-    m = fmaxf(m, fabsf(b[i]));
+    m = fmaxf(m, fabsf(fb));
   }
   atomicMax(reinterpret_cast<int*>(out), __float_as_int(d));
   atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(m));
 }
+inline unsigned blocks_for(size_t n) { return static_cast<unsigned>((n + 255) / 256); }
 }  // namespace
 
 extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff,
@@ -224,33 +239,55 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
     VRAG_CUDA(cudaSetDevice(ctx->device));
-    VRAG_CHECK(epilogue == EPI_F32, VRAG_ERR_ARG, "selftest_gemm: only the plain fp32 epilogue (10) is supported");
-    DevBuf A, W, C0, C1, R;
+    const bool f32_out = epilogue == EPI_F32 || epilogue == EPI_RESID_F32;
+    VRAG_CHECK(epilogue == EPI_F32 || epilogue == EPI_F16 || epilogue == EPI_ROPE_QKV || epilogue == EPI_RESID_F32 ||
+                   epilogue == EPI_GEGLU, VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3");
+    VRAG_CHECK(epilogue != EPI_ROPE_QKV || N % 192 == 0, VRAG_ERR_ARG, "selftest_gemm: ROPE needs N = 3 * hidden");
+    const int out_cols = epilogue == EPI_GEGLU ? N / 2 : N;
+    const size_t out_n = static_cast<size_t>(M) * out_cols;
+    const size_t out_bytes = out_n * (f32_out ? 4 : 2);
+    const int max_pos = 512;
+    DevBuf A, W, C0, C1, R, POS, CS, SN;
     A.reserve(static_cast<size_t>(M) * K * 2);
     W.reserve(static_cast<size_t>(N) * K * 2);
-    C0.reserve(static_cast<size_t>(M) * N * 4);
-    C1.reserve(static_cast<size_t>(M) * N * 4);
+    C0.reserve(out_bytes);
+    C1.reserve(out_bytes);
     R.reserve(8);
-    fill_half_kernel<<<static_cast<unsigned>((static_cast<size_t>(M) * K + 255) / 256), 256, 0, ctx->stream>>>(
-        A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
-    fill_half_kernel<<<static_cast<unsigned>((static_cast<size_t>(N) * K + 255) / 256), 256, 0, ctx->stream>>>(
-        W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
-    VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, static_cast<size_t>(M) * N * 4, ctx->stream));
-    VRAG_CUDA(cudaMemsetAsync(C1.p, 0, static_cast<size_t>(M) * N * 4, ctx->stream));
-    VRAG_CUDA(cudaMemsetAsync(R.p, 0, 8, ctx->stream));
-    GemmEpiParams p;
-    p.M = M; p.ld32 = N;
-    p.out32 = C0.as<float>();
-    launch_gemm(ctx, EPI_F32, A.as<__half>(), W.as<__half>(), M, N, K, p, 0);
-    p.out32 = C1.as<float>();
-    launch_gemm(ctx, EPI_F32, A.as<__half>(), W.as<__half>(), M, N, K, p, 1);
-    diff_kernel<<<256, 256, 0, ctx->stream>>>(C0.as<float>(), C1.as<float>(), static_cast<size_t>(M) * N, R.as<float>());
+    POS.reserve(static_cast<size_t>(M) * 4);
+    CS.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    SN.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    cudaStream_t st = ctx->stream;
+    fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
+    fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
+    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos);
+    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(CS.as<float>(), max_pos * 32, 5u, 1.0f);
+    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(SN.as<float>(), max_pos * 32, 6u, 1.0f);
+    if (epilogue == EPI_RESID_F32) {  // both paths accumulate onto the same initial residual
+      fill_float_kernel<<<blocks_for(out_n), 256, 0, st>>>(C0.as<float>(), out_n, 33u, 1.0f);
+      VRAG_CUDA(cudaMemcpyAsync(C1.p, C0.p, out_bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, out_bytes, st));  // NaN pattern: unwritten outputs are detected
+      VRAG_CUDA(cudaMemsetAsync(C1.p, 0, out_bytes, st));
+    }
+    VRAG_CUDA(cudaMemsetAsync(R.p, 0, 8, st));
+    for (int ref = 0; ref < 2; ++ref) {
+      GemmEpiParams p;
+      p.M = M;
+      p.ld32 = out_cols; p.ld16 = out_cols;
+      p.out32 = (ref ? C1 : C0).as<float>();
+      p.out16 = (ref ? C1 : C0).as<__half>();
+      p.pos = POS.as<int32_t>(); p.rope_cos = CS.as<float>(); p.rope_sin = SN.as<float>();
+      p.hidden = N / 3;
+      launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, ref);
+    }
+    if (f32_out) diff_kernel<float><<<256, 256, 0, st>>>(C0.as<float>(), C1.as<float>(), out_n, R.as<float>());
+    else diff_kernel<__half><<<256, 256, 0, st>>>(C0.as<__half>(), C1.as<__half>(), out_n, R.as<float>());
     float h[2];
-    VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, st));
+    VRAG_CUDA(cudaStreamSynchronize(st));
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
-    A.release(); W.release(); C0.release(); C1.release(); R.release();
+    for (DevBuf* b : {&A, &W, &C0, &C1, &R, &POS, &CS, &SN}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();

@@ -1,0 +1,270 @@
+// tcgen05 self-attention over unpadded sequences: one (128-query tile, head, sequence) per CTA, 2 CTAs per SM.
+//
+//   warp 0      : TMA producer  (Q tile once; K/V blocks of 64 keys into a 2-stage ring, SWIZZLE_128B boxes)
+//   warp 1      : MMA issuer    S = Q K^T   (tcgen05.mma 128x64x16, both operands K-major)  -> TMEM S[2]
+//                               PV = P V    (tcgen05.mma 128x64x16, A = P from smem, B = V MN-major) -> TMEM Otmp
+//   warps 2..5  : softmax       thread == query row: tcgen05.ld S, scale + mask, online max / sum in base 2,
+//                               P (fp16) -> swizzled smem, fold the previous block's PV into O (registers)
+// S is double buffered so QK^T of block j+1 overlaps the softmax of block j; the second CTA on the SM fills the
+// MMA <-> softmax dependency bubbles.  q/k already carry RoPE (Wqkv GEMM epilogue).  On local layers only the key
+// blocks intersecting |i - j| <= window are visited.
+#include "encoder.cuh"
+#include "ptx.cuh"
+
+namespace vrag {
+
+namespace {
+
+constexpr int AQ = 128, AK = 64, AD = 64;
+constexpr int ATT_THREADS = 192;
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64)  S1 [64,128)  Otmp [128,192)
+constexpr int SQ_BYTES = AQ * AD * 2;    // 16384
+constexpr int SKV_BYTES = AK * AD * 2;   // 8192
+constexpr int SP_BYTES = AQ * AK * 2;    // 16384
+constexpr int ATT_SMEM = SQ_BYTES + 2 * 2 * SKV_BYTES + SP_BYTES + 1024 + 256;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    __half* __restrict__ out, const int32_t* __restrict__ cu_seqlens, int hidden, float scale_log2e,
+                    int window) {
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int s0 = cu_seqlens[seq];
+  const int L = cu_seqlens[seq + 1] - s0;
+  const int q0 = blockIdx.x * AQ;
+  if (q0 >= L) return;  // uniform for the CTA, before any barrier / TMEM allocation
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + SQ_BYTES;               // stage s: K at sKV + s*16384, V at +8192
+  uint8_t* sP = sKV + 4 * SKV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + SP_BYTES);
+  uint64_t* bar_q = bars;            // 1
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;       // [2]
+  uint64_t* s_empty = bars + 7;      // [2]
+  uint64_t* p_full = bars + 9;       // 1
+  uint64_t* pv_done = bars + 10;     // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kv_lo = 0, kv_hi = L;
+  if (LOCAL) {
+    kv_lo = max(0, q0 - window);
+    kv_hi = min(L, q0 + AQ + window);
+  }
+  const int j_lo = kv_lo / AK;
+  const int nb = (kv_hi + AK - 1) / AK - j_lo;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(kv_full + i, 1);
+      mbar_init(kv_empty + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(s_empty + i, 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, SQ_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, head * AD, s0 + q0);
+      for (int i = 0; i < nb; ++i) {
+        const int st = i & 1;
+        mbar_wait(kv_empty + st, ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full + st, 2 * SKV_BYTES);
+        const int row = s0 + (j_lo + i) * AK;
+        tma_load_2d(sKV + st * 2 * SKV_BYTES, &tmKV, kv_full + st, hidden + head * AD, row);
+        tma_load_2d(sKV + st * 2 * SKV_BYTES + SKV_BYTES, &tmKV, kv_full + st, 2 * hidden + head * AD, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
+      constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+      mbar_wait(bar_q, 0);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(kv_full + st, (i >> 1) & 1);
+        mbar_wait(s_empty + st, ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
+#pragma unroll
+        for (int k = 0; k < AD / 16; ++k)
+          umma_f16(tmem_base + st * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
+                   k > 0 ? 1u : 0u);
+        umma_commit(s_full + st);
+      };
+      issue_s(0);
+      for (int i = 0; i < nb; ++i) {
+        if (i + 1 < nb) issue_s(i + 1);
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        const int st = i & 1;
+        const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
+#pragma unroll
+        for (int k = 0; k < AK / 16; ++k)  // 16 keys per step = two 8-row groups of the V tile = 2048 bytes
+          umma_f16(tmem_base + 2 * AK, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128(v_addr + k * 2048), idesc_pv,
+                   k > 0 ? 1u : 0u);
+        umma_commit(pv_done);
+        umma_commit(kv_empty + st);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const int q = q0 + r;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float o[AD];
+#pragma unroll
+    for (int d = 0; d < AD; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+
+    auto fold = [&](int i_done) {  // O = O * alpha + PV_{i_done}
+      mbar_wait(pv_done, i_done & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < AD / 16; ++h) {
+        uint32_t t[16];
+        tmem_ld_32x32b_x16(t_lane + 2 * AK + h * 16, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[h * 16 + e] = fmaf(o[h * 16 + e], alpha_prev, __uint_as_float(t[e]));
+      }
+    };
+
+    for (int i = 0; i < nb; ++i) {
+      if (i > 0) fold(i - 1);
+      const int st = i & 1;
+      mbar_wait(s_full + st, (i >> 1) & 1);
+      tc_fence_after();
+      float s[AK];
+      {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(t_lane + st * AK, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(t[e]);
+        tmem_ld_32x32b_x32(t_lane + st * AK + 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s[32 + e] = __uint_as_float(t[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + st);
+
+      const int key0 = (j_lo + i) * AK;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < AK; ++e) {
+        const int key = key0 + e;
+        bool ok = key < L;
+        if (LOCAL) ok = ok && (key - q <= window) && (q - key <= window);
+        s[e] = ok ? s[e] * scale_log2e : -INFINITY;
+        mx = fmaxf(mx, s[e]);
+      }
+      const float m_new = fmaxf(m, mx);
+      const float mu = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = ex2(m - mu);  // first block: ex2(-inf) = 0
+      float sum = 0.f;
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          p[e] = ex2(s[c * 8 + e] - mu);
+          sum += p[e];
+        }
+        uint4 u;
+        u.x = pack_half2(p[0], p[1]);
+        u.y = pack_half2(p[2], p[3]);
+        u.z = pack_half2(p[4], p[5]);
+        u.w = pack_half2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
+      }
+      l = fmaf(l, alpha, sum);
+      m = m_new;
+      alpha_prev = alpha;
+      fence_proxy_async_smem();  // P written with st.shared must be visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    fold(nb - 1);
+    if (q < L) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(s0 + q) * hidden + head * AD);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_half2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+        u.y = pack_half2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+        u.z = pack_half2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+        u.w = pack_half2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+        dst[c] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev, int nseq,
+                         int total_tokens, int max_len, int heads, int hidden, int window /* <0: full */) {
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  ProfScope prof(ctx, PROF_ATTENTION);
+  CUtensorMap tmQ = make_tmap_2d(ctx, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AQ, AD);
+  CUtensorMap tmKV = make_tmap_2d(ctx, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AK, AD);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((max_len + AQ - 1) / AQ, heads, nseq);
+  if (window >= 0)
+    attention_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tmQ, tmKV, out, cu_seqlens_dev, hidden,
+                                                                            scale_log2e, window);
+  else
+    attention_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tmQ, tmKV, out, cu_seqlens_dev, hidden,
+                                                                             scale_log2e, 0);
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+}  // namespace vrag

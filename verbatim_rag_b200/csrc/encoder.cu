@@ -24,6 +24,11 @@ struct vrag_encoder {
   int kind = 0, layers = 0, vocab = 0, vocab_pad = 0, max_tokens = 0, max_seqs = 0, max_pos = 0;
   int ffn = 0;  // GeGLU width (1152) or FFN width (3072)
   bool use_reference_gemm = false;
+  bool legacy_attention = false;
+  void attention(const __half* qkv, __half* out, int nseq, int total_tokens, int max_len, int window) {
+    if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
+    else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), nseq, total_tokens, max_len, 12, vrag::HIDDEN, window);
+  }
   std::vector<DevBuf*> owned;
   // shared
   float *emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
@@ -271,7 +276,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     p.rope_cos = global ? e->cos_g : e->cos_l;
     p.rope_sin = global ? e->sin_g : e->sin_l;
     launch_gemm(ctx, EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
-    launch_attention(ctx, qkv, o16, e->cu.as<int32_t>(), ns, ps.max_len, 12, H, global ? -1 : 64);
+    e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);
     GemmEpiParams r;
     r.M = T; r.out32 = x32; r.ld32 = H;
     launch_gemm(ctx, EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
@@ -304,7 +309,7 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
     GemmEpiParams p;
     p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.bias = L.bqkv;
     launch_gemm(ctx, EPI_BIAS_F16, h16, L.wqkv, T, 3 * H, H, p, ref);
-    launch_attention(ctx, qkv, o16, e->cu.as<int32_t>(), ns, ps.max_len, 12, H, -1);
+    e->attention(qkv, o16, ns, T, ps.max_len, -1);
     GemmEpiParams r;
     r.M = T; r.out32 = x32; r.ld32 = H; r.bias = L.bo;
     launch_gemm(ctx, EPI_BIAS_RESID_F32, o16, L.wo, T, H, H, r, ref);
@@ -355,6 +360,8 @@ extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int 
   e->max_seqs = std::max(64, max_tokens / 8);
   const char* dbg = getenv("VRAG_GEMM_REFERENCE");
   e->use_reference_gemm = dbg && dbg[0] == '1';
+  const char* leg = getenv("VRAG_ATTENTION_LEGACY");
+  e->legacy_attention = leg && leg[0] == '1';
   WeightSet w(tensors, num_tensors);
   if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
   else build_bert(e.get(), w);

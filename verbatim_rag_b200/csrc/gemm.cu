@@ -1,7 +1,9 @@
 // tcgen05 GEMM for sm_100a: persistent, warp-specialised.
 //   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes into a 4-stage smem ring)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma 128x256x16, fp32 accumulators in TMEM)
-//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> fused tail -> global)
+//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> fused tail -> swizzled smem box ->
+//                                 TMA store, or TMA reduce-add for the fp32 residual stream: x += acc happens in
+//                                 the memory system, the SM never reads x)
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Tiles are walked n-fastest so concurrently running CTAs share the same A rows (L2 reuse); W is L2 resident.
 #include "gemm.cuh"
@@ -12,11 +14,14 @@ namespace vrag {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// per epilogue warp: two 4 KB TMA-store boxes (32 rows x 128 B, SWIZZLE_128B) + cos/sin rows of its 32 tokens
+constexpr int EPI_BOX_BYTES = 4096;
+constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES + 2 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -195,13 +200,170 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Staged epilogue (tcgen05 path): thread == row writes its 128-byte piece of a [32 rows x 128 B] box into smem with
+// the 128B swizzle (16-byte chunk c of row r at c ^ (r & 7): conflict-free per quarter warp and exactly the layout a
+// SWIZZLE_128B tensor map expects); one lane then issues a TMA store / reduce-add of the box.  Boxes are
+// double-buffered per warp; cp.async.bulk.wait_group.read gates buffer reuse.
+// ---------------------------------------------------------------------------------------------------------------
+template <int EPI>
+constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_ROPE_QKV ||
+                          EPI == EPI_GEGLU || EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32);
+
+struct BoxStager {
+  uint8_t* base;      // this warp's two boxes
+  uint32_t issued;    // boxes submitted so far (same value in every lane)
+  __device__ __forceinline__ uint8_t* acquire(int lane) {
+    if (issued >= 2 && lane == 0) bulk_wait_read<1>();  // the box submitted two steps ago has been read out
+    __syncwarp();
+    return base + (issued & 1) * EPI_BOX_BYTES;
+  }
+  template <bool REDUCE>
+  __device__ __forceinline__ void submit(const CUtensorMap* tm, uint8_t* box, int x, int y, int lane) {
+    fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
+    __syncwarp();
+    if (lane == 0) {
+      if (REDUCE) tma_reduce_add_2d(tm, box, x, y);
+      else tma_store_2d(tm, box, x, y);
+      bulk_commit();
+    }
+    ++issued;
+  }
+};
+
+// write 32 fp32 values as 16 halves-pairs = 64 bytes = chunks [4*half_idx, 4*half_idx+4) of this thread's box row
+__device__ __forceinline__ void box_put_half32(uint8_t* box, int r, int half_idx, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(box + r * 128 + (((half_idx * 4 + i) ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void box_put_float32(uint8_t* box, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(box + r * 128 + ((i ^ (r & 7)) << 4)) =
+        make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+template <int EPI>
+__device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st,
+                                                float* cs_s, float* sn_s, int m0, int n_tile, const TmemLoader& ld,
+                                                int lane) {
+  const int col0 = n_tile * BN;
+  const int r = lane;  // row of this thread inside the warp's 32-row slab
+  float v[32];
+  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll 1
+    for (int b = 0; b < BN / 64; ++b) {
+      uint8_t* box = st.acquire(lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ld.load(2 * b + h, v);
+        if constexpr (EPI != EPI_F16) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + (2 * b + h) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+          }
+        }
+        if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        box_put_half32(box, r, h, v);
+      }
+      st.submit<false>(tmOut, box, col0 + b * 64, m0, lane);
+    }
+  } else if constexpr (EPI == EPI_ROPE_QKV) {
+    const bool rotate = col0 < 2 * p.hidden;  // q / k tiles
+    if (rotate) {
+      // stage cos/sin rows of this warp's 32 tokens: coalesced 128-byte reads, swizzled so thread == row reads are
+      // conflict free
+      const int row = m0 + lane;
+      const int my_pos = row < p.M ? __ldg(p.pos + row) : 0;
+      __syncwarp();
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const int ps = __shfl_sync(0xffffffffu, my_pos, rr);
+        const int o = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+        cs_s[o] = __ldg(p.rope_cos + static_cast<size_t>(ps) * 32 + lane);
+        sn_s[o] = __ldg(p.rope_sin + static_cast<size_t>(ps) * 32 + lane);
+      }
+      __syncwarp();
+    }
+    float w2[32];
+#pragma unroll 1
+    for (int h = 0; h < BN / 64; ++h) {
+      uint8_t* box = st.acquire(lane);
+      ld.load(2 * h, v);
+      ld.load(2 * h + 1, w2);
+      if (rotate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 c = *reinterpret_cast<const float4*>(cs_s + r * 32 + ((i ^ (r & 7)) << 2));
+          const float4 s = *reinterpret_cast<const float4*>(sn_s + r * 32 + ((i ^ (r & 7)) << 2));
+          const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x1 = v[4 * i + e], x2 = w2[4 * i + e];
+            v[4 * i + e] = x1 * cc[e] - x2 * ss[e];
+            w2[4 * i + e] = x2 * cc[e] + x1 * ss[e];
+          }
+        }
+      }
+      box_put_half32(box, r, 0, v);
+      box_put_half32(box, r, 1, w2);
+      st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
+    }
+  } else if constexpr (EPI == EPI_GEGLU) {
+    float g[32];
+#pragma unroll 1
+    for (int b = 0; b < 2; ++b) {
+      uint8_t* box = st.acquire(lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ld.load(2 * b + h, v);
+        ld.load(4 + 2 * b + h, g);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]) * g[i];
+        box_put_half32(box, r, h, v);
+      }
+      st.submit<false>(tmOut, box, n_tile * 128 + b * 64, m0, lane);
+    }
+  } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint8_t* box = st.acquire(lane);
+      ld.load(c, v);
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + i);
+          v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+        }
+      }
+      box_put_float32(box, r, v);
+      st.submit<true>(tmOut, box, col0 + c * 32, m0, lane);
+    }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int m_tiles,
-                    int n_tiles, int k_blocks, GemmEpiParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, int m_tiles, int n_tiles, int k_blocks,
+                    GemmEpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(epi_smem + 4 * EPI_WARP_BYTES);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
@@ -282,6 +444,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* my_smem = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+    BoxStager stager{my_smem, 0u};
+    float* cs_s = reinterpret_cast<float*>(my_smem + 2 * EPI_BOX_BYTES);
+    float* sn_s = cs_s + 1024;
+    if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -289,13 +456,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(bar_tfull + acc, acc_phase);
       tc_fence_after();
       TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
-      epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld);
+      if constexpr (kStaged<EPI>)
+        staged_epilogue<EPI>(p, &tmOut, stager, cs_s, sn_s, m_idx * BM + quarter * 32, n_idx, ld, lane);
+      else
+        epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (kStaged<EPI> && lane == 0) bulk_wait<0>();  // all TMA stores / reductions of this warp have landed
   }
 
   tc_fence_before();
@@ -328,6 +499,11 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
   } else {
     CUtensorMap tmA = make_tmap_2d(ctx, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, K, BM, BK);
     CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN, BK);
+    CUtensorMap tmOut = tmA;  // placeholder for the epilogues that write directly
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32)
+      tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
+    else if constexpr (kStaged<EPI>)
+      tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
     static bool attr_set[16] = {};
     if (!attr_set[EPI]) {
       VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -336,7 +512,8 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
     }
     const int total = m_tiles * n_tiles;
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-    gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, m_tiles, n_tiles, k_blocks, p);
+    gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, m_tiles, n_tiles,
+                                                                              k_blocks, p);
   }
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -52,12 +52,12 @@ def gather_and_merge(local_ids: torch.Tensor, local_s64: torch.Tensor, k: int, g
     if world == 1:
         all_i, all_s = local_ids, local_s64
     else:
-        gi = torch.empty((world,) + tuple(local_ids.shape), dtype=local_ids.dtype, device=local_ids.device)
-        gs = torch.empty((world,) + tuple(local_s64.shape), dtype=local_s64.dtype, device=local_s64.device)
-        dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
+        gi = torch.empty((world * Q, k), dtype=local_ids.dtype, device=local_ids.device)
+        gs = torch.empty((world * Q, k), dtype=local_s64.dtype, device=local_s64.device)
+        dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)    # rank r -> rows [r*Q, (r+1)*Q)
         dist.all_gather_into_tensor(gs, local_s64.contiguous(), group=group)
-        all_i = gi.permute(1, 0, 2).reshape(Q, world * k).contiguous()
-        all_s = gs.permute(1, 0, 2).reshape(Q, world * k).contiguous()
+        all_i = gi.view(world, Q, k).permute(1, 0, 2).reshape(Q, world * k).contiguous()
+        all_s = gs.view(world, Q, k).permute(1, 0, 2).reshape(Q, world * k).contiguous()
     if all_i.is_cuda:
         assert ctx is not None, "device merge needs the native context"
         out_i = torch.empty((Q, k), dtype=torch.int64, device=all_i.device)

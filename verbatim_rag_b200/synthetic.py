@@ -120,7 +120,7 @@ def make_modernbert_weights(seed: int = 1001, spec: ModernBertSpec = ModernBertS
 
 
 def make_bert_mlm_weights(seed: int = 1002, spec: BertSpec = BertSpec(),
-                          decoder_bias_sigmas: float = 2.6) -> Dict[str, np.ndarray]:
+                          decoder_bias_sigmas: float = 4.0) -> Dict[str, np.ndarray]:
     """Seeded BERT-MLM weights (HF ``BertForMaskedLM`` names; decoder tied to word embeddings).
 
     The MLM decoder bias is set to ``-decoder_bias_sigmas * sigma_logit`` so the
