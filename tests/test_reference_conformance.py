@@ -1,0 +1,153 @@
+"""Plugin conformance against the reference's REAL orchestration (build container only: needs /root/reference).
+
+The B200 plugin classes are plugged into the unmodified ``VerbatimIndex`` / ``VerbatimRAG`` imported from
+/root/reference.  There is no GPU here and no reference on the GPU box, so the native handles are replaced by the
+oracle-backed fakes of tests/fake_native.py: everything ABOVE the C ABI (the code a reference user actually touches)
+runs for real -- tokenisation, windowing, payload handling, query branches, result shaping -- and is compared with the
+reference-shaped oracle plugins (oracle/plugins.py) driven through the same reference classes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture()
+def ref_env(reference_pkgs, monkeypatch):
+    import importlib
+    import fake_native
+    # re-import interfaces so the plugin classes subclass the reference's own ABCs
+    for m in ["verbatim_rag_b200.interfaces", "verbatim_rag_b200.extractor", "verbatim_rag_b200.providers",
+              "verbatim_rag_b200.vector_store"]:
+        sys.modules.pop(m, None)
+    interfaces = importlib.import_module("verbatim_rag_b200.interfaces")
+    assert all(interfaces.USING_REFERENCE_ABCS.values()), interfaces.USING_REFERENCE_ABCS
+    fake_native.install(monkeypatch)
+    yield
+    for m in ["verbatim_rag_b200.interfaces", "verbatim_rag_b200.extractor", "verbatim_rag_b200.providers",
+              "verbatim_rag_b200.vector_store", "oracle.plugins"]:
+        sys.modules.pop(m, None)
+
+
+def _small_models():
+    import cases
+    from verbatim_rag_b200.synthetic import (BertSpec, ModernBertSpec, make_bert_mlm_weights, make_modernbert_weights)
+    mspec, bspec = ModernBertSpec(layers=2), BertSpec(layers=1)
+    return (make_modernbert_weights(5, mspec), cases.tokenizer("modernbert"), mspec,
+            make_bert_mlm_weights(6, bspec, decoder_bias_sigmas=3.0), cases.tokenizer("bert"), bspec)
+
+
+def test_plugins_subclass_reference_abcs_and_run_verbatim_rag(ref_env):
+    from verbatim_core.extractors import SpanExtractor
+    from verbatim_rag.embedding_providers import SparseEmbeddingProvider
+    from verbatim_rag.vector_stores.base import SearchResult, VectorStore
+    from verbatim_rag import VerbatimIndex, VerbatimRAG
+    from verbatim_rag.schema import DocumentSchema
+    from verbatim_rag_b200 import B200SpanExtractor, B200SpladeProvider, B200VectorStore
+    from oracle.plugins import OracleFlatStore, OracleSpanExtractor, OracleSpladeProvider
+
+    mw, mtok, mspec, bw, btok, bspec = _small_models()
+    ext = B200SpanExtractor(weights=mw, tokenizer=mtok, num_layers=mspec.layers, vocab_size=mspec.vocab_size)
+    prov = B200SpladeProvider(weights=bw, tokenizer=btok, num_layers=bspec.layers, vocab_size=bspec.vocab_size)
+    store = B200VectorStore(enable_dense=False, enable_sparse=True)
+    assert isinstance(ext, SpanExtractor) and isinstance(prov, SparseEmbeddingProvider) and isinstance(store, VectorStore)
+
+    rng = np.random.default_rng(3)
+    docs = [DocumentSchema(content="\n\n".join(btok.make_text(rng, 60) for _ in range(3)), title=f"doc {i}")
+            for i in range(4)]
+    question = btok.make_question(rng, 6)
+
+    def build(vector_store, sparse_provider, extractor):
+        index = VerbatimIndex(vector_store=vector_store, sparse_provider=sparse_provider)
+        index.add_documents(docs)
+        rag = VerbatimRAG(index, extractor=extractor, k=3, template_mode="static")
+        return index, rag
+
+    index, rag = build(store, prov, ext)
+    o_index, o_rag = build(OracleFlatStore(enable_dense=False, enable_sparse=True, sparse_dim=bspec.vocab_size),
+                           OracleSpladeProvider(bw, btok, bspec),
+                           OracleSpanExtractor(mw, mtok, mspec))
+    got = index.query(text=question, k=3)
+    exp = o_index.query(text=question, k=3)
+    assert [r.text for r in got] == [r.text for r in exp]          # ids are uuid4 per ingest: compare payloads
+    assert np.allclose([r.score for r in got], [r.score for r in exp], atol=1e-6)
+    assert all(isinstance(r, SearchResult) for r in got)
+
+    resp = rag.query(question)
+    o_resp = o_rag.query(question)
+    assert resp.answer == o_resp.answer
+    got_h = [[(h.start, h.end) for h in d.highlights] for d in resp.documents]
+    exp_h = [[(h.start, h.end) for h in d.highlights] for d in o_resp.documents]
+    assert got_h == exp_h
+
+    # the extractor contract on the same retrieved chunks: identical dict (keys = chunk text, values = verbatim spans)
+    spans = ext.extract_spans(question, got)
+    o_spans = OracleSpanExtractor(mw, mtok, mspec).extract_spans(question, got)
+    assert spans == o_spans
+    for text, sp in spans.items():
+        assert all(s in text for s in sp)
+    # empty / whitespace contexts yield [] without a model call (extractors.py:209-211)
+    class R:  # noqa: D401
+        def __init__(self, t):
+            self.text = t
+    assert ext.extract_spans(question, [R(""), R("   ")]) == {"": [], "   ": []}
+
+
+def test_vector_store_branches_match_reference_semantics(ref_env):
+    from verbatim_rag_b200 import B200VectorStore
+    from oracle.plugins import OracleFlatStore
+    rng = np.random.default_rng(0)
+    n, dim = 40, 768
+    dense = rng.standard_normal((n, dim)).astype(np.float32)
+    sparse = [{int(t): float(abs(v) + 0.05) for t, v in zip(rng.choice(30522, 20, replace=False), rng.standard_normal(20))}
+              for _ in range(n)]
+    ids = [f"c{i:03d}" for i in range(n)]
+    texts = [f"text {i}" for i in range(n)]
+    metas = [{"document_id": f"d{i % 4}", "year": 2020 + i % 5} for i in range(n)]
+    store = B200VectorStore(dense_dim=dim, enable_dense=True, enable_sparse=True)
+    ora = OracleFlatStore(dense_dim=dim)
+    for s in (store, ora):
+        s.add_vectors(ids, dense.tolist(), sparse, texts, texts, metas)
+    dq = rng.standard_normal(dim).astype(np.float32).tolist()
+    sq = {k: 1.0 for k in list(sparse[3])[:8]}
+    for st in ("dense", "sparse", "hybrid"):
+        a = store.query(dense_query=dq, sparse_query=sq, top_k=5, search_type=st, rrf_k=60, search_params=None)
+        b = ora.query(dense_query=dq, sparse_query=sq, top_k=5, search_type=st, rrf_k=60)
+        assert [r.id for r in a] == [r.id for r in b], st
+        assert np.allclose([r.score for r in a], [r.score for r in b], atol=1e-6)
+    assert store.query(dense_query=dq, sparse_query=sq, top_k=3, search_type="dense")[0].metadata["document_id"].startswith("d")
+    with pytest.raises(ValueError):
+        store.query(dense_query=dq, top_k=3, search_type="sparse")
+    # N-way weighted hybrid (milvus_base.py:366-459) with a single available method degrades to that method
+    w = store.query(dense_query=dq, top_k=4, hybrid_weights={"dense": 2.0, "full_text": 1.0})
+    assert [r.id for r in w] == [r.id for r in store.query(dense_query=dq, top_k=4, search_type="dense")]
+    # filter-only browse: score 1.0, limit, promoted field filter
+    br = store.query(top_k=7)
+    assert len(br) == 7 and all(r.score == 1.0 for r in br)
+    assert {r.metadata["document_id"] for r in store.query(top_k=50, filter='document_id == "d1"')} == {"d1"}
+    assert all(r.metadata["year"] >= 2023 for r in store.query(top_k=50, filter='metadata["year"] >= 2023'))
+    # delete: rows vanish from search and browse
+    top = store.query(dense_query=dq, top_k=1, search_type="dense")[0].id
+    store.delete([top])
+    assert top not in [r.id for r in store.query(dense_query=dq, top_k=40, search_type="dense")]
+    assert len(store) == n - 1
+    with pytest.raises(ValueError):
+        B200VectorStore(enable_dense=False, enable_sparse=False)
+
+
+def test_provider_output_types(ref_env):
+    from verbatim_rag_b200 import B200SpladeProvider
+    _, _, _, bw, btok, bspec = _small_models()
+    prov = B200SpladeProvider(weights=bw, tokenizer=btok, num_layers=bspec.layers, vocab_size=bspec.vocab_size)
+    rng = np.random.default_rng(1)
+    texts = [btok.make_text(rng, n) for n in (12, 40, 700)]      # the last one is truncated to 512 tokens
+    batch = prov.embed_batch(texts)
+    one = prov.embed_text(texts[0])
+    assert prov.get_dimension() == bspec.vocab_size
+    assert all(type(k) is int and type(v) is float for d in batch for k, v in d.items())
+    assert set(one) <= set(batch[0]) and all(abs(v) > 1e-6 for v in one.values())

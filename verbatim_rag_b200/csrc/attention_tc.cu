@@ -95,7 +95,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_2d(sQ, &tmQ, bar_q, head * AD, s0 + q0);
       for (int i = 0; i < nb; ++i) {
         const int st = i & 1;
-        mbar_wait(kv_empty + st, ((i >> 1) & 1) ^ 1);
+        mbar_wait_tagged(kv_empty + st, ((i >> 1) & 1) ^ 1, 3);
         mbar_arrive_expect_tx(kv_full + st, 2 * SKV_BYTES);
         const int row = s0 + (j_lo + i) * AK;
         tma_load_2d(sKV + st * 2 * SKV_BYTES, &tmKV, kv_full + st, hidden + head * AD, row);
@@ -107,11 +107,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
       constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
-      mbar_wait(bar_q, 0);
+      mbar_wait_tagged(bar_q, 0, 1);
       auto issue_s = [&](int i) {
         const int st = i & 1;
-        mbar_wait(kv_full + st, (i >> 1) & 1);
-        mbar_wait(s_empty + st, ((i >> 1) & 1) ^ 1);
+        mbar_wait_tagged(kv_full + st, (i >> 1) & 1, 2);
+        mbar_wait_tagged(s_empty + st, ((i >> 1) & 1) ^ 1, 5);
         tc_fence_after();
         const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
 #pragma unroll
@@ -123,7 +123,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       issue_s(0);
       for (int i = 0; i < nb; ++i) {
         if (i + 1 < nb) issue_s(i + 1);
-        mbar_wait(p_full, i & 1);
+        mbar_wait_tagged(p_full, i & 1, 6);
         tc_fence_after();
         const int st = i & 1;
         const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
@@ -146,7 +146,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
 
     auto fold = [&](int i_done) {  // O = O * alpha + PV_{i_done}
-      mbar_wait(pv_done, i_done & 1);
+      mbar_wait_tagged(pv_done, i_done & 1, 7);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < AD / 16; ++h) {
@@ -161,7 +161,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < nb; ++i) {
       if (i > 0) fold(i - 1);
       const int st = i & 1;
-      mbar_wait(s_full + st, (i >> 1) & 1);
+      mbar_wait_tagged(s_full + st, (i >> 1) & 1, 4);
       tc_fence_after();
       float s[AK];
       {

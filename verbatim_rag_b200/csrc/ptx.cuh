@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace vrag {
 
@@ -50,6 +51,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+
+// Bounded wait for bring-up: after ~2^22 failed probes print which barrier is stuck and trap (a protocol bug then
+// costs an error message instead of a hung GPU).
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("[vrag] mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x,
+         blockIdx.y, blockIdx.z, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_tagged(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && spins > (1u << 22)) mbar_timeout(tag, parity);
+  }
 }
 
 // ------------------------------------------------------------------ TMA

@@ -133,6 +133,121 @@ dense_scan_kernel(const float* __restrict__ rows, int64_t n, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------- dense: scan, TMA-bulk streamed
+// The corpus is row-major contiguous, so 16 rows are ONE contiguous block: a producer thread streams such blocks
+// with cp.async.bulk (1D TMA, no registers, up to ~190 KB in flight per SM) into an mbarrier ring; 8 consumer warps
+// take 2 rows each per block, read them from smem as conflict-free float4 and keep the queries in registers
+// (NQ <= 4) or in smem (NQ = 8).  Bytes in flight no longer depend on register allocation / occupancy.
+constexpr int SCAN_ROWS = 16;
+constexpr int SCAN_CONSUMER_WARPS = 8;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int VEC, int NQ>  // dim = VEC * 128; NQ queries handled per corpus pass
+__global__ void __launch_bounds__(32 * (SCAN_CONSUMER_WARPS + 1), 1)
+dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __restrict__ queries,
+                      const float* __restrict__ inv_norm_d, const float* __restrict__ inv_norm_q,
+                      const uint8_t* __restrict__ deleted, float* __restrict__ scores, int nstage, int nq) {
+  constexpr int DIM = VEC * 128;
+  constexpr uint32_t STAGE_BYTES = SCAN_ROWS * DIM * 4;
+  extern __shared__ __align__(128) uint8_t scan_smem[];
+  uint8_t* stage0 = scan_smem;
+  float4* sq = reinterpret_cast<float4*>(scan_smem + static_cast<size_t>(nstage) * STAGE_BYTES);  // [NQ][VEC*32]
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sq) + NQ * DIM * 4);
+  uint64_t* empty = full + nstage;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nblocks = (n + SCAN_ROWS - 1) / SCAN_ROWS;
+
+  for (int i = threadIdx.x; i < NQ * VEC * 32; i += blockDim.x)
+    sq[i] = (i / (VEC * 32)) < nq ? reinterpret_cast<const float4*>(queries)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, SCAN_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == SCAN_CONSUMER_WARPS) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const int64_t r0 = b * SCAN_ROWS;
+        const int64_t rows_here = (n - r0) < SCAN_ROWS ? (n - r0) : SCAN_ROWS;
+        const uint32_t bytes = static_cast<uint32_t>(rows_here) * DIM * 4;
+        mbar_wait(empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(full + st, bytes);
+        bulk_load_1d(stage0 + static_cast<size_t>(st) * STAGE_BYTES, rows + r0 * DIM, bytes, full + st);
+        if (++st == nstage) { st = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  float4 qr[NQ <= 4 ? NQ : 1][VEC];
+  if (NQ <= 4) {
+#pragma unroll
+    for (int qi = 0; qi < (NQ <= 4 ? NQ : 1); ++qi)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qr[qi][i] = sq[qi * VEC * 32 + i * 32 + lane];
+  }
+  float qn[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) qn[qi] = qi < nq ? inv_norm_q[qi] : 0.f;
+
+  int st = 0;
+  uint32_t ph = 0;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    mbar_wait(full + st, ph);
+    const float4* blk = reinterpret_cast<const float4*>(stage0 + static_cast<size_t>(st) * STAGE_BYTES);
+    float acc[2][NQ];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) acc[rr][qi] = 0.f;
+    const float4* r0p = blk + (warp * 2) * (VEC * 32);
+    const float4* r1p = r0p + VEC * 32;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 a = r0p[i * 32 + lane], c = r1p[i * 32 + lane];
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        const float4 qv = NQ <= 4 ? qr[NQ <= 4 ? qi : 0][i] : sq[qi * VEC * 32 + i * 32 + lane];
+        acc[0][qi] += (a.x * qv.x + a.y * qv.y) + (a.z * qv.z + a.w * qv.w);
+        acc[1][qi] += (c.x * qv.x + c.y * qv.y) + (c.z * qv.z + c.w * qv.w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);  // this warp is done reading the stage
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) acc[rr][qi] = warp_sum(acc[rr][qi]);
+    // lane k < 2*NQ writes (row k / NQ, query k % NQ)
+    float mine = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi)
+        if (lane == rr * NQ + qi) mine = acc[rr][qi] * qn[qi];
+    if (lane < 2 * NQ) {
+      const int64_t row = b * SCAN_ROWS + warp * 2 + lane / NQ;
+      if (row < n && (lane % NQ) < nq) {
+        const float v = deleted[row] ? -INFINITY : mine * inv_norm_d[row];
+        scores[static_cast<size_t>(lane % NQ) * n + row] = v;
+      }
+    }
+    if (++st == nstage) { st = 0; ph ^= 1; }
+  }
+}
+
 // generic dimension (dim % 4 == 0): one warp per row, queries read from global/L1
 __global__ void __launch_bounds__(256)
 dense_scan_generic_kernel(const float* __restrict__ rows, int64_t n, int dim, const float* __restrict__ queries,
@@ -635,20 +750,40 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
     {
-    ProfScope prof(_ctx, PROF_SCAN);
-#define VRAG_SCAN(V)                                                                                            \
-  dense_scan_kernel<V><<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, qt, nt, idx->inv32.as<float>(), \
-                                                        qn, idx->deleted.as<uint8_t>(), idx->scores.as<float>())
-    if (dim == 768) VRAG_SCAN(6);
-    else if (dim == 384) VRAG_SCAN(3);
-    else if (dim == 1024) VRAG_SCAN(8);
-    else
-      dense_scan_generic_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, dim, qt, nt,
-                                                                idx->inv32.as<float>(), qn,
-                                                                idx->deleted.as<uint8_t>(), idx->scores.as<float>());
-#undef VRAG_SCAN
-    VRAG_CUDA(cudaGetLastError());
-    _ctx->launches++;
+      ProfScope prof(_ctx, PROF_SCAN);
+      if (dim == 768 || dim == 384 || dim == 1024) {
+        const int nqt = nt <= 1 ? 1 : (nt <= 2 ? 2 : (nt <= 4 ? 4 : 8));
+        const int stage_bytes = SCAN_ROWS * dim * 4;
+        const int q_bytes = nqt * dim * 4;
+        const int nstage = std::max(2, std::min(4, (200 * 1024 - q_bytes) / stage_bytes));
+        const int smem = nstage * stage_bytes + q_bytes + 2 * nstage * 8 + 16;
+        const int tgrid = static_cast<int>(std::min<int64_t>((n + SCAN_ROWS - 1) / SCAN_ROWS, _ctx->num_sms));
+#define VRAG_SCAN_T(V, Q)                                                                                          \
+  do {                                                                                                             \
+    VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tma_kernel<V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    dense_scan_tma_kernel<V, Q><<<tgrid, 32 * (SCAN_CONSUMER_WARPS + 1), smem, _ctx->stream>>>(                     \
+        idx->rows.as<float>(), n, qt, idx->inv32.as<float>(), qn, idx->deleted.as<uint8_t>(),                       \
+        idx->scores.as<float>(), nstage, nt);                                                                      \
+  } while (0)
+#define VRAG_SCAN_Q(V)                                \
+  do {                                                \
+    if (nqt == 1) VRAG_SCAN_T(V, 1);                  \
+    else if (nqt == 2) VRAG_SCAN_T(V, 2);             \
+    else if (nqt == 4) VRAG_SCAN_T(V, 4);             \
+    else VRAG_SCAN_T(V, 8);                           \
+  } while (0)
+        if (dim == 768) VRAG_SCAN_Q(6);
+        else if (dim == 384) VRAG_SCAN_Q(3);
+        else VRAG_SCAN_Q(8);
+#undef VRAG_SCAN_Q
+#undef VRAG_SCAN_T
+      } else {
+        dense_scan_generic_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, dim, qt, nt,
+                                                                  idx->inv32.as<float>(), qn,
+                                                                  idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+      }
+      VRAG_CUDA(cudaGetLastError());
+      _ctx->launches++;
     }
     select_and_rank(idx, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
                     d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
