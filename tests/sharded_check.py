@@ -1,0 +1,55 @@
+"""torchrun worker: row-sharded dense + sparse top-k over NCCL must equal the unsharded search bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from verbatim_rag_b200 import _native  # noqa: E402
+from verbatim_rag_b200.distributed import shard_bounds, sharded_search_dense, sharded_search_sparse  # noqa: E402
+from verbatim_rag_b200.synthetic import make_dense_corpus, make_dense_queries, make_sparse_rows  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = _native.default_context(local)
+    n, k = 60001, 10
+    corpus = make_dense_corpus(n, 768, seed=1004)
+    corpus[5] = corpus[n - 7]                      # an exact tie across shards
+    queries = make_dense_queries(24, 768, seed=2004)
+    lo, hi = shard_bounds(n, rank, world)
+    shard = _native.Index(ctx, _native.INDEX_DENSE_COSINE, 768)
+    shard.set_id_base(lo)
+    shard.add_dense(corpus[lo:hi])
+    ids, s32, s64 = sharded_search_dense(shard, torch.from_numpy(queries).to(dev), k)
+    full = _native.Index(ctx, _native.INDEX_DENSE_COSINE, 768)
+    full.add_dense(corpus)
+    fid, fs32, fs64 = full.search_dense(queries, k, want64=True)
+    assert np.array_equal(ids.cpu().numpy(), fid), "dense ids differ"
+    assert np.array_equal(s64.cpu().numpy(), fs64), "dense fp64 scores differ"
+
+    ip, ix, vl = make_sparse_rows(8000, seed=1002)
+    qip, qix, qvl = make_sparse_rows(16, seed=2002, query=True)
+    lo, hi = shard_bounds(8000, rank, world)
+    ss = _native.Index(ctx, _native.INDEX_SPARSE_IP, 30522)
+    ss.set_id_base(lo)
+    ss.add_sparse(ip[lo:hi + 1], ix, vl)
+    sid, _, sd = sharded_search_sparse(ss, qip, qix, qvl, k, dev)
+    fsx = _native.Index(ctx, _native.INDEX_SPARSE_IP, 30522)
+    fsx.add_sparse(ip, ix, vl)
+    rid, _, rd = fsx.search_sparse(qip, qix, qvl, k, want64=True)
+    assert np.array_equal(sid.cpu().numpy(), rid), "sparse ids differ"
+    assert np.array_equal(sd.cpu().numpy(), rd), "sparse fp64 scores differ"
+    dist.barrier()
+    if rank == 0:
+        print("SHARDED_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

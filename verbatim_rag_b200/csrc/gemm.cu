@@ -1,7 +1,7 @@
 // tcgen05 GEMM for sm_100a: persistent, warp-specialised.
 //   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes into a 4-stage smem ring)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma 128x256x16, fp32 accumulators in TMEM)
-//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> fused tail -> swizzled smem box ->
+//   warps 2..9  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> fused tail -> swizzled smem box ->
 //                                 TMA store, or TMA reduce-add for the fp32 residual stream: x += acc happens in
 //                                 the memory system, the SM never reads x)
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
@@ -18,11 +18,14 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-// per epilogue warp: two 4 KB TMA-store boxes (32 rows x 128 B, SWIZZLE_128B) + cos/sin rows of its 32 tokens
+// per epilogue warp: two 4 KB TMA-store boxes (32 rows x 128 B, SWIZZLE_128B); the RoPE epilogue also borrows them
+// to transpose the cos/sin rows of its 32 tokens into registers
 constexpr int EPI_BOX_BYTES = 4096;
-constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES + 2 * 4096;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
+                              // scheduler cannot hide its own ALU / TMEM-load latency, two can
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -75,13 +78,14 @@ struct ReferenceLoader {  // SIMT dot products (debug / self test)
 
 // The fused tail for one thread == one output row of one 128x256 tile.  All 32 lanes of a warp call this together.
 template <int EPI, typename Loader>
-__device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, int n_tile, const Loader& ld) {
+__device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, int n_tile, const Loader& ld,
+                                             int c_begin = 0, int c_end = BN / 32) {
   const bool valid = row < p.M;
   const int col0 = n_tile * BN;
   float v[32];
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
       if constexpr (EPI != EPI_F16) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
@@ -99,7 +103,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
     }
   } else if constexpr (EPI == EPI_F32 || EPI == EPI_GELU_F32 || EPI == EPI_BIAS_GELU_F32) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
       if constexpr (EPI == EPI_BIAS_GELU_F32) {
 #pragma unroll
@@ -113,7 +117,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
     }
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
       if (valid) {
         float4* x4 = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32);
@@ -177,7 +181,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
     const bool uniform = __all_sync(0xffffffffu, seq == seq0) && seq0 >= 0;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
       const int cbase = col0 + c * 32;
       if (cbase >= p.n_valid) continue;  // warp-uniform
@@ -252,14 +256,13 @@ __device__ __forceinline__ void box_put_float32(uint8_t* box, int r, const float
 
 template <int EPI>
 __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st,
-                                                float* cs_s, float* sn_s, int m0, int n_tile, const TmemLoader& ld,
-                                                int lane) {
+                                                int m0, int n_tile, const TmemLoader& ld, int lane, int half) {
   const int col0 = n_tile * BN;
   const int r = lane;  // row of this thread inside the warp's 32-row slab
   float v[32];
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll 1
-    for (int b = 0; b < BN / 64; ++b) {
+    for (int b = 2 * half; b < 2 * half + 2; ++b) {
       uint8_t* box = st.acquire(lane);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -282,12 +285,16 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
     }
   } else if constexpr (EPI == EPI_ROPE_QKV) {
     const bool rotate = col0 < 2 * p.hidden;  // q / k tiles
+    float cs[32], sn[32];                     // this thread's (row's) cos / sin, kept in registers for the 4 heads
     if (rotate) {
-      // stage cos/sin rows of this warp's 32 tokens: coalesced 128-byte reads, swizzled so thread == row reads are
-      // conflict free
+      // Borrow the warp's two store boxes as a transpose buffer: coalesced 128-byte reads of the 32 tokens'
+      // cos / sin rows, swizzled so the thread == row read-back is conflict free.
+      if (lane == 0) bulk_wait_read<0>();     // no TMA store may still be reading the boxes
+      __syncwarp();
+      float* cs_s = reinterpret_cast<float*>(st.base);
+      float* sn_s = reinterpret_cast<float*>(st.base + EPI_BOX_BYTES);
       const int row = m0 + lane;
       const int my_pos = row < p.M ? __ldg(p.pos + row) : 0;
-      __syncwarp();
 #pragma unroll 4
       for (int rr = 0; rr < 32; ++rr) {
         const int ps = __shfl_sync(0xffffffffu, my_pos, rr);
@@ -296,25 +303,28 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
         sn_s[o] = __ldg(p.rope_sin + static_cast<size_t>(ps) * 32 + lane);
       }
       __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 c = *reinterpret_cast<const float4*>(cs_s + r * 32 + ((i ^ (r & 7)) << 2));
+        const float4 s4 = *reinterpret_cast<const float4*>(sn_s + r * 32 + ((i ^ (r & 7)) << 2));
+        cs[4 * i] = c.x; cs[4 * i + 1] = c.y; cs[4 * i + 2] = c.z; cs[4 * i + 3] = c.w;
+        sn[4 * i] = s4.x; sn[4 * i + 1] = s4.y; sn[4 * i + 2] = s4.z; sn[4 * i + 3] = s4.w;
+      }
+      __syncwarp();
+      st.issued = 0;                          // both boxes are free again; restart the double-buffer bookkeeping
     }
     float w2[32];
 #pragma unroll 1
-    for (int h = 0; h < BN / 64; ++h) {
+    for (int h = 2 * half; h < 2 * half + 2; ++h) {
       uint8_t* box = st.acquire(lane);
       ld.load(2 * h, v);
       ld.load(2 * h + 1, w2);
       if (rotate) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 c = *reinterpret_cast<const float4*>(cs_s + r * 32 + ((i ^ (r & 7)) << 2));
-          const float4 s = *reinterpret_cast<const float4*>(sn_s + r * 32 + ((i ^ (r & 7)) << 2));
-          const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x1 = v[4 * i + e], x2 = w2[4 * i + e];
-            v[4 * i + e] = x1 * cc[e] - x2 * ss[e];
-            w2[4 * i + e] = x2 * cc[e] + x1 * ss[e];
-          }
+        for (int e = 0; e < 32; ++e) {
+          const float x1 = v[e], x2 = w2[e];
+          v[e] = x1 * cs[e] - x2 * sn[e];
+          w2[e] = x2 * cs[e] + x1 * sn[e];
         }
       }
       box_put_half32(box, r, 0, v);
@@ -324,7 +334,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   } else if constexpr (EPI == EPI_GEGLU) {
     float g[32];
 #pragma unroll 1
-    for (int b = 0; b < 2; ++b) {
+    for (int b = half; b < half + 1; ++b) {
       uint8_t* box = st.acquire(lane);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -338,7 +348,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
     }
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 4 * half; c < 4 * half + 4; ++c) {
       uint8_t* box = st.acquire(lane);
       ld.load(c, v);
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -363,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(epi_smem + 4 * EPI_WARP_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_WARP_BYTES);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
@@ -380,7 +390,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + a, 1);
-      mbar_init(bar_tempty + a, 4);
+      mbar_init(bar_tempty + a, EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -443,11 +453,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's 256 columns this warp drains
     uint8_t* my_smem = epi_smem + (warp - 2) * EPI_WARP_BYTES;
     BoxStager stager{my_smem, 0u};
-    float* cs_s = reinterpret_cast<float*>(my_smem + 2 * EPI_BOX_BYTES);
-    float* sn_s = cs_s + 1024;
     if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -457,9 +466,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
       if constexpr (kStaged<EPI>)
-        staged_epilogue<EPI>(p, &tmOut, stager, cs_s, sn_s, m_idx * BM + quarter * 32, n_idx, ld, lane);
+        staged_epilogue<EPI>(p, &tmOut, stager, m_idx * BM + quarter * 32, n_idx, ld, lane, half);
       else
-        epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld);
+        epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld, 4 * half, 4 * half + 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + acc);

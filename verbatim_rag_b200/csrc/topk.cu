@@ -134,12 +134,13 @@ dense_scan_kernel(const float* __restrict__ rows, int64_t n, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------- dense: scan, TMA-bulk streamed
-// The corpus is row-major contiguous, so 16 rows are ONE contiguous block: a producer thread streams such blocks
+// The corpus is row-major contiguous, so 32 rows are ONE contiguous block: a producer thread streams such blocks
 // with cp.async.bulk (1D TMA, no registers, up to ~190 KB in flight per SM) into an mbarrier ring; 8 consumer warps
-// take 2 rows each per block, read them from smem as conflict-free float4 and keep the queries in registers
+// take 4 rows each per block, read them from smem as conflict-free float4 and keep the queries in registers
 // (NQ <= 4) or in smem (NQ = 8).  Bytes in flight no longer depend on register allocation / occupancy.
-constexpr int SCAN_ROWS = 16;
+constexpr int SCAN_ROWS = 32;
 constexpr int SCAN_CONSUMER_WARPS = 8;
+constexpr int RW = SCAN_ROWS / SCAN_CONSUMER_WARPS;  // rows per consumer warp per block
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -198,51 +199,55 @@ dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __
 #pragma unroll
       for (int i = 0; i < VEC; ++i) qr[qi][i] = sq[qi * VEC * 32 + i * 32 + lane];
   }
-  float qn[NQ];
-#pragma unroll
-  for (int qi = 0; qi < NQ; ++qi) qn[qi] = qi < nq ? inv_norm_q[qi] : 0.f;
-
   int st = 0;
   uint32_t ph = 0;
   for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
     mbar_wait(full + st, ph);
     const float4* blk = reinterpret_cast<const float4*>(stage0 + static_cast<size_t>(st) * STAGE_BYTES);
-    float acc[2][NQ];
+    float acc[RW * NQ];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int qi = 0; qi < NQ; ++qi) acc[rr][qi] = 0.f;
-    const float4* r0p = blk + (warp * 2) * (VEC * 32);
-    const float4* r1p = r0p + VEC * 32;
+    for (int i = 0; i < RW * NQ; ++i) acc[i] = 0.f;
+    const float4* rp = blk + (warp * RW) * (VEC * 32) + lane;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 a = r0p[i * 32 + lane], c = r1p[i * 32 + lane];
+      float4 d[RW];
+#pragma unroll
+      for (int rr = 0; rr < RW; ++rr) d[rr] = rp[rr * (VEC * 32) + i * 32];
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
         const float4 qv = NQ <= 4 ? qr[NQ <= 4 ? qi : 0][i] : sq[qi * VEC * 32 + i * 32 + lane];
-        acc[0][qi] += (a.x * qv.x + a.y * qv.y) + (a.z * qv.z + a.w * qv.w);
-        acc[1][qi] += (c.x * qv.x + c.y * qv.y) + (c.z * qv.z + c.w * qv.w);
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr)
+          acc[rr * NQ + qi] += (d[rr].x * qv.x + d[rr].y * qv.y) + (d[rr].z * qv.z + d[rr].w * qv.w);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + st);  // this warp is done reading the stage
+    // Transposing butterfly: NV = RW*NQ partial sums per lane -> lane l ends with the full sum of value
+    // (l >> (5 - log2 NV)); NV - 1 + (5 - log2 NV) shuffles instead of 5 * NV.
+    constexpr int NV = RW * NQ;
+    int off = 16;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
+    for (int cnt = NV / 2; cnt >= 1; cnt >>= 1) {
+      const bool upper = (lane & off) != 0;
 #pragma unroll
-      for (int qi = 0; qi < NQ; ++qi) acc[rr][qi] = warp_sum(acc[rr][qi]);
-    // lane k < 2*NQ writes (row k / NQ, query k % NQ)
-    float mine = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int qi = 0; qi < NQ; ++qi)
-        if (lane == rr * NQ + qi) mine = acc[rr][qi] * qn[qi];
-    if (lane < 2 * NQ) {
-      const int64_t row = b * SCAN_ROWS + warp * 2 + lane / NQ;
-      if (row < n && (lane % NQ) < nq) {
-        const float v = deleted[row] ? -INFINITY : mine * inv_norm_d[row];
-        scores[static_cast<size_t>(lane % NQ) * n + row] = v;
+      for (int i = 0; i < cnt; ++i) {
+        const float send = upper ? acc[i] : acc[i + cnt];
+        const float keep = upper ? acc[i + cnt] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
+      off >>= 1;
+    }
+    float total = acc[0];
+#pragma unroll
+    for (int o2 = 16 / NV; o2 >= 1; o2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o2);
+    constexpr int GROUP = 32 / NV;  // lanes holding the same value
+    if ((lane % GROUP) == 0) {
+      const int idx = lane / GROUP, rr = idx / NQ, qi = idx % NQ;
+      const int64_t row = b * SCAN_ROWS + warp * RW + rr;
+      if (row < n && qi < nq)
+        scores[static_cast<size_t>(qi) * n + row] =
+            deleted[row] ? -INFINITY : total * inv_norm_q[qi] * inv_norm_d[row];
     }
     if (++st == nstage) { st = 0; ph ^= 1; }
   }
@@ -396,6 +401,65 @@ select_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ key
   }
 }
 
+// kp <= 32 (k <= 16, the common case): the warp's sorted list lives in REGISTERS, one key per lane (lane j holds the
+// j-th best).  An insertion is one ballot + one 64-bit shuffle, no shared memory round trips.
+__device__ __forceinline__ uint64_t reg_list_insert(uint64_t mine, uint64_t x, int kp, int lane) {
+  const int pos = __popc(__ballot_sync(0xffffffffu, mine > x));  // sorted descending: lanes [0,pos) hold keys > x
+  const uint64_t up = __shfl_up_sync(0xffffffffu, mine, 1);
+  if (lane == pos) mine = x;
+  else if (lane > pos) mine = up;
+  return lane < kp ? mine : 0;
+}
+
+template <bool FROM_SCORES>
+__global__ void __launch_bounds__(32 * SEL_WARPS)
+select_reg_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int kp,
+                  uint64_t* __restrict__ keys_out /* [nq][gridDim.x][kp] */) {
+  __shared__ uint64_t lists[SEL_WARPS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.y;
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = per_block * blockIdx.x, b1 = min(n, b0 + per_block);
+  const int64_t per_warp = (b1 - b0 + SEL_WARPS - 1) / SEL_WARPS;
+  const int64_t w0 = b0 + per_warp * warp, w1 = min(b1, w0 + per_warp);
+  uint64_t mine = 0, thr = 0;
+  for (int64_t i0 = w0; i0 < w1; i0 += 32) {
+    const int64_t i = i0 + lane;
+    uint64_t key = 0;
+    if (i < w1) {
+      if (FROM_SCORES) {
+        const float s = scores[static_cast<size_t>(q) * n + i];
+        key = (s == -INFINITY) ? 0 : make_key(s, static_cast<uint32_t>(i));
+      } else {
+        key = keys_in[static_cast<size_t>(q) * n + i];
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, key > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t x = __shfl_sync(0xffffffffu, key, src);
+      if (x > thr) {
+        mine = reg_list_insert(mine, x, kp, lane);
+        thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+      }
+    }
+  }
+  lists[warp][lane] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < SEL_WARPS; ++w) {
+      for (int j = 0; j < kp; ++j) {
+        const uint64_t x = lists[w][j];
+        if (x <= thr) break;  // sorted descending
+        mine = reg_list_insert(mine, x, kp, lane);
+        thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+      }
+    }
+    if (lane < kp) keys_out[(static_cast<size_t>(q) * gridDim.x + blockIdx.x) * kp + lane] = mine;
+  }
+}
+
 // ---------------------------------------------------------------------------------- rescore (fp64)
 __global__ void __launch_bounds__(256)
 dense_rescore_kernel(const float* __restrict__ rows, int dim, const double* __restrict__ norm64,
@@ -540,7 +604,8 @@ void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float
   vrag_ctx* ctx = ix->ctx;
   const int64_t n = ix->n;
   const int kp = static_cast<int>(std::min<int64_t>(k + MARGIN, std::max<int64_t>(n, 1)));
-  const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, ctx->num_sms * 4)));
+  // 8192 scores per block (1024 per warp list): list insertions stay a small fraction of the streaming compares
+  const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 8191) / 8192, ctx->num_sms * 4)));
   const size_t smem = static_cast<size_t>(SEL_WARPS) * kp * 8;
   static bool smem_attr = false;
   if (!smem_attr) {
@@ -551,14 +616,22 @@ void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float
   ix->keys0.reserve(static_cast<size_t>(nq_tile) * nblk0 * kp * 8);
   ix->keys1.reserve(static_cast<size_t>(nq_tile) * kp * 8);
   ProfScope prof(ctx, PROF_SELECT);
-  select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
-      ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
+  if (kp <= 32)
+    select_reg_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, 0, ctx->stream>>>(
+        ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
+  else
+    select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
+        ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
   const uint64_t* final_keys = ix->keys0.as<uint64_t>();
   if (nblk0 > 1) {
-    select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
-        nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
+    if (kp <= 32)
+      select_reg_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, 0, ctx->stream>>>(
+          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
+    else
+      select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
+          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
     VRAG_CUDA(cudaGetLastError());
     ctx->launches++;
     final_keys = ix->keys1.as<uint64_t>();
@@ -751,11 +824,12 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     const float* qn = idx->qnorm.as<float>() + q0;
     {
       ProfScope prof(_ctx, PROF_SCAN);
-      if (dim == 768 || dim == 384 || dim == 1024) {
+      // two 32-row stages + the query block must fit in 227 KB of shared memory (dim 1024 does not: generic path)
+      if ((dim == 768 || dim == 384) || (dim == 1024 && 2 * SCAN_ROWS * dim * 4 + 8 * dim * 4 < 220 * 1024)) {
         const int nqt = nt <= 1 ? 1 : (nt <= 2 ? 2 : (nt <= 4 ? 4 : 8));
         const int stage_bytes = SCAN_ROWS * dim * 4;
         const int q_bytes = nqt * dim * 4;
-        const int nstage = std::max(2, std::min(4, (200 * 1024 - q_bytes) / stage_bytes));
+        const int nstage = std::max(2, std::min(4, (210 * 1024 - q_bytes) / stage_bytes));
         const int smem = nstage * stage_bytes + q_bytes + 2 * nstage * 8 + 16;
         const int tgrid = static_cast<int>(std::min<int64_t>((n + SCAN_ROWS - 1) / SCAN_ROWS, _ctx->num_sms));
 #define VRAG_SCAN_T(V, Q)                                                                                          \
