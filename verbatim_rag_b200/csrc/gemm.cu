@@ -14,9 +14,9 @@ namespace vrag {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
+constexpr int B_BYTES = (BN / 2) * BK * 2;  // each CTA of the pair holds HALF of the 256-row W tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 // per epilogue warp: two 4 KB TMA-store boxes (32 rows x 128 B, SWIZZLE_128B); the RoPE epilogue also borrows them
 // to transpose the cos/sin rows of its 32 tokens into registers
@@ -365,8 +365,16 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   }
 }
 
+// Launched as clusters of 2 CTAs (an SM pair) that cooperate on one 256 x 256 output tile with
+// tcgen05.mma.cta_group::2: each CTA holds its own 128 rows of A and HALF of the W tile (128 of the 256 N rows) and
+// its own 128 x 256 fp32 accumulator in TMEM.  Per SM and k-block this moves 32 KB into smem and the tensor core reads
+// 32 KB back, instead of 48 + 48 KB for a 1-CTA 128 x 256 tile -- measured, the 1-CTA mainloop saturates the
+// 128 B/clk shared-memory port at ~66 % tensor-pipe activity (profiles/), so operand bytes per flop are the lever.
+// The leader CTA (cluster rank 0) issues the MMAs; both CTAs' TMA loads signal the leader's `full` barrier; the MMA
+// commit is multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator by
+// arriving on the leader's `tmem_empty` barrier.
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, int m_tiles, int n_tiles, int k_blocks,
                     GemmEpiParams p) {
@@ -381,16 +389,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = m_tiles * n_tiles;
+  const int cta_rank = static_cast<int>(cluster_ctarank());      // 0 / 1 inside the CTA pair
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_pairs = ((m_tiles + 1) >> 1) * n_tiles;        // (two M tiles) x (one N tile) per cluster step
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s, 1);
-      mbar_init(bar_empty + s, 1);
+      mbar_init(bar_empty + s, 1);   // the leader's MMA commit (multicast to both CTAs)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + a, 1);
-      mbar_init(bar_tempty + a, EPI_WARPS);
+      mbar_init(bar_tempty + a, 2 * EPI_WARPS);   // leader's barrier: epilogue warps of BOTH CTAs arrive
     }
     fence_mbar_init();
   }
@@ -399,11 +409,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_pair(tmem_holder, TMEM_COLS);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into its smem
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -411,43 +422,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_idx = tile / n_tiles, n_idx = tile % n_tiles;
+      for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+        const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(bar_empty + stage, phase ^ 1);
-          mbar_arrive_expect_tx(bar_full + stage, STAGE_BYTES);
+          mbar_wait_tagged(bar_empty + stage, phase ^ 1, 11);
+          // one barrier in the leader tracks both CTAs' operands: 2 x (A 16 KB + W half 16 KB)
+          if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + stage, 2 * STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA, bar_full + stage, kb * BK, m_idx * BM);
-          tma_load_2d(sa + A_BYTES, &tmB, bar_full + stage, kb * BK, n_idx * BN);
+          tma_load_2d_pair(sa, &tmA, bar_full + stage, kb * BK, m_idx * BM);
+          tma_load_2d_pair(sa + A_BYTES, &tmB, bar_full + stage, kb * BK, n_idx * BN + cta_rank * (BN / 2));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, BM, BN);
+    if (lane == 0 && cta_rank == 0) {   // the leader CTA issues the pair's MMAs
+      constexpr uint32_t idesc = umma_idesc(0 /*f16*/, 2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + acc, acc_phase ^ 1);
+      for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+        mbar_wait_tagged(bar_tempty + acc, acc_phase ^ 1, 12);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(bar_full + stage, phase);
+          mbar_wait_tagged(bar_full + stage, phase, 13);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + stage);  // smem slot reusable once these MMAs retire
+          // slot reusable (in BOTH CTAs) once these MMAs retire
+          umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + acc);      // accumulator complete -> epilogue
+        umma_commit_pair(bar_tfull + acc, static_cast<uint16_t>(3));   // accumulators complete -> both epilogues
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -460,9 +473,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_idx = tile / n_tiles, n_idx = tile % n_tiles;
-      mbar_wait(bar_tfull + acc, acc_phase);
+    for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+      const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
+      mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
       tc_fence_after();
       TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
       if constexpr (kStaged<EPI>)
@@ -471,7 +484,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld, 4 * half, 4 * half + 4);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + acc);
+      if (lane == 0) {
+        if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
+        else mbar_arrive_remote(bar_tempty + acc, 0);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -480,10 +496,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the peer may still multicast into my smem / arrive on my barriers until it is done too
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -507,7 +524,7 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
     gemm_reference_kernel<EPI><<<m_tiles * n_tiles, 128, 0, ctx->stream>>>(A, W, K, n_tiles, p);
   } else {
     CUtensorMap tmA = make_tmap_2d(ctx, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, K, BM, BK);
-    CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN, BK);
+    CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN / 2, BK);  // half W tile
     CUtensorMap tmOut = tmA;  // placeholder for the epilogues that write directly
     if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32)
       tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
@@ -519,8 +536,9 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
                                      SMEM_BYTES));
       attr_set[EPI] = true;
     }
-    const int total = m_tiles * n_tiles;
-    const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+    const int total_pairs = ((m_tiles + 1) / 2) * n_tiles;
+    const int max_clusters = ctx->num_sms / 2;
+    const int grid = 2 * (total_pairs < max_clusters ? total_pairs : max_clusters);   // CTA pairs (clusters of 2)
     gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, m_tiles, n_tiles,
                                                                               k_blocks, p);
   }

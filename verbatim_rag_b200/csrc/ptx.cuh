@@ -62,6 +62,7 @@ static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_tagged(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
         "{\n\t"
@@ -72,7 +73,12 @@ __device__ __forceinline__ void mbar_wait_tagged(uint64_t* bar, uint32_t parity,
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (!done && spins > (1u << 22)) mbar_timeout(tag, parity);
+    if (!done && (spins & 15u) == 15u) {  // wall-clock bound (try_wait itself may block for a while per probe)
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity);  // 2 s
+    }
   }
 }
 
@@ -99,6 +105,60 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUte
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two SMs of a cluster cooperate on one 256-row MMA ----
+// 2D tile load into THIS CTA's smem, completion signalled on the LEADER CTA's mbarrier (same smem offset, rank bit
+// cleared), so one barrier in the leader tracks the operands of both CTAs.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t x,
+                                                 int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y)
+      : "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 split by rows over the CTA pair, B split by N over the pair.
+// Issued by ONE thread of the leader CTA; descriptors hold leader-local smem offsets (identical layout in the peer).
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
