@@ -98,44 +98,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // The producer and MMA loops run in the WHOLE warp (warp-uniform values); only the TMA / MMA / commit instructions
+  // are predicated on one elected lane -- under `if (lane == 0)` every descriptor is a divergent value and each
+  // UTCHMMA / UTMALDG gets wrapped in an ELECT + R2UR waterfall (dozens of extra instructions per MMA).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_q, SQ_BYTES);
       tma_load_2d(sQ, &tmQ, bar_q, head * AD, s0 + q0);
-      for (int i = 0; i < nb; ++i) {
-        const int st = i & 1;
-        mbar_wait_tagged(kv_empty + st, ((i >> 1) & 1) ^ 1, 3);
+    }
+    __syncwarp();
+    for (int i = 0; i < nb; ++i) {
+      const int st = i & 1;
+      mbar_wait_tagged(kv_empty + st, ((i >> 1) & 1) ^ 1, 3);
+      const int row = s0 + (j_lo + i) * AK;
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full + st, 2 * SKV_BYTES);
-        const int row = s0 + (j_lo + i) * AK;
         tma_load_2d(sKV + st * 2 * SKV_BYTES, &tmKV, kv_full + st, hidden + head * AD, row);
         tma_load_2d(sKV + st * 2 * SKV_BYTES + SKV_BYTES, &tmKV, kv_full + st, 2 * hidden + head * AD, row);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
-      constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
-      mbar_wait_tagged(bar_q, 0, 1);
-      auto issue_s = [&](int i) {
-        const int st = i & 1;
-        mbar_wait_tagged(kv_full + st, (i >> 1) & 1, 2);
-        mbar_wait_tagged(s_empty + st, ((i >> 1) & 1) ^ 1, 5);
-        tc_fence_after();
-        const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
+    constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
+    constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
+    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+    mbar_wait_tagged(bar_q, 0, 1);
+    auto issue_s = [&](int i) {
+      const int st = i & 1;
+      mbar_wait_tagged(kv_full + st, (i >> 1) & 1, 2);
+      mbar_wait_tagged(s_empty + st, ((i >> 1) & 1) ^ 1, 5);
+      tc_fence_after();
+      const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AD / 16; ++k)
           umma_f16(tmem_base + st * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
                    k > 0 ? 1u : 0u);
         umma_commit(s_full + st);
-      };
-      issue_s(0);
-      for (int i = 0; i < nb; ++i) {
-        if (i + 1 < nb) issue_s(i + 1);
-        mbar_wait_tagged(p_full, i & 1, 6);
-        tc_fence_after();
-        const int st = i & 1;
-        const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int i = 0; i < nb; ++i) {
+      if (i + 1 < nb) issue_s(i + 1);
+      mbar_wait_tagged(p_full, i & 1, 6);
+      tc_fence_after();
+      const int st = i & 1;
+      const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AK / 16; ++k)  // 16 keys per step = two 8-row groups of the V tile = 2048 bytes
           umma_f16(tmem_base + 2 * AK + (i & 1) * AD, umma_desc_sw128(p_addr + k * 32),
@@ -143,6 +153,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(pv_done);
         umma_commit(kv_empty + st);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;        // TMEM lane quarter

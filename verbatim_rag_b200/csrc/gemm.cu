@@ -218,7 +218,9 @@ struct BoxStager {
   uint8_t* base;      // this warp's two boxes
   uint32_t issued;    // boxes submitted so far (same value in every lane)
   __device__ __forceinline__ uint8_t* acquire(int lane) {
-    if (issued >= 2 && lane == 0) bulk_wait_read<1>();  // the box submitted two steps ago has been read out
+    if (issued >= 2) {                                  // the box submitted two steps ago has been read out
+      if (elect_one()) bulk_wait_read<1>();             // (bulk groups belong to the issuing = elected lane)
+    }
     __syncwarp();
     return base + (issued & 1) * EPI_BOX_BYTES;
   }
@@ -226,7 +228,7 @@ struct BoxStager {
   __device__ __forceinline__ void submit(const CUtensorMap* tm, uint8_t* box, int x, int y, int lane) {
     fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {
       if (REDUCE) tma_reduce_add_2d(tm, box, x, y);
       else tma_store_2d(tm, box, x, y);
       bulk_commit();
@@ -289,7 +291,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
     if (rotate) {
       // Borrow the warp's two store boxes as a transpose buffer: coalesced 128-byte reads of the 32 tokens'
       // cos / sin rows, swizzled so the thread == row read-back is conflict free.
-      if (lane == 0) bulk_wait_read<0>();     // no TMA store may still be reading the boxes
+      if (elect_one()) bulk_wait_read<0>();   // no TMA store may still be reading the boxes
       __syncwarp();
       float* cs_s = reinterpret_cast<float*>(st.base);
       float* sn_s = reinterpret_cast<float*>(st.base + EPI_BOX_BYTES);
@@ -418,25 +420,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // NOTE: the producer and MMA loops are executed by the WHOLE warp (convergent, warp-uniform values) and only the
+  // TMA / MMA / commit instructions themselves are predicated on one elected lane.  Running the loops under
+  // `if (lane == 0)` makes every descriptor a divergent value and the compiler wraps each UTCHMMA / UTMALDG in an
+  // ELECT + R2UR waterfall (~30 extra instructions per MMA, measured: the issue thread became the bottleneck).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
-        const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_tagged(bar_empty + stage, phase ^ 1, 11);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+      const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_tagged(bar_empty + stage, phase ^ 1, 11);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        if (elect_one()) {
           // one barrier in the leader tracks both CTAs' operands: 2 x (A 16 KB + W half 16 KB)
           if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + stage, 2 * STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_2d_pair(sa, &tmA, bar_full + stage, kb * BK, m_idx * BM);
           tma_load_2d_pair(sa + A_BYTES, &tmB, bar_full + stage, kb * BK, n_idx * BN + cta_rank * (BN / 2));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {   // the leader CTA issues the pair's MMAs
+    if (cta_rank == 0) {   // the leader CTA issues the pair's MMAs
       constexpr uint32_t idesc = umma_idesc(0 /*f16*/, 2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -451,16 +458,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+            }
+            // slot reusable (in BOTH CTAs) once these MMAs retire
+            umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
           }
-          // slot reusable (in BOTH CTAs) once these MMAs retire
-          umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(bar_tfull + acc, static_cast<uint16_t>(3));   // accumulators complete -> both epilogues
+        if (elect_one()) umma_commit_pair(bar_tfull + acc, static_cast<uint16_t>(3));   // accumulators -> epilogues
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -491,7 +502,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (kStaged<EPI> && lane == 0) bulk_wait<0>();  // all TMA stores / reductions of this warp have landed
+    if (kStaged<EPI>) {
+      if (elect_one()) bulk_wait<0>();  // all TMA stores / reductions of this warp have landed
+    }
+    __syncwarp();
   }
 
   tc_fence_before();
