@@ -64,7 +64,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* pv_done = bars + 10;     // 1
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
+  const int lane = threadIdx.x & 31;
   int kv_lo = 0, kv_hi = L;
   if (LOCAL) {
     kv_lo = max(0, q0 - window);

@@ -389,7 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
   const int cta_rank = static_cast<int>(cluster_ctarank());      // 0 / 1 inside the CTA pair
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;

@@ -161,7 +161,7 @@ dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __
   float4* sq = reinterpret_cast<float4*>(scan_smem + static_cast<size_t>(nstage) * STAGE_BYTES);  // [NQ][VEC*32]
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sq) + NQ * DIM * 4);
   uint64_t* empty = full + nstage;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int64_t nblocks = (n + SCAN_ROWS - 1) / SCAN_ROWS;
 
   for (int i = threadIdx.x; i < NQ * VEC * 32; i += blockDim.x)
