@@ -260,6 +260,7 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner there)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)

@@ -1,6 +1,6 @@
 // tcgen05 self-attention over unpadded sequences: one (128-query tile, head, sequence) per CTA, 2 CTAs per SM.
 //
-//   warp 0      : TMA producer  (Q tile once; K/V blocks of 64 keys into a 2-stage ring, SWIZZLE_128B boxes)
+//   warp 0      : TMA producer  (Q tile once; K/V blocks of 64 keys into a 4-stage ring, SWIZZLE_128B boxes)
 //   warp 1      : MMA issuer    S = Q K^T   (tcgen05.mma 128x64x16, both operands K-major)   -> TMEM S[2]
 //                               PV = P V    (tcgen05.mma 128x64x16, A = P from smem, B = V MN-major) -> TMEM Otmp[2]
 //   warps 2..9  : softmax       two warps per TMEM lane quarter; thread == (query row, half of the 64 columns):
@@ -19,13 +19,14 @@ namespace {
 
 constexpr int AQ = 128, AK = 64, AD = 64;
 constexpr int SOFT_WARPS = 8;
+constexpr int KVS = 4;                  // K/V ring depth: TMA latency (~1-2k cycles) must be covered by >= 2 blocks in flight
 constexpr int ATT_THREADS = 32 * (2 + SOFT_WARPS);
 constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64)  S1 [64,128)  Otmp0 [128,192)  Otmp1 [192,256)
 constexpr int SQ_BYTES = AQ * AD * 2;    // 16384
 constexpr int SKV_BYTES = AK * AD * 2;   // 8192
 constexpr int SP_BYTES = AQ * AK * 2;    // 16384
 constexpr int SX_BYTES = 2 * 2 * AQ * 4; // row-max exchange [block parity][half][row]
-constexpr int ATT_SMEM = SQ_BYTES + 2 * 2 * SKV_BYTES + SP_BYTES + SX_BYTES + 1024 + 256;
+constexpr int ATT_SMEM = SQ_BYTES + KVS * 2 * SKV_BYTES + SP_BYTES + SX_BYTES + 1024 + 256;
 constexpr int HC = AK / 2;               // columns per softmax thread (32)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -52,17 +53,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + SQ_BYTES;               // stage s: K at sKV + s*16384, V at +8192
-  uint8_t* sP = sKV + 4 * SKV_BYTES;
+  uint8_t* sP = sKV + KVS * 2 * SKV_BYTES;
   float* sX = reinterpret_cast<float*>(sP + SP_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + SX_BYTES);
   uint64_t* bar_q = bars;            // 1
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;       // [2]
-  uint64_t* s_empty = bars + 7;      // [2]
-  uint64_t* p_full = bars + 9;       // 1
-  uint64_t* pv_done = bars + 10;     // 1
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;              // [KVS]
+  uint64_t* kv_empty = kv_full + KVS;        // [KVS]
+  uint64_t* s_full = kv_empty + KVS;         // [2]
+  uint64_t* s_empty = s_full + 2;            // [2]
+  uint64_t* p_full = s_empty + 2;            // 1
+  uint64_t* pv_done = p_full + 1;            // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -76,9 +77,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < KVS; ++i) {
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(s_full + i, 1);
       mbar_init(s_empty + i, SOFT_WARPS);
     }
@@ -109,8 +112,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     __syncwarp();
     for (int i = 0; i < nb; ++i) {
-      const int st = i & 1;
-      mbar_wait_tagged(kv_empty + st, ((i >> 1) & 1) ^ 1, 3);
+      const int st = i % KVS;
+      mbar_wait_tagged(kv_empty + st, ((i / KVS) & 1) ^ 1, 3);
       const int row = s0 + (j_lo + i) * AK;
       if (elect_one()) {
         mbar_arrive_expect_tx(kv_full + st, 2 * SKV_BYTES);
@@ -125,17 +128,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
     mbar_wait_tagged(bar_q, 0, 1);
     auto issue_s = [&](int i) {
-      const int st = i & 1;
-      mbar_wait_tagged(kv_full + st, (i >> 1) & 1, 2);
-      mbar_wait_tagged(s_empty + st, ((i >> 1) & 1) ^ 1, 5);
+      const int st = i % KVS, sb = i & 1;   // K/V ring slot, S buffer
+      mbar_wait_tagged(kv_full + st, (i / KVS) & 1, 2);
+      mbar_wait_tagged(s_empty + sb, ((i >> 1) & 1) ^ 1, 5);
       tc_fence_after();
       const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AD / 16; ++k)
-          umma_f16(tmem_base + st * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
+          umma_f16(tmem_base + sb * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
                    k > 0 ? 1u : 0u);
-        umma_commit(s_full + st);
+        umma_commit(s_full + sb);
       }
       __syncwarp();
     };
@@ -144,7 +147,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (i + 1 < nb) issue_s(i + 1);
       mbar_wait_tagged(p_full, i & 1, 6);
       tc_fence_after();
-      const int st = i & 1;
+      const int st = i % KVS;
       const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
       if (elect_one()) {
 #pragma unroll
