@@ -370,6 +370,31 @@ def run_gpu_arm(args):
                      "flops_per_launch_avg": gemm_flops / max(gemm_n, 1),
                      "share_of_step": {k: v["ms"] / (ms_total) for k, v in prof.items() if v["launches"]}},
     }
+    if world == 1 and args.secondary:
+        # plugin level: strings in -> verbatim span strings out (B200SpanExtractor.extract_spans_batch), small sample.
+        # Host tokenisation (tokenizers library, word-level synthetic vocab) dominates this number, not the GPU.
+        from verbatim_rag_b200 import B200SpanExtractor
+        from verbatim_rag_b200.synthetic import SyntheticTokenizer
+        tk = SyntheticTokenizer("modernbert")
+        ext = B200SpanExtractor.__new__(B200SpanExtractor)
+        ext.tokenizer, ext.threshold, ext.min_span_chars, ext.merge_gap_chars = tk, 0.2, 30, 20
+        ext.max_length, ext.doc_stride, ext._enc, ext._ctx = 8192, 256, enc, ctx
+        ext._lock = threading.Lock()
+        prng = np.random.default_rng(7)
+        nq_p, nchunk_p = 16, 16
+
+        class _R:
+            def __init__(self, t):
+                self.text = t
+        qs = [tk.make_question(prng, Q_LEN) for _ in range(nq_p)]
+        rs = [[_R(tk.make_text(prng, SEQ_LEN - Q_LEN - 3)) for _ in range(nchunk_p)] for _ in range(nq_p)]
+        ext.extract_spans_batch(qs[:2], rs[:2])
+        t0 = time.perf_counter()
+        res = ext.extract_spans_batch(qs, rs)
+        dtp = time.perf_counter() - t0
+        line["e2e_plugin_strings"] = {"value": nq_p * nchunk_p / dtp, "unit": UNIT, "pairs": nq_p * nchunk_p,
+                                      "spans": int(sum(len(v) for d in res for v in d.values())),
+                                      "note": "extract_spans_batch(strings): host tokenisation bound"}
     if world == 1 and args.cpu_baseline:
         rate, dt, cores = time_cpu(args.cpu_sample, 1, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -27,7 +27,8 @@ struct vrag_encoder {
   bool legacy_attention = false;
   void attention(const __half* qkv, __half* out, int nseq, int total_tokens, int max_len, int window) {
     if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
-    else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), nseq, total_tokens, max_len, 12, vrag::HIDDEN, window);
+    else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), work.as<int32_t>(), n_pairs, total_tokens, 12,
+                                   vrag::HIDDEN, window);
   }
   std::vector<DevBuf*> owned;
   // shared
@@ -49,12 +50,13 @@ struct vrag_encoder {
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled;
+      pooled, work;
+  int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
-                      &counts, &indptr, &sp_idx, &sp_val, &pooled})
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work})
       b->release();
   }
   template <typename T>
@@ -247,9 +249,18 @@ void stage_pass(vrag_encoder* e, const Pass& ps, const int32_t* ids, const int32
   const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0;
   VRAG_CUDA(cudaMemcpyAsync(e->ids.p, ids + ps.t0, static_cast<size_t>(T) * 4,
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-  int32_t* cu_h = static_cast<int32_t*>(ctx->pinned_reserve((static_cast<size_t>(ns) + 1) * 4));
+  // attention work list: one entry per (sequence, 128-query tile) of this pass
+  int n_pairs = 0;
+  for (int i = 0; i < ns; ++i) n_pairs += (cu[ps.s0 + i + 1] - cu[ps.s0 + i] + 127) / 128;
+  int32_t* cu_h = static_cast<int32_t*>(ctx->pinned_reserve((static_cast<size_t>(ns) + 1 + 2 * static_cast<size_t>(n_pairs)) * 4));
   for (int i = 0; i <= ns; ++i) cu_h[i] = cu[ps.s0 + i] - ps.t0;
+  int32_t* work_h = cu_h + ns + 1;
+  for (int i = 0, w = 0; i < ns; ++i)
+    for (int q0 = 0; q0 < cu_h[i + 1] - cu_h[i]; q0 += 128) { work_h[2 * w] = i; work_h[2 * w + 1] = q0; ++w; }
+  e->work.reserve(static_cast<size_t>(2 * n_pairs) * 4);
+  e->n_pairs = n_pairs;
   VRAG_CUDA(cudaMemcpyAsync(e->cu.p, cu_h, (static_cast<size_t>(ns) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VRAG_CUDA(cudaMemcpyAsync(e->work.p, work_h, static_cast<size_t>(2 * n_pairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
   VRAG_CUDA(cudaStreamSynchronize(ctx->stream));  // cu_h (pinned scratch) is reused by the next pass
   launch_token_meta(ctx, e->cu.as<int32_t>(), ns, T, e->pos.as<int32_t>(), e->seqrow.as<int32_t>());
 }
@@ -279,6 +290,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);
     GemmEpiParams r;
     r.M = T; r.out32 = x32; r.ld32 = H;
+    { const char* dm = getenv("VRAG_DEBUG_RESID"); r.debug_mode = dm ? atoi(dm) : 0; }
     launch_gemm(ctx, EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
     launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
     GemmEpiParams g;

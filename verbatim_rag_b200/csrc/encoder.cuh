@@ -13,8 +13,9 @@ void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32
 
 // attention_tc.cu: tcgen05 version (default); the mma.sync kernel above stays as a debug cross-check
 // (VRAG_ATTENTION_LEGACY=1 at encoder creation).
-void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev, int nseq,
-                         int total_tokens, int max_len, int heads, int hidden, int window);
+void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
+                         const int32_t* work_dev /* [n_pairs][2] = (sequence, q0) */, int n_pairs, int total_tokens,
+                         int heads, int hidden, int window);
 
 // rowops.cu  (one warp per token row, H = 768)
 void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, int total, int32_t* pos,

@@ -362,7 +362,9 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
         }
       }
       box_put_float32(box, r, v);
-      st.submit<true>(tmOut, box, col0 + c * 32, m0, lane);
+      if (p.debug_mode == 0) st.submit<true>(tmOut, box, col0 + c * 32, m0, lane);
+      else if (p.debug_mode == 1) st.submit<false>(tmOut, box, col0 + c * 32, m0, lane);
+      else { __syncwarp(); }
     }
   }
 }

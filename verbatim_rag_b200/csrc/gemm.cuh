@@ -34,6 +34,8 @@ struct GemmEpiParams {
   int splade_ld = 0;
   int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail)
   int M = 0;                          // valid rows
+  int debug_mode = 0;                 // timing experiments only (VRAG_DEBUG_RESID): 1 = plain store instead of
+                                      // reduce-add (wrong values), 2 = no store at all
 };
 
 constexpr int GEMM_BM = 128;
