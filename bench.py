@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs-per-step", type=int, default=SEQS_PER_STEP)
-    ap.add_argument("--max-tokens", type=int, default=65536)
+    ap.add_argument("--max-tokens", type=int, default=131072)  # pass-size sweep: profiles/README.md
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")

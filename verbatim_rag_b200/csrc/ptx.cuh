@@ -61,25 +61,65 @@ static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
   __trap();
 }
 __device__ __forceinline__ void mbar_wait_tagged(uint64_t* bar, uint32_t parity, int tag) {
-  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
   uint64_t t0 = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
+  for (;;) {
+    // tight probe loop (3 issue slots per failed probe; the probe itself suspends the warp for a while); the
+    // wall-clock check below runs once per 64 failed probes only
+    uint32_t done;
     asm volatile(
         "{\n\t"
-        ".reg .pred P1;\n\t"
+        ".reg .pred P1, P2;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "LAB_TRY:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "@P1 bra LAB_OUT;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 P2, n, 64;\n\t"
+        "@P2 bra LAB_TRY;\n\t"
+        "LAB_OUT:\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(addr), "r"(parity)
         : "memory");
-    if (!done && (spins & 15u) == 15u) {  // wall-clock bound (try_wait itself may block for a while per probe)
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity);  // 2 s
-    }
+    if (done) break;
+    uint64_t now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity);  // 2 s
   }
+}
+
+// ------------------------------------------------------------------ packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_bits(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 // ------------------------------------------------------------------ TMA
