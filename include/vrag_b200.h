@@ -113,6 +113,13 @@ int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_
  * an in-library SIMT reference GEMM on random data and return the max |diff| (device-side self check). */
 int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff, double* ref_abs_max);
 
+/* Debug / test hook: one self-attention launch (12 heads x 64, as in both encoders; reference semantics:
+ * transformers ModernBertAttention sdpa path -- softmax(q k^T / 8 + window mask) v per sequence) on caller-supplied
+ * fp16 rows qkv_f16 [total_tokens, 2304] = q|k|v (q, k already rotated), host memory.  window < 0: full attention,
+ * else keys with |i - j| <= window.  legacy != 0 runs the mma.sync cross-check kernel.  out_f16 [total_tokens, 768]. */
+int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, const int32_t* cu_seqlens, int nseq, int window,
+                            int legacy, uint16_t* out_f16);
+
 /* Debug hook (tests): vrag_span_forward with host buffers that also returns the fp32 residual stream after
  * the embedding and after every layer, hidden_out [num_layers + 1, total_tokens, 768]; single pass only. */
 int vrag_debug_span_hidden(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,

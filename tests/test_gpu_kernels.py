@@ -59,6 +59,56 @@ def _modernbert_case(layers, lens, seed):
     return spec, w, seqs
 
 
+# ------------------------------------------------------------------------------------------ attention
+def _attention_f64(qkv16, cu, window):
+    """softmax(q k^T / 8 + window mask) v per (sequence, head) in float64 on the fp16-rounded rows
+    (reference semantics: transformers ModernBertAttention, sdpa path; oracle/modernbert.py `_attention`)."""
+    T = qkv16.shape[0]
+    x = qkv16.astype(np.float64).reshape(T, 3, 12, 64)
+    out = np.zeros((T, 12, 64))
+    for s in range(len(cu) - 1):
+        a, b = int(cu[s]), int(cu[s + 1])
+        L = b - a
+        idx = np.arange(L)
+        mask = np.abs(idx[:, None] - idx[None, :]) <= window if window >= 0 else np.ones((L, L), bool)
+        for h in range(12):
+            q, k, v = x[a:b, 0, h], x[a:b, 1, h], x[a:b, 2, h]
+            sc = np.where(mask, q @ k.T / 8.0, -np.inf)
+            sc -= sc.max(axis=1, keepdims=True)
+            p = np.exp(sc)
+            out[a:b, h] = (p / p.sum(axis=1, keepdims=True)) @ v
+    return out.reshape(T, 768)
+
+
+@pytest.mark.parametrize("window", [-1, 64])
+@pytest.mark.parametrize("case", ["moderate", "wide_scores", "rising_max"])
+def test_attention_kernel_vs_float64(ctx, window, case):
+    """tcgen05 attention on its own: ragged lengths (tails of 1..127 queries, a single-token sequence), score
+    ranges far beyond what the encoder produces (forces the online-softmax rescaling on most key blocks), and keys
+    whose scores rise monotonically along the sequence (every block raises the running max)."""
+    rng = np.random.default_rng(11)
+    lens = [512, 200, 77, 1, 129, 640]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    T = int(cu[-1])
+    qkv = rng.standard_normal((T, 3, 12, 64))
+    if case == "wide_scores":
+        qkv[:, :2] *= 4.0                      # score std ~ 16 -> ~23 in log2 units
+    elif case == "rising_max":
+        pos = np.concatenate([np.arange(n) for n in lens])[:, None]
+        qkv[:, 0, :, 0] = 6.0                  # q . k grows with the key position: max rises every block
+        qkv[:, 1, :, 0] = pos * 0.25
+    qkv16 = qkv.reshape(T, 2304).astype(np.float16)
+    ref = _attention_f64(qkv16, cu, window)
+    got = ctx.selftest_attention(qkv16, cu, window=window).astype(np.float64)
+    err = np.abs(got - ref)
+    _diag(test="attention_selftest", case=case, window=window, max_abs_err=err.max(), ref_abs_max=np.abs(ref).max())
+    assert np.isfinite(got).all()
+    # P and the output are rounded to fp16 (2^-11 relative each); accumulation is fp32
+    assert err.max() <= 4e-3 * max(np.abs(ref).max(), 1.0), (case, window, err.max())
+    legacy = ctx.selftest_attention(qkv16, cu, window=window, legacy=True).astype(np.float64)
+    assert np.abs(legacy - ref).max() <= 4e-3 * max(np.abs(ref).max(), 1.0)
+
+
 @pytest.mark.parametrize("use_ref_gemm,legacy_attn", [(True, True), (False, True), (False, False)])
 def test_modernbert_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
     from verbatim_rag_b200 import _native

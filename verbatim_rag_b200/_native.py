@@ -24,7 +24,7 @@ POOL_MEAN, POOL_CLS = 0, 1
 EXPORTS = [
     "vrag_ctx_create", "vrag_ctx_destroy", "vrag_last_error", "vrag_sync", "vrag_stream", "vrag_launch_count",
     "vrag_version", "vrag_profile", "vrag_profile_read", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
-    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_debug_span_hidden", "vrag_spans_from_probs",
+    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_selftest_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
@@ -76,6 +76,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_splade_forward": (i32, [vp, vp, vp, i32, f32, vp, vp, vp, i64, P(i64), vp, i32]),
             "vrag_dense_forward": (i32, [vp, vp, vp, i32, i32, i32, vp, i32]),
             "vrag_selftest_gemm": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
+            "vrag_selftest_attention": (i32, [vp, vp, vp, i32, i32, i32, vp]),
             "vrag_spans_from_probs": (i32, [vp, vp, vp, vp, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
             "vrag_index_create": (i32, [vp, i32, i32, P(vp)]),
             "vrag_index_destroy": (None, [vp]),
@@ -157,6 +158,17 @@ class Context:
         d, m = C.c_double(), C.c_double()
         self.check(self.lib.vrag_selftest_gemm(self.h, M, N, K, epilogue, C.byref(d), C.byref(m)))
         return d.value, m.value
+
+    def selftest_attention(self, qkv_f16, cu_seqlens, window: int = -1, legacy: bool = False):
+        """One attention launch on host fp16 rows qkv_f16 [T, 2304] (q|k|v, 12 heads x 64); returns fp16 [T, 768]."""
+        import numpy as np
+        qkv = np.ascontiguousarray(qkv_f16, dtype=np.float16)
+        cu = np.ascontiguousarray(cu_seqlens, dtype=np.int32)
+        assert qkv.ndim == 2 and qkv.shape[1] == 2304 and qkv.shape[0] == int(cu[-1])
+        out = np.empty((qkv.shape[0], 768), dtype=np.float16)
+        self.check(self.lib.vrag_selftest_attention(self.h, qkv.ctypes.data, cu.ctypes.data, len(cu) - 1, int(window),
+                                                    1 if legacy else 0, out.ctypes.data))
+        return out
 
     def topk_merge(self, scores64, ids, nq: int, m: int, k: int, ids_out, scores_out, scores64_out=None):
         """Device buffers (torch tensors or raw pointers)."""

@@ -6,6 +6,7 @@
 #include <random>
 
 #include "common.cuh"
+#include "encoder.cuh"
 #include "gemm.cuh"
 
 using namespace vrag;
@@ -288,6 +289,60 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
     for (DevBuf* b : {&A, &W, &C0, &C1, &R, &POS, &CS, &SN}) b->release();
+    return VRAG_OK;
+  } catch (const Error& e) {
+    ctx->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->last_error = e.what();
+    return VRAG_ERR_INTERNAL;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention self test: runs one attention launch (tcgen05 kernel, or the mma.sync cross-check with legacy != 0) on
+// caller-supplied fp16 q|k|v rows, so tests can drive score ranges the encoder never produces (online-softmax
+// rescaling, ragged tails, local windows) against a float64 host computation.
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, const int32_t* cu_seqlens, int nseq,
+                                       int window, int legacy, uint16_t* out_f16) {
+  if (!ctx || !qkv_f16 || !cu_seqlens || !out_f16 || nseq < 1) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  try {
+    VRAG_CUDA(cudaSetDevice(ctx->device));
+    const int T = cu_seqlens[nseq];
+    VRAG_CHECK(cu_seqlens[0] == 0 && T > 0, VRAG_ERR_ARG, "selftest_attention: cu_seqlens must start at 0");
+    std::vector<int32_t> work;
+    int max_len = 0;
+    for (int i = 0; i < nseq; ++i) {
+      const int L = cu_seqlens[i + 1] - cu_seqlens[i];
+      VRAG_CHECK(L > 0, VRAG_ERR_ARG, "selftest_attention: empty sequence");
+      max_len = std::max(max_len, L);
+      for (int q0 = 0; q0 < L; q0 += 128) {
+        work.push_back(cu_seqlens[i]);
+        work.push_back(L);
+        work.push_back(q0);
+        work.push_back(0);
+      }
+    }
+    DevBuf QKV, OUT, CU, WORK;
+    QKV.reserve(static_cast<size_t>(T) * 3 * HIDDEN * 2);
+    OUT.reserve(static_cast<size_t>(T) * HIDDEN * 2);
+    CU.reserve(static_cast<size_t>(nseq + 1) * 4);
+    WORK.reserve(work.size() * 4);
+    cudaStream_t st = ctx->stream;
+    VRAG_CUDA(cudaMemcpyAsync(QKV.p, qkv_f16, static_cast<size_t>(T) * 3 * HIDDEN * 2, cudaMemcpyHostToDevice, st));
+    VRAG_CUDA(cudaMemcpyAsync(CU.p, cu_seqlens, static_cast<size_t>(nseq + 1) * 4, cudaMemcpyHostToDevice, st));
+    VRAG_CUDA(cudaMemcpyAsync(WORK.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, st));
+    VRAG_CUDA(cudaMemsetAsync(OUT.p, 0xff, static_cast<size_t>(T) * HIDDEN * 2, st));  // NaN pattern
+    if (legacy)
+      launch_attention(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), nseq, max_len, 12, HIDDEN, window);
+    else
+      launch_attention_tc(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), WORK.as<int32_t>(),
+                          static_cast<int>(work.size() / 4), T, 12, HIDDEN, window);
+    VRAG_CUDA(cudaMemcpyAsync(out_f16, OUT.p, static_cast<size_t>(T) * HIDDEN * 2, cudaMemcpyDeviceToHost, st));
+    VRAG_CUDA(cudaStreamSynchronize(st));
+    for (DevBuf* b : {&QKV, &OUT, &CU, &WORK}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();

@@ -252,15 +252,20 @@ void stage_pass(vrag_encoder* e, const Pass& ps, const int32_t* ids, const int32
   // attention work list: one entry per (sequence, 128-query tile) of this pass
   int n_pairs = 0;
   for (int i = 0; i < ns; ++i) n_pairs += (cu[ps.s0 + i + 1] - cu[ps.s0 + i] + 127) / 128;
-  int32_t* cu_h = static_cast<int32_t*>(ctx->pinned_reserve((static_cast<size_t>(ns) + 1 + 2 * static_cast<size_t>(n_pairs)) * 4));
+  int32_t* cu_h = static_cast<int32_t*>(ctx->pinned_reserve((static_cast<size_t>(ns) + 1 + 4 * static_cast<size_t>(n_pairs)) * 4));
   for (int i = 0; i <= ns; ++i) cu_h[i] = cu[ps.s0 + i] - ps.t0;
   int32_t* work_h = cu_h + ns + 1;
   for (int i = 0, w = 0; i < ns; ++i)
-    for (int q0 = 0; q0 < cu_h[i + 1] - cu_h[i]; q0 += 128) { work_h[2 * w] = i; work_h[2 * w + 1] = q0; ++w; }
-  e->work.reserve(static_cast<size_t>(2 * n_pairs) * 4);
+    for (int q0 = 0; q0 < cu_h[i + 1] - cu_h[i]; q0 += 128, ++w) {  // 16-byte entries {s0, L, q0, -}
+      work_h[4 * w] = cu_h[i];
+      work_h[4 * w + 1] = cu_h[i + 1] - cu_h[i];
+      work_h[4 * w + 2] = q0;
+      work_h[4 * w + 3] = 0;
+    }
+  e->work.reserve(static_cast<size_t>(4 * n_pairs) * 4);
   e->n_pairs = n_pairs;
   VRAG_CUDA(cudaMemcpyAsync(e->cu.p, cu_h, (static_cast<size_t>(ns) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  VRAG_CUDA(cudaMemcpyAsync(e->work.p, work_h, static_cast<size_t>(2 * n_pairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VRAG_CUDA(cudaMemcpyAsync(e->work.p, work_h, static_cast<size_t>(4 * n_pairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
   VRAG_CUDA(cudaStreamSynchronize(ctx->stream));  // cu_h (pinned scratch) is reused by the next pass
   launch_token_meta(ctx, e->cu.as<int32_t>(), ns, T, e->pos.as<int32_t>(), e->seqrow.as<int32_t>());
 }
