@@ -47,34 +47,37 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 16-byte store of chunk c of a SWIZZLE_128B row: address = row_base_with_swizzle ^ (c << 4).  The XOR sits inside the
+// asm block so that the compiler cannot hoist eight loop-invariant addresses out of the item loop (it did, and spilled
+// them).
+template <int C>
+__device__ __forceinline__ void st_p_chunk(uint32_t row_sw, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile(
+      "{\n\t.reg .b32 addr;\n\txor.b32 addr, %0, %1;\n\tst.shared.v4.b32 [addr], {%2, %3, %4, %5};\n\t}\n" ::"r"(row_sw),
+      "n"(C << 4), "r"(a), "r"(b), "r"(c), "r"(d)
+      : "memory");
+}
+
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+
 struct Item {  // one (sequence, 128-query tile, head)
   int s0, L, q0, head, j_lo, nb;
 };
 
-// Work cursor: item w = pair * heads + head, advanced by gridDim.x without integer division; the 16-byte work entry
-// {first token of the sequence, sequence length, q0, -} of the NEXT item is fetched while the current one runs (a
-// dependent global-load chain at the top of every item cost ~2k cycles per item: profiles/README.md).
-struct Cursor {
-  int pair, head;
-};
-__device__ __forceinline__ void advance(Cursor& c, int dq, int dr, int heads) {
-  c.pair += dq;
-  c.head += dr;
-  if (c.head >= heads) {
-    c.head -= heads;
-    ++c.pair;
-  }
-}
-__device__ __forceinline__ int4 load_entry(const int4* __restrict__ work, int pair, int n_pairs) {
-  return pair < n_pairs ? __ldg(work + pair) : make_int4(0, 0, 0, 0);
-}
+// Item w = pair * heads + head of this CTA's stream (w = blockIdx.x, += gridDim.x).  Only the producer warp walks the
+// work list (16-byte entries {first token of the sequence, sequence length, q0, -}, next entry prefetched) and
+// publishes {s0, L, q0, head} in shared memory (two slots, item parity) before it arms q_full; the MMA and softmax
+// warps read it after a barrier wait that is causally later, so they carry no decode state in registers.
 template <bool LOCAL>
-__device__ __forceinline__ Item make_item(int4 e, int head, int window) {
+__device__ __forceinline__ Item make_item(int4 e, int window) {
   Item it;
-  it.head = head;
   it.s0 = e.x;
   it.L = e.y;
   it.q0 = e.z;
+  it.head = e.w;
   int kv_lo = 0, kv_hi = it.L;
   if (LOCAL) {
     kv_lo = max(0, it.q0 - window);
@@ -84,20 +87,15 @@ __device__ __forceinline__ Item make_item(int4 e, int head, int window) {
   it.nb = (kv_hi + AK - 1) / AK - it.j_lo;
   return it;
 }
-
-#define VRAG_ITEM_LOOP_BEGIN                                                            \
-  Cursor cur = {static_cast<int>(blockIdx.x) / heads, static_cast<int>(blockIdx.x) % heads}; \
-  const int dq = static_cast<int>(gridDim.x) / heads, dr = static_cast<int>(gridDim.x) % heads; \
-  int4 entry = load_entry(work, cur.pair, n_pairs);                                     \
-  while (cur.pair < n_pairs) {                                                          \
-    Cursor nxt = cur;                                                                   \
-    advance(nxt, dq, dr, heads);                                                        \
-    const int4 entry_next = load_entry(work, nxt.pair, n_pairs);                        \
-    const Item it = make_item<LOCAL>(entry, cur.head, window);
-#define VRAG_ITEM_LOOP_END \
-    cur = nxt;             \
-    entry = entry_next;    \
-  }
+template <bool LOCAL>
+__device__ __forceinline__ Item read_item(const int4* info, uint32_t it_n, int window) {
+  int4 e;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+               : "r"(smem_u32(info + (it_n & 1)))
+               : "memory");
+  return make_item<LOCAL>(e, window);
+}
 
 template <bool LOCAL>
 __global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
@@ -120,6 +118,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = s_empty + 1;            // 1
   uint64_t* pv_done = p_full + 1;            // 1
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 1);
+  int4* info = reinterpret_cast<int4*>(bars + 16);  // [2] published items (16-byte aligned: bars is 1 KB aligned)
+  const int n_work = n_pairs * heads;
+  const uint32_t n_items = blockIdx.x < static_cast<unsigned>(n_work)
+                               ? (static_cast<uint32_t>(n_work) - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -153,10 +155,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t it_n = 0, g = 0;
-    VRAG_ITEM_LOOP_BEGIN
+    uint32_t g = 0;
+    int pair = static_cast<int>(blockIdx.x) / heads, head = static_cast<int>(blockIdx.x) % heads;
+    const int dq = static_cast<int>(gridDim.x) / heads, dr = static_cast<int>(gridDim.x) % heads;
+    int4 entry = pair < n_pairs ? __ldg(work + pair) : make_int4(0, 0, 0, 0);
+    for (uint32_t it_n = 0; it_n < n_items; ++it_n) {
+      int npair = pair + dq, nhead = head + dr;
+      if (nhead >= heads) {
+        nhead -= heads;
+        ++npair;
+      }
+      const int4 entry_next = npair < n_pairs ? __ldg(work + npair) : make_int4(0, 0, 0, 0);
+      entry.w = head;
+      const Item it = make_item<LOCAL>(entry, window);
       mbar_wait_tagged(q_empty, (it_n & 1) ^ 1, 8);  // every S MMA of the previous item has read the Q tile
       if (elect_one()) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(info + (it_n & 1))), "r"(entry.x),
+                     "r"(entry.y), "r"(entry.z), "r"(entry.w)
+                     : "memory");  // released by the arrive below
         mbar_arrive_expect_tx(q_full, SQ_BYTES);
         tma_load_2d(sQ, &tmQ, q_full, it.head * AD, it.s0 + it.q0);
       }
@@ -172,36 +188,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
       }
-      ++it_n;
-    VRAG_ITEM_LOOP_END
+      pair = npair;
+      head = nhead;
+      entry = entry_next;
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // One flat stream of key blocks across items: S of the NEXT block (possibly the next item's first) is issued
+    // before waiting for the current block's P, so the softmax warps never wait for a QK^T at an item boundary.
     constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
     constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
     const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
-    uint32_t it_n = 0, g = 0;
-    VRAG_ITEM_LOOP_BEGIN
-      mbar_wait_tagged(q_full, it_n & 1, 1);
-      auto issue_s = [&](uint32_t G, bool last) {
-        const int st = G % KVS;
-        mbar_wait_tagged(kv_full + st, (G / KVS) & 1, 2);
-        mbar_wait_tagged(s_empty, (G & 1) ^ 1, 5);  // the softmax warps hold S_{G-1} in registers
-        tc_fence_after();
-        const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
-        if (elect_one()) {
+    auto issue_s = [&](uint32_t G, bool last) {
+      const int st = G % KVS;
+      mbar_wait_tagged(kv_full + st, (G / KVS) & 1, 2);
+      mbar_wait_tagged(s_empty, (G & 1) ^ 1, 5);  // the softmax warps hold S_{G-1} in registers
+      tc_fence_after();
+      const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AD / 16; ++k)
-            umma_f16(tmem_base, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
-                     k > 0 ? 1u : 0u);
-          umma_commit(s_full);
-          if (last) umma_commit(q_empty);  // the Q tile is free once this item's last S has completed
-        }
-        __syncwarp();
-      };
-      issue_s(g, it.nb == 1);
-      for (int i = 0; i < it.nb; ++i) {
+        for (int k = 0; k < AD / 16; ++k)
+          umma_f16(tmem_base, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
+                   k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        if (last) umma_commit(q_empty);  // the Q tile is free once this item's last S has completed
+      }
+      __syncwarp();
+    };
+    uint32_t g = 0;
+    int nb = 0;
+    if (n_items > 0) {
+      mbar_wait_tagged(q_full, 0, 1);
+      nb = read_item<LOCAL>(info, 0, window).nb;
+      issue_s(0, nb == 1);
+    }
+    for (uint32_t it_n = 0; it_n < n_items; ++it_n) {
+      int nb_next = 0;
+      for (int i = 0; i < nb; ++i) {
         const uint32_t G = g + i;
-        if (i + 1 < it.nb) issue_s(G + 1, i + 2 == it.nb);
+        if (i + 1 < nb) {
+          issue_s(G + 1, i + 2 == nb);
+        } else if (it_n + 1 < n_items) {
+          mbar_wait_tagged(q_full, (it_n + 1) & 1, 1);
+          nb_next = read_item<LOCAL>(info, it_n + 1, window).nb;
+          issue_s(G + 1, nb_next == 1);
+        }
         mbar_wait_tagged(p_full, G & 1, 6);
         tc_fence_after();
         const int st = G % KVS;
@@ -216,20 +247,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
       }
-      g += it.nb;
-      ++it_n;
-    VRAG_ITEM_LOOP_END
+      g += nb;
+      nb = nb_next;
+    }
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int quarter = warp & 3;        // TMEM lane quarter (hardware: warp w may touch lanes 32*(w%4)..+31)
     const int r = quarter * 32 + lane;   // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t p_dst = smem_u32(sP) + r * 128;
-    const int sw = r & 7;                // SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
+    // SWIZZLE_128B: 16-byte chunk index XOR (row & 7); rows are 128-byte aligned, so chunk c of the row lives at
+    // (row base | (row & 7) << 4) ^ (c << 4)
+    const uint32_t p_row_sw = (smem_u32(sP) + r * 128) | ((r & 7) << 4);
     const uint64_t scale2 = f2_pack(scale_log2e, scale_log2e);
     uint32_t g = 0;
 
-    VRAG_ITEM_LOOP_BEGIN
+    for (uint32_t it_n = 0; it_n < n_items; ++it_n) {
+      mbar_wait_tagged(s_full, g & 1, 4);  // first S of the item: its producer has published the item long before
+      const Item it = read_item<LOCAL>(info, it_n, window);
       const int q = it.q0 + r;
       float m_used = -INFINITY;          // reference max of this row (log2 units); -inf until a key is seen
       uint64_t l2 = 0ull;                // row sum relative to m_used, two partial chains
@@ -243,15 +277,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int key0 = (it.j_lo + i) * AK;
         const int e_lo = k_lo - key0, e_hi = k_hi - key0;  // valid local columns
         const bool dead = __all_sync(0xffffffffu, e_hi < 0 || e_lo > AK - 1);
-        mbar_wait_tagged(s_full, G & 1, 4);
+        if (i > 0) mbar_wait_tagged(s_full, G & 1, 4);
         tc_fence_after();
-        uint32_t pk[AK / 2];             // P row, packed fp16 pairs
+        // P smem was read by PV_{G-1}: pv_done(G-1) is observed before the P stores.  (That wait also keeps pv_done at
+        // most one phase ahead of this warp: PV_G cannot be issued until it has arrived on p_full below.)
         if (dead) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_empty);
-#pragma unroll
-          for (int e = 0; e < AK / 2; ++e) pk[e] = 0u;
+          if (i > 0) mbar_wait_tagged(pv_done, (G - 1) & 1, 7);
+          st_p_chunk<0>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<1>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<2>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<3>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<4>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<5>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<6>(p_row_sw, 0u, 0u, 0u, 0u);
+          st_p_chunk<7>(p_row_sw, 0u, 0u, 0u, 0u);
         } else {
           float s[AK];
           {
@@ -322,25 +364,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float mu = m_used == -INFINITY ? 0.f : m_used;
           const uint64_t nmu2 = f2_pack(-mu, -mu);
           uint64_t sum2 = 0ull, sum2b = 0ull;
+          if (i > 0) mbar_wait_tagged(pv_done, (G - 1) & 1, 7);  // (a second wait on a completed phase returns at once)
+          auto chunk = [&](auto cc) {  // 8 columns -> one 16-byte chunk of the P row, stored as it is produced
+            constexpr int c = decltype(cc)::value;
+            float pe[8];
 #pragma unroll
-          for (int e = 0; e < AK / 2; ++e) {
-            float x0, x1;
-            f2_unpack(f2_fma(f2_pack(s[2 * e], s[2 * e + 1]), scale2, nmu2), x0, x1);
-            const float p0 = ex2(x0), p1 = ex2(x1);  // masked: fma(-inf, .) = -inf -> 0
-            if (e & 1) sum2b = f2_add(sum2b, f2_pack(p0, p1));
-            else sum2 = f2_add(sum2, f2_pack(p0, p1));
-            pk[e] = pack_half2(p0, p1);
-          }
+            for (int e = 0; e < 4; ++e) {
+              float x0, x1;
+              f2_unpack(f2_fma(f2_pack(s[c * 8 + 2 * e], s[c * 8 + 2 * e + 1]), scale2, nmu2), x0, x1);
+              pe[2 * e] = ex2(x0);      // masked: fma(-inf, .) = -inf -> 0
+              pe[2 * e + 1] = ex2(x1);
+              if (e & 1) sum2b = f2_add(sum2b, f2_pack(pe[2 * e], pe[2 * e + 1]));
+              else sum2 = f2_add(sum2, f2_pack(pe[2 * e], pe[2 * e + 1]));
+            }
+            st_p_chunk<c>(p_row_sw, pack_half2(pe[0], pe[1]), pack_half2(pe[2], pe[3]), pack_half2(pe[4], pe[5]),
+                          pack_half2(pe[6], pe[7]));
+          };
+          chunk(IntC<0>{}); chunk(IntC<1>{}); chunk(IntC<2>{}); chunk(IntC<3>{});
+          chunk(IntC<4>{}); chunk(IntC<5>{}); chunk(IntC<6>{}); chunk(IntC<7>{});
           l2 = f2_add(l2, f2_add(sum2, sum2b));
         }
-        // P smem was read by PV_{G-1}.  (Also keeps pv_done at most one phase ahead of this warp: PV_G cannot be
-        // issued until it has arrived on p_full below.)
-        if (i > 0) mbar_wait_tagged(pv_done, (G - 1) & 1, 7);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_dst + ((c ^ sw) << 4)), "r"(pk[4 * c]),
-                       "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                       : "memory");
         fence_proxy_async_smem();  // P written with st.shared must be visible to the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();
@@ -378,7 +421,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       g += it.nb;
-    VRAG_ITEM_LOOP_END
+    }
   }
 
   tc_fence_before();
