@@ -1,7 +1,8 @@
 // Exact top-k similarity scan behind the vector store (dense COSINE, sparse IP).
 //
-// Pipeline per query tile (<= 8 queries per corpus pass):
-//   1. scan     : stream the corpus once from HBM, fp32 FMA dot products -> scores[q][row]       (HBM-bound)
+// Pipeline per query tile (one corpus pass each: <= 8 queries on the FMA scan, 16 on the tensor-core scan):
+//   1. scan     : stream the corpus once from HBM, fp32 FMA dot products (or split-tf32 tcgen05 MMAs)
+//                 -> scores[q][row]                                                               (HBM-bound)
 //   2. select   : per query, threshold-filtered warp top-k' lists over 64-bit keys
 //                 key = (ordered(score) << 32) | ~row   => order (score desc, row asc); two levels
 //   3. rescore  : the k' = k + margin candidates are re-evaluated in fp64 from the stored fp32 values
@@ -9,6 +10,7 @@
 // The fp64 rescoring makes results independent of the summation order of pass 1 and identical across shard
 // counts, which is what lets the sharded multi-GPU search be bit-identical to the 1-GPU search.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <memory>
@@ -250,6 +252,210 @@ dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __
             deleted[row] ? -INFINITY : total * inv_norm_q[qi] * inv_norm_d[row];
     }
     if (++st == nstage) { st = 0; ph ^= 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------------- dense: scan, tensor cores
+// 16 queries per corpus pass (the HBM-bound regime of the batched search).  scores = X Q^T on tcgen05
+// kind::tf32 with fp32-level accuracy from a three-term split: x = x_hi + x_lo, q = q_hi + q_lo (each part exactly
+// representable in tf32), x.q ~= x_hi.q_hi + x_hi.q_lo + x_lo.q_hi, fp32 accumulation in TMEM; the dropped x_lo.q_lo
+// term is 2^-22 relative, the size of one fp32 rounding.  Exactness of the final ids does not rest on it anyway: as on
+// the FMA path these scores only pick the k + margin candidates that are re-scored in fp64.
+//   warp 0      : TMA producer — corpus tile chunks [128 rows x 32 dims] fp32 (SWIZZLE_128B box, 16 KB), 4-stage ring
+//   warps 2..9  : split        — x_hi = rna_tf32(x) written back in place, x_lo = rna_tf32(x - x_hi) to a second tile;
+//                               two groups of 4 warps take alternate stages (thread = row), so the proxy fence that
+//                               ends a stage (~0.5k cycles) overlaps the other group's stage
+//   warp 1      : MMA issuer   — D1[128 x 32] += X_hi [Q_hi ; Q_lo]^T   (N = 32),  D2[128 x 16] += X_lo Q_hi^T (N = 16)
+//                               B = the query block, split once per CTA, resident in smem (dim/32 swizzled 4 KB tiles)
+//   warps 10..13: epilogue     — tcgen05.ld, (D1[q] + D1[16+q] + D2[q]) * 1/|q| * 1/|x| -> scores[q][row] (coalesced
+//                               along rows); two TMEM accumulator buffers, so it overlaps the next tile's MMAs
+constexpr int TCQ = 16;
+constexpr int TC_ROWS = 128;
+constexpr int TC_STAGES = 4;
+constexpr int TC_SPLIT_WARPS = 8, TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + TC_EPI_WARPS);
+constexpr int TC_TILE_BYTES = TC_ROWS * 128;   // one [128 x 32] fp32 tile
+constexpr int TC_BTILE_BYTES = 2 * TCQ * 128;  // one [32 x 32] fp32 tile of the split query block
+constexpr uint32_t TC_TMEM_COLS = 128;         // 2 buffers x 64 columns: [0,32) D1, [32,48) D2
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim, const float* __restrict__ queries,
+                     int nq, const float* __restrict__ inv_norm_d, const float* __restrict__ inv_norm_q,
+                     const uint8_t* __restrict__ deleted, float* __restrict__ scores) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nchunk = dim / 32;
+  uint8_t* sA = smem;                                   // stage s: hi tile at s*32 KB, lo tile at +16 KB
+  uint8_t* sB = sA + TC_STAGES * 2 * TC_TILE_BYTES;     // nchunk tiles of 4 KB: rows 0..15 q_hi, 16..31 q_lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(nchunk) * TC_BTILE_BYTES);
+  uint64_t* full = bars;                     // [TC_STAGES] TMA landed
+  uint64_t* split_done = full + TC_STAGES;   // [TC_STAGES] hi / lo tiles written
+  uint64_t* stage_empty = split_done + TC_STAGES;  // [TC_STAGES] MMAs reading the stage completed
+  uint64_t* d_full = stage_empty + TC_STAGES;      // [2]
+  uint64_t* d_empty = d_full + 2;                  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int64_t ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+
+  // split query block -> swizzled K-major tiles (element (row, k): tile k/32, 16-byte chunk ((k%32)/4) ^ (row & 7))
+  for (int i = threadIdx.x; i < 2 * TCQ * (dim / 4); i += blockDim.x) {
+    const int row = i / (dim / 4), k4 = i - row * (dim / 4);
+    const int qrow = row & (TCQ - 1);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qrow < nq) q = __ldg(reinterpret_cast<const float4*>(queries + static_cast<size_t>(qrow) * dim) + k4);
+    float4 h = make_float4(rna_tf32(q.x), rna_tf32(q.y), rna_tf32(q.z), rna_tf32(q.w));
+    if (row >= TCQ) h = make_float4(rna_tf32(q.x - h.x), rna_tf32(q.y - h.y), rna_tf32(q.z - h.z), rna_tf32(q.w - h.w));
+    const int c = k4 >> 3, j = k4 & 7;
+    sts128(smem_u32(sB) + c * TC_BTILE_BYTES + row * 128 + ((j ^ (row & 7)) << 4), h);
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(split_done + s, TC_SPLIT_WARPS / 2);
+      mbar_init(stage_empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(d_full + b, 1);
+      mbar_init(d_empty + b, TC_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, TC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t gs = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int c = 0; c < nchunk; ++c, ++gs) {
+        const int st = gs % TC_STAGES;
+        mbar_wait_tagged(stage_empty + st, ((gs / TC_STAGES) & 1) ^ 1, 21);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full + st, TC_TILE_BYTES);
+          tma_load_2d(sA + st * 2 * TC_TILE_BYTES, &tmX, full + st, c * 32, static_cast<int32_t>(t * TC_ROWS));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_hi = umma_idesc(2, TC_ROWS, 2 * TCQ);
+    constexpr uint32_t idesc_lo = umma_idesc(2, TC_ROWS, TCQ);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    uint32_t gs = 0, ti = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      mbar_wait_tagged(d_empty + buf, ((ti >> 1) & 1) ^ 1, 22);  // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d1 = tmem_base + buf * 64, d2 = d1 + 2 * TCQ;
+      for (int c = 0; c < nchunk; ++c, ++gs) {
+        const int st = gs % TC_STAGES;
+        mbar_wait_tagged(split_done + st, (gs / TC_STAGES) & 1, 23);
+        tc_fence_after();
+        const uint32_t hi = a_base + st * 2 * TC_TILE_BYTES, lo = hi + TC_TILE_BYTES, bt = b_base + c * TC_BTILE_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // K = 8 tf32 = 32 bytes per instruction
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_tf32(d1, umma_desc_sw128(hi + k * 32), umma_desc_sw128(bt + k * 32), idesc_hi, acc);
+            umma_tf32(d2, umma_desc_sw128(lo + k * 32), umma_desc_sw128(bt + k * 32), idesc_lo, acc);
+          }
+          umma_commit(stage_empty + st);
+          if (c + 1 == nchunk) umma_commit(d_full + buf);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
+    // ------------------------------------------------------------------ split warps: 2 groups x (thread = row)
+    const int sidx = threadIdx.x - 64, group = sidx >> 7, row = sidx & 127;
+    const uint32_t a_base = smem_u32(sA);
+    const int sw = row & 7;
+    uint32_t gs = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int c = 0; c < nchunk; ++c, ++gs) {
+        if ((gs & 1) != static_cast<uint32_t>(group)) continue;  // TC_STAGES is even: a stage always has the same group
+        const int st = gs % TC_STAGES;
+        mbar_wait_tagged(full + st, (gs / TC_STAGES) & 1, 24);
+        const uint32_t hi = a_base + st * 2 * TC_TILE_BYTES + row * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = static_cast<uint32_t>((i ^ sw) << 4);
+          const float4 x = lds128(hi + off);
+          const float4 h = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
+          const float4 l = make_float4(rna_tf32(x.x - h.x), rna_tf32(x.y - h.y), rna_tf32(x.z - h.z), rna_tf32(x.w - h.w));
+          sts128(hi + off, h);
+          sts128(hi + TC_TILE_BYTES + off, l);
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_done + st);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: thread = row (TMEM lane)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float qn[TCQ];
+#pragma unroll
+    for (int q = 0; q < TCQ; ++q) qn[q] = q < nq ? inv_norm_q[q] : 0.f;
+    uint32_t ti = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1;
+      mbar_wait_tagged(d_full + buf, (ti >> 1) & 1, 25);
+      tc_fence_after();
+      uint32_t d1[32], d2[16];
+      tmem_ld_32x32b_x32(t_lane + buf * 64, d1);
+      tmem_ld_32x32b_x16(t_lane + buf * 64 + 2 * TCQ, d2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + buf);
+      const int64_t row = t * TC_ROWS + r;
+      if (row < n) {
+        const float inv = inv_norm_d[row];
+        const bool dead = deleted[row] != 0;
+#pragma unroll
+        for (int q = 0; q < TCQ; ++q)
+          if (q < nq) {
+            const float v = (__uint_as_float(d1[TCQ + q]) + __uint_as_float(d2[q])) + __uint_as_float(d1[q]);
+            scores[static_cast<size_t>(q) * n + row] = dead ? -INFINITY : v * qn[q] * inv;
+          }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -816,13 +1022,33 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   query_norm_kernel<<<nq, 32, 0, _ctx->stream>>>(qd, dim, idx->qnorm.as<float>());
   VRAG_CUDA(cudaGetLastError());
   _ctx->launches++;
-  idx->scores.reserve(static_cast<size_t>(QT) * n * 4);
+  // more than 8 queries left: 16 per corpus pass on the tensor cores (the split query block must fit in smem)
+  static const bool simt_only = getenv("VRAG_SCAN_SIMT") != nullptr;  // debug: force the FMA path
+  const bool tc_ok = !simt_only && dim % 32 == 0 && dim <= 768 && n < (int64_t(1) << 31) - TC_ROWS;
+  idx->scores.reserve(static_cast<size_t>(tc_ok && nq > QT ? TCQ : QT) * n * 4);
   const int grid = static_cast<int>(std::min<int64_t>((n + 31) / 32, static_cast<int64_t>(_ctx->num_sms) * 2));
-  for (int q0 = 0; q0 < nq; q0 += QT) {
-    const int nt = std::min(QT, nq - q0);
+  for (int q0 = 0; q0 < nq;) {
+    const bool use_tc = tc_ok && nq - q0 > QT;
+    const int nt = std::min(use_tc ? TCQ : QT, nq - q0);
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
-    {
+    if (use_tc) {
+      ProfScope prof(_ctx, PROF_SCAN);
+      const CUtensorMap tmX = make_tmap_2d(_ctx, idx->rows.as<float>(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                           static_cast<uint64_t>(n), dim, dim, TC_ROWS, 32);
+      const int smem = TC_STAGES * 2 * TC_TILE_BYTES + (dim / 32) * TC_BTILE_BYTES + 256 + 1024;
+      static bool attr = false;
+      if (!attr) {
+        VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+      }
+      const int tgrid = static_cast<int>(std::min<int64_t>((n + TC_ROWS - 1) / TC_ROWS, _ctx->num_sms));
+      dense_scan_tc_kernel<<<tgrid, TC_THREADS, smem, _ctx->stream>>>(tmX, n, dim, qt, nt, idx->inv32.as<float>(), qn,
+                                                                      idx->deleted.as<uint8_t>(),
+                                                                      idx->scores.as<float>());
+      VRAG_CUDA(cudaGetLastError());
+      _ctx->launches++;
+    } else {
       ProfScope prof(_ctx, PROF_SCAN);
       // two 32-row stages + the query block must fit in 227 KB of shared memory (dim 1024 does not: generic path)
       if ((dim == 768 || dim == 384) || (dim == 1024 && 2 * SCAN_ROWS * dim * 4 + 8 * dim * 4 < 220 * 1024)) {
@@ -861,6 +1087,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     }
     select_and_rank(idx, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
                     d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
+    q0 += nt;
   }
   if (!on_device) {
     VRAG_CUDA(cudaMemcpyAsync(ids_out, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
