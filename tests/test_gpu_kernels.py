@@ -215,6 +215,40 @@ def test_dense_topk_bit_exact_ids(ctx, n, dim, nq, k):
     ix.close()
 
 
+@pytest.mark.parametrize("nq", [5, 16, 40])
+def test_dense_topk_tensor_core_scan_near_ties(ctx, nq, monkeypatch):
+    """Tensor-core scan (>= 5 queries per call: split-tf32 tcgen05 MMAs) on a corpus whose top scores are packed
+    ~1e-5 apart — far below a single tf32 product's 5e-4 error — with ragged tile (n % 128 != 0), deleted rows and
+    exact duplicates; ids must equal the float64 oracle's and the FMA scan's (VRAG_SCAN_TC_MIN=0)."""
+    from verbatim_rag_b200 import _native
+    from oracle.flat_topk import dense_cosine_scores
+    rng = np.random.default_rng(77)
+    n, dim, k = 20011, 768, 10
+    centres = rng.standard_normal((nq, dim)).astype(np.float32)
+    corpus = (centres[rng.integers(0, nq, n)] + 0.01 * rng.standard_normal((n, dim))).astype(np.float32)
+    corpus[100] = corpus[50]                               # exact duplicate -> exact tie, lower row first
+    queries = centres.copy()
+    ix = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    ix.add_dense(corpus)
+    dead = [3, 50, 19999]
+    ix.mark_deleted(dead)
+    ids_tc, s_tc = ix.search_dense(queries, k)
+    monkeypatch.setenv("VRAG_SCAN_TC_MIN", "0")
+    ids_fma, s_fma = ix.search_dense(queries, k)
+    monkeypatch.delenv("VRAG_SCAN_TC_MIN")
+    sc = dense_cosine_scores(corpus, queries)
+    sc[:, dead] = -np.inf
+    top = np.sort(sc, axis=1)[:, ::-1][:, :k + 1]
+    _diag(test="dense_topk_tc_near_ties", nq=nq, min_gap=float(np.min(top[:, :-1] - top[:, 1:])),
+          tc_equals_fma=bool(np.array_equal(ids_tc, ids_fma)))
+    for qi in range(nq):
+        order = np.lexsort((np.arange(n), -sc[qi]))[:k]
+        assert np.array_equal(ids_tc[qi], order), qi
+        assert np.array_equal(ids_fma[qi], order), qi
+    assert np.array_equal(s_tc, s_fma)                     # both are the fp64 re-scored values
+    ix.close()
+
+
 def test_dense_topk_ties_and_deletes(ctx):
     from verbatim_rag_b200 import _native
     from oracle.flat_topk import dense_cosine_scores, dense_cosine_topk

@@ -30,13 +30,13 @@ def main():
         ctx.sync()
         return ids, sc
 
-    # cross-check: 64 queries in one call (tensor-core scan) vs 8 calls of 8 (FMA scan)
+    # cross-check: 64 queries in one call (tensor-core scan) vs 16 calls of 4 (FMA scan)
     ids_tc, sc_tc = search(q[:64].contiguous())
-    ids_fma = torch.cat([search(q[i:i + 8].contiguous())[0] for i in range(0, 64, 8)])
-    sc_fma = torch.cat([search(q[i:i + 8].contiguous())[1] for i in range(0, 64, 8)])
+    ids_fma = torch.cat([search(q[i:i + 4].contiguous())[0] for i in range(0, 64, 4)])
+    sc_fma = torch.cat([search(q[i:i + 4].contiguous())[1] for i in range(0, 64, 4)])
     out["tc_vs_fma_ids_equal"] = bool((ids_tc == ids_fma).all().item())
     out["tc_vs_fma_score_maxdiff"] = float((sc_tc - sc_fma).abs().max().item())
-    for nq in (1, 8, 16, 64, 256):
+    for nq in (1, 2, 4, 8, 16, 64, 256):
         qq = q[:nq].contiguous()
         search(qq)
         ctx.profile(True)

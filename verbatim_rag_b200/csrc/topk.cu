@@ -261,22 +261,29 @@ dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __
 // representable in tf32), x.q ~= x_hi.q_hi + x_hi.q_lo + x_lo.q_hi, fp32 accumulation in TMEM; the dropped x_lo.q_lo
 // term is 2^-22 relative, the size of one fp32 rounding.  Exactness of the final ids does not rest on it anyway: as on
 // the FMA path these scores only pick the k + margin candidates that are re-scored in fp64.
-//   warp 0      : TMA producer — corpus tile chunks [128 rows x 32 dims] fp32 (SWIZZLE_128B box, 16 KB), 4-stage ring
-//   warps 2..9  : split        — x_hi = rna_tf32(x) written back in place, x_lo = rna_tf32(x - x_hi) to a second tile;
-//                               two groups of 4 warps take alternate stages (thread = row), so the proxy fence that
-//                               ends a stage (~0.5k cycles) overlaps the other group's stage
-//   warp 1      : MMA issuer   — D1[128 x 32] += X_hi [Q_hi ; Q_lo]^T   (N = 32),  D2[128 x 16] += X_lo Q_hi^T (N = 16)
-//                               B = the query block, split once per CTA, resident in smem (dim/32 swizzled 4 KB tiles)
+//   warp 0      : TMA producer — corpus tile chunks [128 rows x 32 dims] fp32 (SWIZZLE_128B box, 16 KB), 6-stage ring
+//   warps 2..9  : split        — thread = corpus row: reads its 128 bytes from smem, x_hi = rna_tf32(x),
+//                               x_lo = rna_tf32(x - x_hi), and writes both as the A OPERAND INTO TENSOR MEMORY
+//                               (tcgen05.st, 4 A stages of 64 columns); two groups of 4 warps take alternate chunks.
+//                               (A first version wrote x_hi / x_lo back to shared memory: 100 KB of smem traffic per
+//                               chunk against a budget of 631 cycles x 128 B at the HBM rate, plus a proxy fence per
+//                               chunk — 4.3 TB/s.  With A in TMEM shared memory carries 38 KB per chunk.)
+//   warp 1      : MMA issuer   — D1[128 x 32] += X_hi [Q_hi ; Q_lo]^T   (N = 32),  D2[128 x 16] += X_lo Q_hi^T (N = 16),
+//                               A from TMEM, B = the query block, split once per CTA, resident in smem (dim/32
+//                               swizzled 4 KB tiles)
 //   warps 10..13: epilogue     — tcgen05.ld, (D1[q] + D1[16+q] + D2[q]) * 1/|q| * 1/|x| -> scores[q][row] (coalesced
 //                               along rows); two TMEM accumulator buffers, so it overlaps the next tile's MMAs
 constexpr int TCQ = 16;
+constexpr int TC_MIN_Q = 5;                    // smallest query tile sent to the tensor-core scan
 constexpr int TC_ROWS = 128;
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 6;                   // raw fp32 chunks in shared memory (even: see the split groups)
+constexpr int TC_ASTAGES = 4;                  // split A operands in tensor memory
 constexpr int TC_SPLIT_WARPS = 8, TC_EPI_WARPS = 4;
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + TC_EPI_WARPS);
 constexpr int TC_TILE_BYTES = TC_ROWS * 128;   // one [128 x 32] fp32 tile
 constexpr int TC_BTILE_BYTES = 2 * TCQ * 128;  // one [32 x 32] fp32 tile of the split query block
-constexpr uint32_t TC_TMEM_COLS = 128;         // 2 buffers x 64 columns: [0,32) D1, [32,48) D2
+constexpr uint32_t TC_TMEM_COLS = 512;         // D: 2 x 64 columns ([0,32) D1, [32,48) D2); A: 4 x 64 from column 128
+constexpr uint32_t TC_TMEM_A0 = 128;
 
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
@@ -299,14 +306,15 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const int nchunk = dim / 32;
-  uint8_t* sA = smem;                                   // stage s: hi tile at s*32 KB, lo tile at +16 KB
-  uint8_t* sB = sA + TC_STAGES * 2 * TC_TILE_BYTES;     // nchunk tiles of 4 KB: rows 0..15 q_hi, 16..31 q_lo
+  uint8_t* sA = smem;                                   // raw chunk ring
+  uint8_t* sB = sA + TC_STAGES * TC_TILE_BYTES;         // nchunk tiles of 4 KB: rows 0..15 q_hi, 16..31 q_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(nchunk) * TC_BTILE_BYTES);
-  uint64_t* full = bars;                     // [TC_STAGES] TMA landed
-  uint64_t* split_done = full + TC_STAGES;   // [TC_STAGES] hi / lo tiles written
-  uint64_t* stage_empty = split_done + TC_STAGES;  // [TC_STAGES] MMAs reading the stage completed
-  uint64_t* d_full = stage_empty + TC_STAGES;      // [2]
-  uint64_t* d_empty = d_full + 2;                  // [2]
+  uint64_t* full = bars;                       // [TC_STAGES]  TMA landed
+  uint64_t* raw_empty = full + TC_STAGES;      // [TC_STAGES]  split warps hold the chunk in registers
+  uint64_t* a_full = raw_empty + TC_STAGES;    // [TC_ASTAGES] x_hi / x_lo written to TMEM
+  uint64_t* a_empty = a_full + TC_ASTAGES;     // [TC_ASTAGES] MMAs reading the A stage completed
+  uint64_t* d_full = a_empty + TC_ASTAGES;     // [2]
+  uint64_t* d_empty = d_full + 2;              // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -328,8 +336,11 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(split_done + s, TC_SPLIT_WARPS / 2);
-      mbar_init(stage_empty + s, 1);
+      mbar_init(raw_empty + s, TC_SPLIT_WARPS / 2);
+    }
+    for (int s = 0; s < TC_ASTAGES; ++s) {
+      mbar_init(a_full + s, TC_SPLIT_WARPS / 2);
+      mbar_init(a_empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(d_full + b, 1);
@@ -353,10 +364,10 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       for (int c = 0; c < nchunk; ++c, ++gs) {
         const int st = gs % TC_STAGES;
-        mbar_wait_tagged(stage_empty + st, ((gs / TC_STAGES) & 1) ^ 1, 21);
+        mbar_wait_tagged(raw_empty + st, ((gs / TC_STAGES) & 1) ^ 1, 21);
         if (elect_one()) {
           mbar_arrive_expect_tx(full + st, TC_TILE_BYTES);
-          tma_load_2d(sA + st * 2 * TC_TILE_BYTES, &tmX, full + st, c * 32, static_cast<int32_t>(t * TC_ROWS));
+          tma_load_2d(sA + st * TC_TILE_BYTES, &tmX, full + st, c * 32, static_cast<int32_t>(t * TC_ROWS));
         }
         __syncwarp();
       }
@@ -365,7 +376,7 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_hi = umma_idesc(2, TC_ROWS, 2 * TCQ);
     constexpr uint32_t idesc_lo = umma_idesc(2, TC_ROWS, TCQ);
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t b_base = smem_u32(sB);
     uint32_t gs = 0, ti = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
       const uint32_t buf = ti & 1;
@@ -373,18 +384,18 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
       tc_fence_after();
       const uint32_t d1 = tmem_base + buf * 64, d2 = d1 + 2 * TCQ;
       for (int c = 0; c < nchunk; ++c, ++gs) {
-        const int st = gs % TC_STAGES;
-        mbar_wait_tagged(split_done + st, (gs / TC_STAGES) & 1, 23);
+        const int as = gs % TC_ASTAGES;
+        mbar_wait_tagged(a_full + as, (gs / TC_ASTAGES) & 1, 23);
         tc_fence_after();
-        const uint32_t hi = a_base + st * 2 * TC_TILE_BYTES, lo = hi + TC_TILE_BYTES, bt = b_base + c * TC_BTILE_BYTES;
+        const uint32_t a_hi = tmem_base + TC_TMEM_A0 + as * 64, a_lo = a_hi + 32, bt = b_base + c * TC_BTILE_BYTES;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // K = 8 tf32 = 32 bytes per instruction
+          for (int k = 0; k < 4; ++k) {  // K = 8 tf32 per instruction = 8 TMEM columns of A, 32 bytes of a B row
             const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-            umma_tf32(d1, umma_desc_sw128(hi + k * 32), umma_desc_sw128(bt + k * 32), idesc_hi, acc);
-            umma_tf32(d2, umma_desc_sw128(lo + k * 32), umma_desc_sw128(bt + k * 32), idesc_lo, acc);
+            umma_tf32_ts(d1, a_hi + k * 8, umma_desc_sw128(bt + k * 32), idesc_hi, acc);
+            umma_tf32_ts(d2, a_lo + k * 8, umma_desc_sw128(bt + k * 32), idesc_lo, acc);
           }
-          umma_commit(stage_empty + st);
+          umma_commit(a_empty + as);
           if (c + 1 == nchunk) umma_commit(d_full + buf);
         }
         __syncwarp();
@@ -392,28 +403,43 @@ dense_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, int64_t n, int dim
     }
   } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ------------------------------------------------------------------ split warps: 2 groups x (thread = row)
-    const int sidx = threadIdx.x - 64, group = sidx >> 7, row = sidx & 127;
-    const uint32_t a_base = smem_u32(sA);
+    const int group = (warp - 2) >> 2, quarter = warp & 3;  // TMEM lane quarter: warp w may touch lanes 32*(w%4)..
+    const int row = quarter * 32 + lane;
+    const uint32_t raw_row = smem_u32(sA) + row * 128;
+    const uint32_t t_lane = tmem_base + TC_TMEM_A0 + (static_cast<uint32_t>(quarter * 32) << 16);
     const int sw = row & 7;
     uint32_t gs = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       for (int c = 0; c < nchunk; ++c, ++gs) {
-        if ((gs & 1) != static_cast<uint32_t>(group)) continue;  // TC_STAGES is even: a stage always has the same group
-        const int st = gs % TC_STAGES;
+        if ((gs & 1) != static_cast<uint32_t>(group)) continue;  // stage counts are even: fixed group per stage
+        const int st = gs % TC_STAGES, as = gs % TC_ASTAGES;
         mbar_wait_tagged(full + st, (gs / TC_STAGES) & 1, 24);
-        const uint32_t hi = a_base + st * 2 * TC_TILE_BYTES + row * 128;
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = lds128(raw_row + st * TC_TILE_BYTES + ((i ^ sw) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_empty + st);  // (release: ordered after this warp's reads of the chunk)
+        uint32_t hi[32], lo[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t off = static_cast<uint32_t>((i ^ sw) << 4);
-          const float4 x = lds128(hi + off);
-          const float4 h = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
-          const float4 l = make_float4(rna_tf32(x.x - h.x), rna_tf32(x.y - h.y), rna_tf32(x.z - h.z), rna_tf32(x.w - h.w));
-          sts128(hi + off, h);
-          sts128(hi + TC_TILE_BYTES + off, l);
+          const float h0 = rna_tf32(x[i].x), h1 = rna_tf32(x[i].y), h2 = rna_tf32(x[i].z), h3 = rna_tf32(x[i].w);
+          hi[4 * i] = __float_as_uint(h0);
+          hi[4 * i + 1] = __float_as_uint(h1);
+          hi[4 * i + 2] = __float_as_uint(h2);
+          hi[4 * i + 3] = __float_as_uint(h3);
+          lo[4 * i] = __float_as_uint(rna_tf32(x[i].x - h0));
+          lo[4 * i + 1] = __float_as_uint(rna_tf32(x[i].y - h1));
+          lo[4 * i + 2] = __float_as_uint(rna_tf32(x[i].z - h2));
+          lo[4 * i + 3] = __float_as_uint(rna_tf32(x[i].w - h3));
         }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_wait_tagged(a_empty + as, ((gs / TC_ASTAGES) & 1) ^ 1, 26);
+        tc_fence_after();
+        tmem_st_32x32b_x32(t_lane + as * 64, hi);
+        tmem_st_32x32b_x32(t_lane + as * 64 + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_done + st);
+        if (lane == 0) mbar_arrive(a_full + as);
       }
     }
   } else {
@@ -1022,13 +1048,15 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   query_norm_kernel<<<nq, 32, 0, _ctx->stream>>>(qd, dim, idx->qnorm.as<float>());
   VRAG_CUDA(cudaGetLastError());
   _ctx->launches++;
-  // more than 8 queries left: 16 per corpus pass on the tensor cores (the split query block must fit in smem)
-  static const bool simt_only = getenv("VRAG_SCAN_SIMT") != nullptr;  // debug: force the FMA path
-  const bool tc_ok = !simt_only && dim % 32 == 0 && dim <= 768 && n < (int64_t(1) << 31) - TC_ROWS;
-  idx->scores.reserve(static_cast<size_t>(tc_ok && nq > QT ? TCQ : QT) * n * 4);
+  // TC_MIN_Q or more queries left: 16 per corpus pass on the tensor cores (the split query block must fit in smem);
+  // fewer: the FMA scan, which is faster for 1..4 queries (measured: profiles/README.md)
+  const char* tc_env = getenv("VRAG_SCAN_TC_MIN");  // debug: 0 forces the FMA path, else the smallest tile for TC
+  const int tc_min = tc_env ? atoi(tc_env) : TC_MIN_Q;
+  const bool tc_ok = tc_min > 0 && dim % 32 == 0 && dim <= 768 && n < (int64_t(1) << 31) - TC_ROWS;
+  idx->scores.reserve(static_cast<size_t>(tc_ok ? TCQ : QT) * n * 4);
   const int grid = static_cast<int>(std::min<int64_t>((n + 31) / 32, static_cast<int64_t>(_ctx->num_sms) * 2));
   for (int q0 = 0; q0 < nq;) {
-    const bool use_tc = tc_ok && nq - q0 > QT;
+    const bool use_tc = tc_ok && nq - q0 >= tc_min;
     const int nt = std::min(use_tc ? TCQ : QT, nq - q0);
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
@@ -1036,7 +1064,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       ProfScope prof(_ctx, PROF_SCAN);
       const CUtensorMap tmX = make_tmap_2d(_ctx, idx->rows.as<float>(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                                            static_cast<uint64_t>(n), dim, dim, TC_ROWS, 32);
-      const int smem = TC_STAGES * 2 * TC_TILE_BYTES + (dim / 32) * TC_BTILE_BYTES + 256 + 1024;
+      const int smem = TC_STAGES * TC_TILE_BYTES + (dim / 32) * TC_BTILE_BYTES + 256 + 1024;
       static bool attr = false;
       if (!attr) {
         VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
