@@ -113,6 +113,13 @@ int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_
  * an in-library SIMT reference GEMM on random data and return the max |diff| (device-side self check). */
 int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff, double* ref_abs_max);
 
+/* Timing hook (bench.py's per-kernel table, development): `iters` back-to-back launches of one encoder GEMM shape
+ * (epilogue numbering of csrc/gemm.cuh) on synthetic device operands, CUDA events on the library's stream.
+ * stages: operand ring depth 3..5 (0 = the context's default); debug_mode 3 skips the epilogue (mainloop only).
+ * *ms_out = average launch time in milliseconds. */
+int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
+                    double* ms_out);
+
 /* Debug / test hook: one self-attention launch (12 heads x 64, as in both encoders; reference semantics:
  * transformers ModernBertAttention sdpa path -- softmax(q k^T / 8 + window mask) v per sequence) on caller-supplied
  * fp16 rows qkv_f16 [total_tokens, 2304] = q|k|v (q, k already rotated), host memory.  window < 0: full attention,

@@ -33,7 +33,8 @@ def test_tcgen05_gemm_matches_simt_reference(ctx, M, N, K):
     assert diff <= 1e-3 * max(ref_max, 1.0), (diff, ref_max)
 
 
-@pytest.mark.parametrize("epi,name", [(0, "f16"), (1, "rope_qkv"), (2, "resid_f32"), (3, "geglu")])
+@pytest.mark.parametrize("epi,name", [(0, "f16"), (1, "rope_qkv"), (2, "resid_f32"), (3, "geglu"),
+                                      (11, "resid_stats"), (12, "norm_rope_qkv"), (13, "norm_geglu")])
 @pytest.mark.parametrize("M", [128, 300, 5000])
 def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
     """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel."""
@@ -42,6 +43,16 @@ def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
     _diag(test="gemm_epilogue_selftest", epilogue=name, M=M, max_abs_diff=diff, ref_abs_max=ref_max)
     tol = 2e-3 if epi != 2 else 1e-4   # fp16 outputs: one rounding of slightly different fp32 sums
     assert diff <= tol * max(ref_max, 1.0), (name, diff, ref_max)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 768, 768), (129, 768, 1152), (40000, 768, 768), (33000, 768, 1152)])
+def test_residual_stats_epilogue_encoder_shapes(ctx, M, N, K):
+    """Wo / mlp.Wo shapes of the deferred-LayerNorm path: x += acc through TMA-loaded residual boxes, fp16 copy and
+    the per-row partial moments (sum, sum of squares) vs the SIMT reference (many tiles per CTA pair at the large M:
+    exercises the flat chunk stream across tiles and an odd number of M tiles)."""
+    diff, ref_max = ctx.selftest_gemm(M, N, K, 11)
+    _diag(test="gemm_resid_stats", M=M, N=N, K=K, max_abs_diff=diff, ref_abs_max=ref_max)
+    assert diff <= 2e-3 * max(ref_max, 1.0), (diff, ref_max)
 
 
 # ------------------------------------------------------------------------------------------ ModernBERT

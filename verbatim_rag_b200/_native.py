@@ -24,7 +24,7 @@ POOL_MEAN, POOL_CLS = 0, 1
 EXPORTS = [
     "vrag_ctx_create", "vrag_ctx_destroy", "vrag_last_error", "vrag_sync", "vrag_stream", "vrag_launch_count",
     "vrag_version", "vrag_profile", "vrag_profile_read", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
-    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_selftest_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
+    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_bench_gemm", "vrag_selftest_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
@@ -76,6 +76,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_splade_forward": (i32, [vp, vp, vp, i32, f32, vp, vp, vp, i64, P(i64), vp, i32]),
             "vrag_dense_forward": (i32, [vp, vp, vp, i32, i32, i32, vp, i32]),
             "vrag_selftest_gemm": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
+            "vrag_bench_gemm": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, P(f64)]),
             "vrag_selftest_attention": (i32, [vp, vp, vp, i32, i32, i32, vp]),
             "vrag_spans_from_probs": (i32, [vp, vp, vp, vp, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
             "vrag_index_create": (i32, [vp, i32, i32, P(vp)]),
@@ -154,10 +155,18 @@ class Context:
 
     def selftest_gemm(self, M: int, N: int, K: int, epilogue: int = 10) -> Tuple[float, float]:
         """tcgen05 GEMM vs the SIMT reference GEMM on the device; epilogue 10 = fp32, 0 = fp16, 1 = RoPE-QKV,
-        2 = fp32 residual add, 3 = GeGLU."""
+        2 = fp32 residual add, 3 = GeGLU, 11 = residual add + fp16 copy + row moments, 12 / 13 = RoPE-QKV / GeGLU
+        on rstd-scaled accumulators (deferred LayerNorm)."""
         d, m = C.c_double(), C.c_double()
         self.check(self.lib.vrag_selftest_gemm(self.h, M, N, K, epilogue, C.byref(d), C.byref(m)))
         return d.value, m.value
+
+    def bench_gemm(self, M: int, N: int, K: int, epilogue: int, stages: int = 0, debug_mode: int = 0,
+                   iters: int = 10) -> float:
+        """Average launch time (ms) of one encoder GEMM shape on synthetic operands (CUDA events)."""
+        ms = C.c_double()
+        self.check(self.lib.vrag_bench_gemm(self.h, M, N, K, epilogue, stages, debug_mode, iters, C.byref(ms)))
+        return ms.value
 
     def selftest_attention(self, qkv_f16, cu_seqlens, window: int = -1, legacy: bool = False):
         """One attention launch on host fp16 rows qkv_f16 [T, 2304] (q|k|v, 12 heads x 64); returns fp16 [T, 768]."""

@@ -26,18 +26,20 @@ void* vrag_ctx::pinned_reserve(size_t n) {
 namespace vrag {
 
 CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt, size_t elem_bytes, uint64_t rows,
-                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols,
+                         CUtensorMapSwizzle swizzle) {
   CUtensorMap m;
   memset(&m, 0, sizeof(m));
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {row_stride_elems * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  VRAG_CHECK(box_cols * elem_bytes == 128, VRAG_ERR_INTERNAL, "tensor map: inner box must span 128 bytes");
+  VRAG_CHECK(box_cols * elem_bytes == (swizzle == CU_TENSOR_MAP_SWIZZLE_64B ? 64u : 128u), VRAG_ERR_INTERNAL,
+             "tensor map: inner box must span the swizzle width (128 / 64 bytes)");
   VRAG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (gstride[0] & 15) == 0, VRAG_ERR_INTERNAL,
              "tensor map: base / stride not 16-byte aligned");
   CUresult r = ctx->encode_tiled(&m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(VRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   return m;
@@ -72,6 +74,10 @@ extern "C" int vrag_ctx_create(int device, vrag_ctx** out) {
     VRAG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) throw Error(VRAG_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     c->encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (const char* st = getenv("VRAG_GEMM_STAGES")) {
+      const int v = atoi(st);
+      if (v >= 3 && v <= 5) c->gemm_stages = v;
+    }
     *out = c.release();
     return VRAG_OK;
   } catch (const Error& e) {
@@ -217,6 +223,14 @@ __global__ void fill_pos_kernel(int32_t* p, size_t n, int max_pos) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = static_cast<int32_t>(hash_u32(static_cast<uint32_t>(i) + 7u) % max_pos);
 }
+// plausible partial row moments (sum, sum of squares) for the deferred-LayerNorm epilogues: |sum| <= 8, sumsq in [64, 192]
+__global__ void fill_stats_kernel(float* p, size_t n_pairs, uint32_t seed) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const uint32_t h = hash_u32(static_cast<uint32_t>(i) * 2654435761u + seed);
+  p[2 * i] = (static_cast<float>(h & 0xffff) / 32768.0f - 1.0f) * 8.0f;
+  p[2 * i + 1] = 128.0f + (static_cast<float>(h >> 16) / 32768.0f - 1.0f) * 64.0f;
+}
 template <typename T>
 __global__ void diff_kernel(const T* a, const T* b, size_t n, float* out /*[2]: max diff, max |b|*/) {
   float d = 0.f, m = 0.f;
@@ -240,19 +254,28 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
     VRAG_CUDA(cudaSetDevice(ctx->device));
-    const bool f32_out = epilogue == EPI_F32 || epilogue == EPI_RESID_F32;
-    VRAG_CHECK(epilogue == EPI_F32 || epilogue == EPI_F16 || epilogue == EPI_ROPE_QKV || epilogue == EPI_RESID_F32 ||
-                   epilogue == EPI_GEGLU, VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3");
-    VRAG_CHECK(epilogue != EPI_ROPE_QKV || N % 192 == 0, VRAG_ERR_ARG, "selftest_gemm: ROPE needs N = 3 * hidden");
-    const int out_cols = epilogue == EPI_GEGLU ? N / 2 : N;
+    const bool stats = epilogue == EPI_RESID_STATS;
+    const bool f32_out = epilogue == EPI_F32 || epilogue == EPI_RESID_F32 || stats;
+    const bool rope = epilogue == EPI_ROPE_QKV || epilogue == EPI_NORM_ROPE_QKV;
+    const bool geglu = epilogue == EPI_GEGLU || epilogue == EPI_NORM_GEGLU;
+    VRAG_CHECK(epilogue == EPI_F32 || epilogue == EPI_F16 || epilogue == EPI_RESID_F32 || rope || geglu || stats,
+               VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3, 11, 12, 13");
+    VRAG_CHECK(!rope || N % 192 == 0, VRAG_ERR_ARG, "selftest_gemm: ROPE needs N = 3 * hidden");
+    const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
     const size_t out_bytes = out_n * (f32_out ? 4 : 2);
     const int max_pos = 512;
-    DevBuf A, W, C0, C1, R, POS, CS, SN;
+    const int slots = N / 128;   // EPI_RESID_STATS writes one (sum, sumsq) pair per row and 128 columns
+    const size_t st_pairs = static_cast<size_t>(M) * (stats ? slots : 6);
+    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS, SN;
     A.reserve(static_cast<size_t>(M) * K * 2);
     W.reserve(static_cast<size_t>(N) * K * 2);
     C0.reserve(out_bytes);
     C1.reserve(out_bytes);
+    H0.reserve(out_n * 2);
+    H1.reserve(out_n * 2);
+    S0.reserve(st_pairs * 8);
+    S1.reserve(st_pairs * 8);
     R.reserve(8);
     POS.reserve(static_cast<size_t>(M) * 4);
     CS.reserve(static_cast<size_t>(max_pos) * 32 * 4);
@@ -263,12 +286,20 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos);
     fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(CS.as<float>(), max_pos * 32, 5u, 1.0f);
     fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(SN.as<float>(), max_pos * 32, 6u, 1.0f);
-    if (epilogue == EPI_RESID_F32) {  // both paths accumulate onto the same initial residual
+    if (epilogue == EPI_RESID_F32 || stats) {  // both paths accumulate onto the same initial residual
       fill_float_kernel<<<blocks_for(out_n), 256, 0, st>>>(C0.as<float>(), out_n, 33u, 1.0f);
       VRAG_CUDA(cudaMemcpyAsync(C1.p, C0.p, out_bytes, cudaMemcpyDeviceToDevice, st));
     } else {
       VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, out_bytes, st));  // NaN pattern: unwritten outputs are detected
       VRAG_CUDA(cudaMemsetAsync(C1.p, 0, out_bytes, st));
+    }
+    if (stats) {
+      VRAG_CUDA(cudaMemsetAsync(H0.p, 0xff, out_n * 2, st));
+      VRAG_CUDA(cudaMemsetAsync(H1.p, 0, out_n * 2, st));
+      VRAG_CUDA(cudaMemsetAsync(S0.p, 0xff, st_pairs * 8, st));
+      VRAG_CUDA(cudaMemsetAsync(S1.p, 0, st_pairs * 8, st));
+    } else {   // moments read by the EPI_NORM_* epilogues (identical for both paths)
+      fill_stats_kernel<<<blocks_for(st_pairs), 256, 0, st>>>(S0.as<float>(), st_pairs, 8u);
     }
     VRAG_CUDA(cudaMemsetAsync(R.p, 0, 8, st));
     for (int ref = 0; ref < 2; ++ref) {
@@ -276,24 +307,110 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       p.M = M;
       p.ld32 = out_cols; p.ld16 = out_cols;
       p.out32 = (ref ? C1 : C0).as<float>();
-      p.out16 = (ref ? C1 : C0).as<__half>();
+      p.out16 = stats ? (ref ? H1 : H0).as<__half>() : (ref ? C1 : C0).as<__half>();
       p.pos = POS.as<int32_t>(); p.rope_cos = CS.as<float>(); p.rope_sin = SN.as<float>();
       p.hidden = N / 3;
+      p.stats_in = S0.as<float>();
+      p.stats_out = stats ? (ref ? S1 : S0).as<float>() : nullptr;
+      p.stats_slots = 6;
       launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, ref);
     }
     if (f32_out) diff_kernel<float><<<256, 256, 0, st>>>(C0.as<float>(), C1.as<float>(), out_n, R.as<float>());
     else diff_kernel<__half><<<256, 256, 0, st>>>(C0.as<__half>(), C1.as<__half>(), out_n, R.as<float>());
-    float h[2];
+    float h[2], hs[2] = {0.f, 0.f};
     VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, st));
     VRAG_CUDA(cudaStreamSynchronize(st));
+    if (stats) {   // the fp16 copy like the fp32 stream; the moments relative to their magnitude
+      diff_kernel<__half><<<256, 256, 0, st>>>(H0.as<__half>(), H1.as<__half>(), out_n, R.as<float>());
+      VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, st));
+      VRAG_CUDA(cudaStreamSynchronize(st));
+      VRAG_CUDA(cudaMemsetAsync(R.p, 0, 8, st));
+      diff_kernel<float><<<256, 256, 0, st>>>(S0.as<float>(), S1.as<float>(), st_pairs * 2, R.as<float>());
+      VRAG_CUDA(cudaMemcpyAsync(hs, R.p, 8, cudaMemcpyDeviceToHost, st));
+      VRAG_CUDA(cudaStreamSynchronize(st));
+      const float rel = hs[0] / fmaxf(hs[1], 1.0f);
+      if (!(rel == rel)) h[0] = NAN;
+      else h[0] = fmaxf(h[0], rel * fmaxf(h[1], 1.0f));
+    }
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
-    for (DevBuf* b : {&A, &W, &C0, &C1, &R, &POS, &CS, &SN}) b->release();
+    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS, &SN}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();
     return e.code;
   } catch (const std::exception& e) {
+    ctx->last_error = e.what();
+    return VRAG_ERR_INTERNAL;
+  }
+}
+
+// GEMM timing hook (development / bench.py's per-kernel table): `iters` back-to-back launches of one encoder GEMM
+// shape on synthetic operands, CUDA events on the library's stream; *ms_out = average launch time.
+extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
+                               double* ms_out) {
+  if (!ctx || !ms_out || iters < 1) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const int saved_stages = ctx->gemm_stages;
+  try {
+    VRAG_CUDA(cudaSetDevice(ctx->device));
+    VRAG_CHECK(epilogue == EPI_F16 || epilogue == EPI_ROPE_QKV || epilogue == EPI_RESID_F32 || epilogue == EPI_GEGLU ||
+                   epilogue == EPI_RESID_STATS || epilogue == EPI_NORM_ROPE_QKV || epilogue == EPI_NORM_GEGLU,
+               VRAG_ERR_ARG, "bench_gemm: unsupported epilogue");
+    const bool f32_out = epilogue == EPI_RESID_F32 || epilogue == EPI_RESID_STATS;
+    const bool geglu = epilogue == EPI_GEGLU || epilogue == EPI_NORM_GEGLU;
+    const int out_cols = geglu ? N / 2 : N;
+    const size_t out_n = static_cast<size_t>(M) * out_cols;
+    const int max_pos = 512;
+    DevBuf A, W, C, C16, POS, CS, SN, ST;
+    A.reserve(static_cast<size_t>(M) * K * 2);
+    W.reserve(static_cast<size_t>(N) * K * 2);
+    C.reserve(out_n * (f32_out ? 4 : 2));
+    C16.reserve(out_n * 2);
+    POS.reserve(static_cast<size_t>(M) * 4);
+    CS.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    SN.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    ST.reserve(static_cast<size_t>(M) * 12 * 4);
+    cudaStream_t st = ctx->stream;
+    fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
+    fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
+    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos);
+    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(CS.as<float>(), max_pos * 32, 5u, 1.0f);
+    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(SN.as<float>(), max_pos * 32, 6u, 1.0f);
+    fill_stats_kernel<<<blocks_for(static_cast<size_t>(M) * 6), 256, 0, st>>>(ST.as<float>(), static_cast<size_t>(M) * 6, 8u);
+    VRAG_CUDA(cudaMemsetAsync(C.p, 0, out_n * (f32_out ? 4 : 2), st));
+    GemmEpiParams p;
+    p.M = M;
+    p.ld32 = out_cols; p.ld16 = out_cols;
+    p.out32 = C.as<float>();
+    p.out16 = f32_out ? C16.as<__half>() : C.as<__half>();
+    p.pos = POS.as<int32_t>(); p.rope_cos = CS.as<float>(); p.rope_sin = SN.as<float>();
+    p.hidden = N / 3;
+    p.stats_in = ST.as<float>(); p.stats_out = ST.as<float>(); p.stats_slots = 6;
+    p.debug_mode = debug_mode;
+    if (stages >= 3 && stages <= 5) ctx->gemm_stages = stages;
+    cudaEvent_t e0, e1;
+    VRAG_CUDA(cudaEventCreate(&e0));
+    VRAG_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, 0);
+    VRAG_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, 0);
+    VRAG_CUDA(cudaEventRecord(e1, st));
+    VRAG_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    VRAG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->gemm_stages = saved_stages;
+    for (DevBuf* b : {&A, &W, &C, &C16, &POS, &CS, &SN, &ST}) b->release();
+    return VRAG_OK;
+  } catch (const Error& e) {
+    ctx->gemm_stages = saved_stages;
+    ctx->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->gemm_stages = saved_stages;
     ctx->last_error = e.what();
     return VRAG_ERR_INTERNAL;
   }

@@ -91,6 +91,7 @@ struct vrag_ctx {
   vrag::PFN_encodeTiled encode_tiled = nullptr;
   std::string last_error;
   std::mutex mu;           // one call at a time per context (plugin objects are shared across threads)
+  int gemm_stages = 4;     // operand ring depth of the tcgen05 GEMM (VRAG_GEMM_STAGES = 3 | 4 | 5)
   uint64_t launches = 0;   // kernels launched through this context (bench.py's gpu_launches)
   // pinned staging for the *_host entry points
   void* pinned = nullptr;
@@ -101,8 +102,10 @@ struct vrag_ctx {
 namespace vrag {
 
 // 2D row-major tensor map, 128-byte swizzle, box = {box_cols (128 bytes worth), box_rows}.
+// (CU_TENSOR_MAP_SWIZZLE_64B: inner box of 64 bytes.)
 CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt, size_t elem_bytes, uint64_t rows,
-                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+                         uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 struct ProfScope {
   vrag_ctx* c;

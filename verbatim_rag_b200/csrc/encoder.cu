@@ -25,6 +25,7 @@ struct vrag_encoder {
   int ffn = 0;  // GeGLU width (1152) or FFN width (3072)
   bool use_reference_gemm = false;
   bool legacy_attention = false;
+  bool deferred_ln = true;  // ModernBERT: LayerNorm folded into the GEMMs (EPI_RESID_STATS / EPI_NORM_*), no LN kernels
   void attention(const __half* qkv, __half* out, int nseq, int total_tokens, int max_len, int window) {
     if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
     else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), work.as<int32_t>(), n_pairs, total_tokens, 12,
@@ -50,13 +51,13 @@ struct vrag_encoder {
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work;
+      pooled, work, stats;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
-                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work})
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats})
       b->release();
   }
   template <typename T>
@@ -121,6 +122,18 @@ void make_rope(vrag_encoder* e, double theta, int max_pos, float** cos_out, floa
   VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
 }
 
+// Deferred LayerNorm: LN(x) W^T = rstd(x) * (x W''^T) with W''[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma[:]) (each row
+// of W'' sums to zero, which is what subtracts the row mean of x).  Computed in double from the fp32 checkpoint.
+void fold_layernorm(const float* w, const float* gamma, size_t rows, size_t cols, float* out) {
+  for (size_t n = 0; n < rows; ++n) {
+    double acc = 0.0;
+    for (size_t k = 0; k < cols; ++k) acc += static_cast<double>(w[n * cols + k]) * gamma[k];
+    const double mean = acc / static_cast<double>(cols);
+    for (size_t k = 0; k < cols; ++k)
+      out[n * cols + k] = static_cast<float>(static_cast<double>(w[n * cols + k]) * gamma[k] - mean);
+  }
+}
+
 void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   const int H = HIDDEN, I = 1152;
   e->ffn = I;
@@ -128,17 +141,28 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   DevBuf staging;
   e->emb = upload_f32(e, w.get("model.embeddings.tok_embeddings.weight", (int64_t)e->vocab * H), (size_t)e->vocab * H);
   e->emb_g = upload_f32(e, w.get("model.embeddings.norm.weight", H), H);
-  std::vector<float> wi_perm(static_cast<size_t>(2 * I) * H);
+  std::vector<float> wi_perm(static_cast<size_t>(2 * I) * H), folded(static_cast<size_t>(3 * H) * H);
   for (int i = 0; i < e->layers; ++i) {
     const std::string p = "model.layers." + std::to_string(i) + ".";
     vrag_encoder::MLayer L{};
-    L.attn_g = i > 0 ? upload_f32(e, w.get(p + "attn_norm.weight", H), H) : nullptr;
-    L.wqkv = upload_f16(e, staging, w.get(p + "attn.Wqkv.weight", 3LL * H * H), 3 * H, H);
+    const float* attn_g = i > 0 ? w.get(p + "attn_norm.weight", H) : nullptr;
+    const float* mlp_g = w.get(p + "mlp_norm.weight", H);
+    L.attn_g = attn_g ? upload_f32(e, attn_g, H) : nullptr;
+    const float* wqkv = w.get(p + "attn.Wqkv.weight", 3LL * H * H);
+    if (e->deferred_ln && attn_g) {
+      fold_layernorm(wqkv, attn_g, 3 * H, H, folded.data());
+      wqkv = folded.data();
+    }
+    L.wqkv = upload_f16(e, staging, wqkv, 3 * H, H);
     L.wo = upload_f16(e, staging, w.get(p + "attn.Wo.weight", (int64_t)H * H), H, H);
-    L.mlp_g = upload_f32(e, w.get(p + "mlp_norm.weight", H), H);
+    L.mlp_g = upload_f32(e, mlp_g, H);
     // GeGLU: Wi = [input rows 0..I) | gate rows I..2I).  Interleave per 128 so one 256-wide GEMM tile holds
     // input[128t..128t+128) and gate[128t..128t+128) -> act(input)*gate is tile-local (EPI_GEGLU).
     const float* wi = w.get(p + "mlp.Wi.weight", 2LL * I * H);
+    if (e->deferred_ln) {
+      fold_layernorm(wi, mlp_g, 2 * I, H, folded.data());
+      wi = folded.data();
+    }
     for (int t = 0; t < I / 128; ++t) {
       memcpy(&wi_perm[static_cast<size_t>(t * 256) * H], wi + static_cast<size_t>(t * 128) * H, sizeof(float) * 128 * H);
       memcpy(&wi_perm[static_cast<size_t>(t * 256 + 128) * H], wi + static_cast<size_t>(I + t * 128) * H,
@@ -223,6 +247,7 @@ void reserve_workspace(vrag_encoder* e) {
   e->buf32.reserve(T * H * 4);
   e->probs.reserve(T * 4);
   e->logits.reserve(T * 8);
+  if (e->kind == VRAG_ENC_MODERNBERT_TOKCLS && e->deferred_ln) e->stats.reserve(T * 6 * 8);
 }
 
 struct Pass { int s0, s1, t0, t1, max_len; };
@@ -281,27 +306,32 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
       VRAG_CUDA(cudaMemcpyAsync(hidden_dbg_host + static_cast<size_t>(slot) * T * H, x32,
                                 static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
   };
+  // h16 always holds the A operand of the next Wqkv / Wi GEMM: LN(x) (plain path), or the fp16 copy of the raw
+  // residual stream (deferred LayerNorm: row moments in `stats`, gamma and the mean folded into the weights).
+  const bool dln = e->deferred_ln;
+  float* stats = e->stats.as<float>();
   launch_embed_ln(ctx, e->ids.as<int32_t>(), T, e->vocab, e->emb, e->emb_g, 1e-5f, x32, h16);
   dump(0);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->ml[i];
     const bool global = (i % 3) == 0;
-    if (i > 0) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false);
+    if (i > 0 && !dln) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false);
     GemmEpiParams p;
     p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.hidden = H; p.pos = e->pos.as<int32_t>();
     p.rope_cos = global ? e->cos_g : e->cos_l;
     p.rope_sin = global ? e->sin_g : e->sin_l;
-    launch_gemm(ctx, EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
+    p.stats_in = stats;
+    launch_gemm(ctx, (dln && i > 0) ? EPI_NORM_ROPE_QKV : EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);
     GemmEpiParams r;
-    r.M = T; r.out32 = x32; r.ld32 = H;
+    r.M = T; r.out32 = x32; r.ld32 = H; r.out16 = h16; r.ld16 = H; r.stats_out = stats;
     { const char* dm = getenv("VRAG_DEBUG_RESID"); r.debug_mode = dm ? atoi(dm) : 0; }
-    launch_gemm(ctx, EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
-    launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
+    launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
+    if (!dln) launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
     GemmEpiParams g;
-    g.M = T; g.out16 = g16; g.ld16 = I;
-    launch_gemm(ctx, EPI_GEGLU, h16, L.wi, T, 2 * I, H, g, ref);
-    launch_gemm(ctx, EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
+    g.M = T; g.out16 = g16; g.ld16 = I; g.stats_in = stats;
+    launch_gemm(ctx, dln ? EPI_NORM_GEGLU : EPI_GEGLU, h16, L.wi, T, 2 * I, H, g, ref);
+    launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
     dump(i + 1);
   }
   launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false);
@@ -379,6 +409,8 @@ extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int 
   e->use_reference_gemm = dbg && dbg[0] == '1';
   const char* leg = getenv("VRAG_ATTENTION_LEGACY");
   e->legacy_attention = leg && leg[0] == '1';
+  const char* dl = getenv("VRAG_DEFERRED_LN");   // "0": separate LayerNorm kernels (cross-check path)
+  e->deferred_ln = !(dl && dl[0] == '0');
   WeightSet w(tensors, num_tensors);
   if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
   else build_bert(e.get(), w);

@@ -14,7 +14,6 @@ namespace vrag {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = (BN / 2) * BK * 2;  // each CTA of the pair holds HALF of the 256-row W tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -22,9 +21,36 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 // to transpose the cos/sin rows of its 32 tokens into registers
 constexpr int EPI_BOX_BYTES = 4096;
 constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;
+constexpr int EPI_STATS_WARP_BYTES = 2 * EPI_BOX_BYTES + 2 * 2048;   // EPI_RESID_STATS: 2 x (fp32 box + fp16 half box)
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
                               // scheduler cannot hide its own ALU / TMEM-load latency, two can
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int epi_warp_bytes(int epi) { return epi == EPI_RESID_STATS ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES; }
+constexpr int smem_bytes(int stages, int epi) {
+  return stages * STAGE_BYTES + EPI_WARPS * epi_warp_bytes(epi) + 1024 /*align slack*/ + 512 /*barriers*/;
+}
+template <int EPI>
+constexpr bool kNorm = (EPI == EPI_NORM_ROPE_QKV || EPI == EPI_NORM_GEGLU);
+template <int EPI>
+constexpr bool kRope = (EPI == EPI_ROPE_QKV || EPI == EPI_NORM_ROPE_QKV);
+template <int EPI>
+constexpr bool kGeglu = (EPI == EPI_GEGLU || EPI == EPI_NORM_GEGLU);
+
+// Deferred LayerNorm: 1 / sqrt(var + eps) of row `row` of the A operand from the partial moments its producer wrote
+// (EPI_RESID_STATS).  One-pass variance E[x^2] - mean^2 in fp32 over 768 columns: relative error ~1e-6 unless
+// mean^2 >> var, which a residual stream does not do.
+__device__ __forceinline__ float row_rstd(const GemmEpiParams& p, int row) {
+  if (row >= p.M) return 0.f;
+  const float2* st = reinterpret_cast<const float2*>(p.stats_in);
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < p.stats_slots; ++j) {
+    const float2 v = __ldg(st + static_cast<size_t>(j) * p.M + row);
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * p.inv_dim;
+  const float var = fmaxf(q * p.inv_dim - mean * mean, 0.f);
+  return rsqrtf(var + p.ln_eps);
+}
 constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -133,17 +159,49 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         }
       }
     }
-  } else if constexpr (EPI == EPI_ROPE_QKV) {
+  } else if constexpr (EPI == EPI_RESID_STATS) {
+    float s = 0.f, q = 0.f;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      ld.load(c, v);
+      if (valid) {
+        float4* x4 = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = x4[i];
+          v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          x4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s += v[i];
+          q = fmaf(v[i], v[i], q);
+        }
+        store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32, v);
+        if ((c & 3) == 3) {
+          reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(2 * n_tile + (c >> 2)) * p.M + row] =
+              make_float2(s, q);
+          s = 0.f;
+          q = 0.f;
+        }
+      }
+    }
+  } else if constexpr (kRope<EPI>) {
     // 4 heads of 64 per tile.  x1 = dims [0,32), x2 = dims [32,64): out1 = x1*cos - x2*sin, out2 = x2*cos + x1*sin
     // (rotate_half convention, fp32, modeling_modernbert.py:197-228).
     float w2[32];
     const int pos = valid ? __ldg(p.pos + row) : 0;
     const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<size_t>(pos) * 32);
     const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<size_t>(pos) * 32);
+    const float rs = kNorm<EPI> ? row_rstd(p, row) : 1.f;
 #pragma unroll 1
     for (int h = 0; h < BN / 64; ++h) {
       ld.load(2 * h, v);
       ld.load(2 * h + 1, w2);
+      if constexpr (kNorm<EPI>) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] *= rs; w2[i] *= rs; }
+      }
       const int gcol = col0 + h * 64;
       if (gcol < 2 * p.hidden) {
 #pragma unroll
@@ -164,14 +222,15 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         store_half32(o + 32, w2);
       }
     }
-  } else if constexpr (EPI == EPI_GEGLU) {
+  } else if constexpr (kGeglu<EPI>) {
     float g[32];
+    const float rs = kNorm<EPI> ? row_rstd(p, row) : 1.f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       ld.load(c, v);
       ld.load(4 + c, g);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]) * g[i];
+      for (int i = 0; i < 32; ++i) v[i] = kNorm<EPI> ? gelu_erf(v[i] * rs) * (g[i] * rs) : gelu_erf(v[i]) * g[i];
       if (valid) store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + n_tile * 128 + c * 32, v);
     }
   } else if constexpr (EPI == EPI_SPLADE) {
@@ -211,8 +270,8 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 // double-buffered per warp; cp.async.bulk.wait_group.read gates buffer reuse.
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
-constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_ROPE_QKV ||
-                          EPI == EPI_GEGLU || EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32);
+constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kRope<EPI> ||
+                          kGeglu<EPI> || EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32);
 
 struct BoxStager {
   uint8_t* base;      // this warp's two boxes
@@ -262,6 +321,8 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   const int col0 = n_tile * BN;
   const int r = lane;  // row of this thread inside the warp's 32-row slab
   float v[32];
+  float rs = 1.f;      // deferred LayerNorm: 1 / sqrt(var + eps) of this thread's row
+  if constexpr (kNorm<EPI>) rs = row_rstd(p, m0 + lane);
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll 1
     for (int b = 2 * half; b < 2 * half + 2; ++b) {
@@ -285,7 +346,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
       }
       st.submit<false>(tmOut, box, col0 + b * 64, m0, lane);
     }
-  } else if constexpr (EPI == EPI_ROPE_QKV) {
+  } else if constexpr (kRope<EPI>) {
     const bool rotate = col0 < 2 * p.hidden;  // q / k tiles
     float cs[32], sn[32];                     // this thread's (row's) cos / sin, kept in registers for the 4 heads
     if (rotate) {
@@ -321,6 +382,10 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
       uint8_t* box = st.acquire(lane);
       ld.load(2 * h, v);
       ld.load(2 * h + 1, w2);
+      if constexpr (kNorm<EPI>) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { v[e] *= rs; w2[e] *= rs; }
+      }
       if (rotate) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -333,7 +398,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
       box_put_half32(box, r, 1, w2);
       st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
     }
-  } else if constexpr (EPI == EPI_GEGLU) {
+  } else if constexpr (kGeglu<EPI>) {
     float g[32];
 #pragma unroll 1
     for (int b = half; b < half + 1; ++b) {
@@ -343,7 +408,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
         ld.load(2 * b + h, v);
         ld.load(4 + 2 * b + h, g);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]) * g[i];
+        for (int i = 0; i < 32; ++i) v[i] = kNorm<EPI> ? gelu_erf(v[i] * rs) * (g[i] * rs) : gelu_erf(v[i]) * g[i];
         box_put_half32(box, r, h, v);
       }
       st.submit<false>(tmOut, box, n_tile * 128 + b * 64, m0, lane);
@@ -377,19 +442,21 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
 // The leader CTA (cluster rank 0) issues the MMAs; both CTAs' TMA loads signal the leader's `full` barrier; the MMA
 // commit is multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator by
 // arriving on the leader's `tmem_empty` barrier.
-template <int EPI>
+template <int EPI, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmOut, int m_tiles, int n_tiles, int k_blocks,
-                    GemmEpiParams p) {
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    int m_tiles, int n_tiles, int k_blocks, GemmEpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_WARP_BYTES);
+  constexpr int EPI_WB = epi_warp_bytes(EPI);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_WB);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_x = bar_tempty + 2;                 // [EPI_WARPS][2]: residual boxes of EPI_RESID_STATS
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_x + 2 * EPI_WARPS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -406,6 +473,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(bar_tfull + a, 1);
       mbar_init(bar_tempty + a, 2 * EPI_WARPS);   // leader's barrier: epilogue warps of BOTH CTAs arrive
     }
+    for (int a = 0; a < 2 * EPI_WARPS; ++a) mbar_init(bar_x + a, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -481,33 +549,134 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which half of the tile's 256 columns this warp drains
-    uint8_t* my_smem = epi_smem + (warp - 2) * EPI_WARP_BYTES;
-    BoxStager stager{my_smem, 0u};
-    if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
+    uint8_t* my_smem = epi_smem + (warp - 2) * EPI_WB;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
-      const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
-      mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
-      tc_fence_after();
-      TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
-      if constexpr (kStaged<EPI>)
-        staged_epilogue<EPI>(p, &tmOut, stager, m_idx * BM + quarter * 32, n_idx, ld, lane, half);
-      else
-        epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld, 4 * half, 4 * half + 4);
-      tc_fence_before();
-      __syncwarp();
+    if constexpr (EPI == EPI_RESID_STATS) {
+      // x = x_old + acc with x_old fetched by TMA: the warp's chunks (32 rows x 32 fp32 columns, four per tile) form
+      // one flat stream across tiles; chunk n lives in buffer n & 1 = {fp32 box (loaded, updated in place, stored),
+      // fp16 half box (stored)}; the load of chunk n + 1 is issued while chunk n is processed, as soon as the stores
+      // of chunk n - 1 (same buffer) have been read out of shared memory.
+      uint64_t* xb = bar_x + 2 * (warp - 2);
+      const int my_tiles = cluster_id < total_pairs ? (total_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
+      const uint32_t n_chunks = 4u * static_cast<uint32_t>(my_tiles);
       if (lane == 0) {
-        if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
-        else mbar_arrive_remote(bar_tempty + acc, 0);
+        tma_prefetch_desc(&tmOut);
+        tma_prefetch_desc(&tmOut2);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      auto chunk_xy = [&](uint32_t n, int& x, int& y) {
+        const int pair = cluster_id + static_cast<int>(n >> 2) * num_clusters;
+        x = (pair % n_tiles) * BN + (4 * half + static_cast<int>(n & 3)) * 32;
+        y = (2 * (pair / n_tiles) + cta_rank) * BM + quarter * 32;
+      };
+      auto issue_load = [&](uint32_t n) {   // elected lane
+        int x, y;
+        chunk_xy(n, x, y);
+        mbar_arrive_expect_tx(xb + (n & 1), EPI_BOX_BYTES);
+        tma_load_2d(my_smem + (n & 1) * EPI_BOX_BYTES, &tmOut, xb + (n & 1), x, y);
+      };
+      if (elect_one()) {
+        if (n_chunks > 0) issue_load(0);
+        if (n_chunks > 1) issue_load(1);
+      }
+      __syncwarp();
+      const int r = lane;
+      uint32_t n = 0;
+      for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+        const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
+        mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
+        tc_fence_after();
+        TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
+        float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc, ++n) {
+          uint8_t* fbox = my_smem + (n & 1) * EPI_BOX_BYTES;
+          uint8_t* hbox = my_smem + 2 * EPI_BOX_BYTES + (n & 1) * 2048;
+          float v[32];
+          ld.load(4 * half + cc, v);
+          if (n >= 1) {   // buffer (n + 1) & 1 was last stored from by chunk n - 1
+            if (elect_one()) {
+              bulk_wait_read<0>();
+              if (n + 1 < n_chunks) issue_load(n + 1);
+            }
+            __syncwarp();
+          }
+          mbar_wait_tagged(xb + (n & 1), (n >> 1) & 1, 15);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4* xp = reinterpret_cast<float4*>(fbox + r * 128 + ((i ^ (r & 7)) << 4));
+            const float4 x = *xp;
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+            *xp = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            sum += v[i];
+            sq = fmaf(v[i], v[i], sq);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {   // 64-byte rows, SWIZZLE_64B: 16-byte chunk i of row r at i ^ ((r >> 1) & 3)
+            uint4 u;
+            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(hbox + r * 64 + ((i ^ ((r >> 1) & 3)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            int x, y;
+            chunk_xy(n, x, y);
+            tma_store_2d(&tmOut, fbox, x, y);
+            tma_store_2d(&tmOut2, hbox, x, y);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+        const int row = m_idx * BM + quarter * 32 + lane;
+        if (row < p.M)
+          reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(2 * n_idx + half) * p.M + row] =
+              make_float2(sum, sq);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
+          else mbar_arrive_remote(bar_tempty + acc, 0);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (elect_one()) bulk_wait<0>();
+      __syncwarp();
+    } else {
+      BoxStager stager{my_smem, 0u};
+      if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
+      for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+        const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
+        mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
+        tc_fence_after();
+        TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
+        if (p.debug_mode == 3) {
+          // timing experiment: mainloop only
+        } else if constexpr (kStaged<EPI>)
+          staged_epilogue<EPI>(p, &tmOut, stager, m_idx * BM + quarter * 32, n_idx, ld, lane, half);
+        else
+          epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld, 4 * half, 4 * half + 4);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
+          else mbar_arrive_remote(bar_tempty + acc, 0);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (kStaged<EPI>) {
+        if (elect_one()) bulk_wait<0>();  // all TMA stores / reductions of this warp have landed
+      }
+      __syncwarp();
     }
-    if (kStaged<EPI>) {
-      if (elect_one()) bulk_wait<0>();  // all TMA stores / reductions of this warp have landed
-    }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -531,6 +700,24 @@ gemm_reference_kernel(const __half* __restrict__ A, const __half* __restrict__ W
   epilogue_row<EPI>(p, row, n_idx, ld);
 }
 
+template <int EPI, int STAGES>
+void launch_tc(vrag_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+               const CUtensorMap& tmOut2, int m_tiles, int n_tiles, int k_blocks, const GemmEpiParams& p) {
+  constexpr int SMEM_BYTES = smem_bytes(STAGES, EPI);
+  static_assert(SMEM_BYTES <= 232448, "GEMM shared memory exceeds the 227 KB per-CTA limit");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total_pairs = ((m_tiles + 1) / 2) * n_tiles;
+  const int max_clusters = ctx->num_sms / 2;
+  const int grid = 2 * (total_pairs < max_clusters ? total_pairs : max_clusters);   // CTA pairs (clusters of 2)
+  gemm_tcgen05_kernel<EPI, STAGES><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmOut2, m_tiles,
+                                                                                    n_tiles, k_blocks, p);
+}
+
 template <int EPI>
 void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int K, const GemmEpiParams& p,
               int use_reference) {
@@ -542,21 +729,25 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
     CUtensorMap tmA = make_tmap_2d(ctx, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, K, BM, BK);
     CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN / 2, BK);  // half W tile
     CUtensorMap tmOut = tmA;  // placeholder for the epilogues that write directly
-    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32)
+    CUtensorMap tmOut2 = tmA;
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_RESID_STATS)
       tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
     else if constexpr (kStaged<EPI>)
       tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
-    static bool attr_set[16] = {};
-    if (!attr_set[EPI]) {
-      VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM_BYTES));
-      attr_set[EPI] = true;
+    if constexpr (EPI == EPI_RESID_STATS) {
+      VRAG_CHECK(p.out16 && p.stats_out && p.ld16 == p.ld32, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / stats_out");
+      tmOut2 = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_64B);
+      // 2 x 6 KB of residual staging per epilogue warp leave room for 3 or 4 operand stages
+      if (ctx->gemm_stages == 3) launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
+      else launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
+    } else {
+      switch (ctx->gemm_stages) {
+        case 3: launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+        case 5: launch_tc<EPI, 5>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+        default: launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+      }
     }
-    const int total_pairs = ((m_tiles + 1) / 2) * n_tiles;
-    const int max_clusters = ctx->num_sms / 2;
-    const int grid = 2 * (total_pairs < max_clusters ? total_pairs : max_clusters);   // CTA pairs (clusters of 2)
-    gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, m_tiles, n_tiles,
-                                                                              k_blocks, p);
   }
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -580,6 +771,9 @@ void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M
     VRAG_CASE(EPI_GELU_F32)
     VRAG_CASE(EPI_BIAS_GELU_F32)
     VRAG_CASE(EPI_F32)
+    VRAG_CASE(EPI_RESID_STATS)
+    VRAG_CASE(EPI_NORM_ROPE_QKV)
+    VRAG_CASE(EPI_NORM_GEGLU)
 #undef VRAG_CASE
     default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
   }

@@ -17,6 +17,13 @@ enum GemmEpi : int {
   EPI_GELU_F32 = 8,       // out32 = gelu(acc)                  (ModernBERT head.dense)
   EPI_BIAS_GELU_F32 = 9,  // out32 = gelu(acc + bias)           (BERT MLM transform.dense)
   EPI_F32 = 10,           // out32 = acc                        (self test)
+  // Deferred LayerNorm (ModernBERT pre-LN blocks).  LN(x) W^T = rstd(x) * (x W''^T) with
+  // W''[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma) folded at load time, so the consumer GEMM reads the RAW residual
+  // (fp16 copy) and only needs one scalar per row; the producer GEMM emits that copy and the row moments.
+  EPI_RESID_STATS = 11,   // x = out32 + acc; out32 = x; out16 = fp16(x); stats_out[slot][row] = (sum x, sum x^2)
+                          // over this warp's 128 columns (slot = 2 * n_tile + column half); N = 768 -> 6 slots
+  EPI_NORM_ROPE_QKV = 12, // EPI_ROPE_QKV on rstd[row] * acc
+  EPI_NORM_GEGLU = 13,    // EPI_GEGLU on rstd[row] * acc
 };
 
 struct GemmEpiParams {
@@ -33,6 +40,11 @@ struct GemmEpiParams {
   float* splade_out = nullptr;        // [nseq, splade_ld], zero-initialised
   int splade_ld = 0;
   int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail)
+  const float* stats_in = nullptr;    // EPI_NORM_*: [stats_slots][M] float2 partial row moments of the A operand's rows
+  float* stats_out = nullptr;         // EPI_RESID_STATS: [N / 128][M] float2
+  int stats_slots = 6;
+  float ln_eps = 1e-5f;
+  float inv_dim = 1.0f / 768.0f;      // 1 / (number of columns the moments were taken over)
   int M = 0;                          // valid rows
   int debug_mode = 0;                 // timing experiments only (VRAG_DEBUG_RESID): 1 = plain store instead of
                                       // reduce-add (wrong values), 2 = no store at all
