@@ -35,9 +35,11 @@ def test_tcgen05_gemm_matches_simt_reference(ctx, M, N, K):
 
 @pytest.mark.parametrize("epi,name", [(0, "f16"), (1, "rope_qkv"), (2, "resid_f32"), (3, "geglu"),
                                       (11, "resid_stats"), (12, "norm_rope_qkv"), (13, "norm_geglu")])
-@pytest.mark.parametrize("M", [128, 300, 5000])
+@pytest.mark.parametrize("M", [128, 300, 5000, 1001])
 def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
-    """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel."""
+    """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel.
+    Token positions in the self test: even M = sequences of 200 tokens (RoPE slabs fetch cos / sin by TMA, the ones
+    straddling a sequence boundary gather), odd M = hashed positions (every slab gathers)."""
     N, K = 2304, 768
     diff, ref_max = ctx.selftest_gemm(M, N, K, epi)
     _diag(test="gemm_epilogue_selftest", epilogue=name, M=M, max_abs_diff=diff, ref_abs_max=ref_max)

@@ -21,23 +21,20 @@ def main():
             out["selftest"].append({"epi": epi, "M": M, "N": N, "K": K, "error": str(e)})
         print(out["selftest"][-1], flush=True)
     M = int(os.environ.get("PROBE_M", "131072"))
-    shapes = [("wqkv", 1, 2304, 768), ("wqkv_norm", 12, 2304, 768), ("wi", 3, 2304, 768), ("wi_norm", 13, 2304, 768),
-              ("wo", 2, 768, 768), ("wo_stats", 11, 768, 768), ("wo2", 2, 768, 1152), ("wo2_stats", 11, 768, 1152)]
-    for name, epi, N, K in shapes:
-        for stages in (3, 4, 5):
-            if epi == 11 and stages == 5:
-                continue
-            for dbg in (0, 3):
-                if epi == 11 and dbg == 3:
-                    continue
-                try:
-                    ms = ctx.bench_gemm(M, N, K, epi, stages=stages, debug_mode=dbg, iters=10)
-                    rec = {"name": name, "epi": epi, "N": N, "K": K, "stages": stages, "debug": dbg, "ms": ms,
-                           "tflops": 2.0 * M * N * K / ms / 1e9}
-                except Exception as e:  # noqa: BLE001
-                    rec = {"name": name, "epi": epi, "stages": stages, "debug": dbg, "error": str(e)}
-                out["bench"].append(rec)
-                print(rec, flush=True)
+    plan = [("wqkv", 1, 2304, 768, (0, 3, 4, 7, 8)), ("wqkv_norm", 12, 2304, 768, (0,)),
+            ("wi", 3, 2304, 768, (0, 3, 4, 7, 8)), ("wi_norm", 13, 2304, 768, (0,)),
+            ("wo", 2, 768, 768, (0,)), ("wo_stats", 11, 768, 768, (0, 4, 6)),
+            ("wo2", 2, 768, 1152, (0,)), ("wo2_stats", 11, 768, 1152, (0, 4, 6))]
+    for name, epi, N, K, modes in plan:
+        for dbg in modes:
+            try:
+                ms = ctx.bench_gemm(M, N, K, epi, stages=0, debug_mode=dbg, iters=10)
+                rec = {"name": name, "epi": epi, "N": N, "K": K, "debug": dbg, "ms": round(ms, 4),
+                       "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}
+            except Exception as e:  # noqa: BLE001
+                rec = {"name": name, "epi": epi, "debug": dbg, "error": str(e)}
+            out["bench"].append(rec)
+            print(rec, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gemm_probe.json"), "w") as f:
         json.dump(out, f, indent=1)

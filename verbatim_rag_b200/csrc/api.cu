@@ -219,9 +219,12 @@ __global__ void fill_float_kernel(float* p, size_t n, uint32_t seed, float scale
   if (i >= n) return;
   p[i] = (static_cast<float>(hash_u32(static_cast<uint32_t>(i) * 2654435761u + seed) & 0xffff) / 32768.0f - 1.0f) * scale;
 }
-__global__ void fill_pos_kernel(int32_t* p, size_t n, int max_pos) {
+// mode 0: sequences of 200 tokens back to back; 1: hashed positions; 2: sequences of 512 tokens
+__global__ void fill_pos_kernel(int32_t* p, size_t n, int max_pos, int mode) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = static_cast<int32_t>(hash_u32(static_cast<uint32_t>(i) + 7u) % max_pos);
+  if (i >= n) return;
+  if (mode == 1) p[i] = static_cast<int32_t>(hash_u32(static_cast<uint32_t>(i) + 7u) % max_pos);
+  else p[i] = static_cast<int32_t>(i % (mode == 0 ? 200 : 512)) % max_pos;
 }
 // plausible partial row moments (sum, sum of squares) for the deferred-LayerNorm epilogues: |sum| <= 8, sumsq in [64, 192]
 __global__ void fill_stats_kernel(float* p, size_t n_pairs, uint32_t seed) {
@@ -267,7 +270,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     const int max_pos = 512;
     const int slots = N / 128;   // EPI_RESID_STATS writes one (sum, sumsq) pair per row and 128 columns
     const size_t st_pairs = static_cast<size_t>(M) * (stats ? slots : 6);
-    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS, SN;
+    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS;
     A.reserve(static_cast<size_t>(M) * K * 2);
     W.reserve(static_cast<size_t>(N) * K * 2);
     C0.reserve(out_bytes);
@@ -278,14 +281,14 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     S1.reserve(st_pairs * 8);
     R.reserve(8);
     POS.reserve(static_cast<size_t>(M) * 4);
-    CS.reserve(static_cast<size_t>(max_pos) * 32 * 4);
-    SN.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    CS.reserve(static_cast<size_t>(max_pos) * 64 * 4);
     cudaStream_t st = ctx->stream;
     fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
     fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
-    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos);
-    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(CS.as<float>(), max_pos * 32, 5u, 1.0f);
-    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(SN.as<float>(), max_pos * 32, 6u, 1.0f);
+    // positions: runs of consecutive positions (sequences of 200 tokens: slabs of 32 rows that straddle a boundary take
+    // the gather path, the others the TMA path), or hashed positions (pos_mode 1: every slab gathers)
+    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos, (M % 2) ? 1 : 0);
+    fill_float_kernel<<<blocks_for(max_pos * 64), 256, 0, st>>>(CS.as<float>(), max_pos * 64, 5u, 1.0f);
     if (epilogue == EPI_RESID_F32 || stats) {  // both paths accumulate onto the same initial residual
       fill_float_kernel<<<blocks_for(out_n), 256, 0, st>>>(C0.as<float>(), out_n, 33u, 1.0f);
       VRAG_CUDA(cudaMemcpyAsync(C1.p, C0.p, out_bytes, cudaMemcpyDeviceToDevice, st));
@@ -308,7 +311,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       p.ld32 = out_cols; p.ld16 = out_cols;
       p.out32 = (ref ? C1 : C0).as<float>();
       p.out16 = stats ? (ref ? H1 : H0).as<__half>() : (ref ? C1 : C0).as<__half>();
-      p.pos = POS.as<int32_t>(); p.rope_cos = CS.as<float>(); p.rope_sin = SN.as<float>();
+      p.pos = POS.as<int32_t>(); p.rope_tab = CS.as<float>(); p.rope_rows = max_pos;
       p.hidden = N / 3;
       p.stats_in = S0.as<float>();
       p.stats_out = stats ? (ref ? S1 : S0).as<float>() : nullptr;
@@ -334,7 +337,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     }
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
-    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS, &SN}) b->release();
+    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();
@@ -362,21 +365,19 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
     const int max_pos = 512;
-    DevBuf A, W, C, C16, POS, CS, SN, ST;
+    DevBuf A, W, C, C16, POS, CS, ST;
     A.reserve(static_cast<size_t>(M) * K * 2);
     W.reserve(static_cast<size_t>(N) * K * 2);
     C.reserve(out_n * (f32_out ? 4 : 2));
     C16.reserve(out_n * 2);
     POS.reserve(static_cast<size_t>(M) * 4);
-    CS.reserve(static_cast<size_t>(max_pos) * 32 * 4);
-    SN.reserve(static_cast<size_t>(max_pos) * 32 * 4);
+    CS.reserve(static_cast<size_t>(max_pos) * 64 * 4);
     ST.reserve(static_cast<size_t>(M) * 12 * 4);
     cudaStream_t st = ctx->stream;
     fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
     fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
-    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos);
-    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(CS.as<float>(), max_pos * 32, 5u, 1.0f);
-    fill_float_kernel<<<blocks_for(max_pos * 32), 256, 0, st>>>(SN.as<float>(), max_pos * 32, 6u, 1.0f);
+    fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos, 2);   // sequences of 512 tokens
+    fill_float_kernel<<<blocks_for(max_pos * 64), 256, 0, st>>>(CS.as<float>(), max_pos * 64, 5u, 1.0f);
     fill_stats_kernel<<<blocks_for(static_cast<size_t>(M) * 6), 256, 0, st>>>(ST.as<float>(), static_cast<size_t>(M) * 6, 8u);
     VRAG_CUDA(cudaMemsetAsync(C.p, 0, out_n * (f32_out ? 4 : 2), st));
     GemmEpiParams p;
@@ -384,7 +385,7 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     p.ld32 = out_cols; p.ld16 = out_cols;
     p.out32 = C.as<float>();
     p.out16 = f32_out ? C16.as<__half>() : C.as<__half>();
-    p.pos = POS.as<int32_t>(); p.rope_cos = CS.as<float>(); p.rope_sin = SN.as<float>();
+    p.pos = POS.as<int32_t>(); p.rope_tab = CS.as<float>(); p.rope_rows = max_pos;
     p.hidden = N / 3;
     p.stats_in = ST.as<float>(); p.stats_out = ST.as<float>(); p.stats_slots = 6;
     p.debug_mode = debug_mode;
@@ -403,7 +404,7 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     ctx->gemm_stages = saved_stages;
-    for (DevBuf* b : {&A, &W, &C, &C16, &POS, &CS, &SN, &ST}) b->release();
+    for (DevBuf* b : {&A, &W, &C, &C16, &POS, &CS, &ST}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->gemm_stages = saved_stages;

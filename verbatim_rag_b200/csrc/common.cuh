@@ -91,7 +91,7 @@ struct vrag_ctx {
   vrag::PFN_encodeTiled encode_tiled = nullptr;
   std::string last_error;
   std::mutex mu;           // one call at a time per context (plugin objects are shared across threads)
-  int gemm_stages = 4;     // operand ring depth of the tcgen05 GEMM (VRAG_GEMM_STAGES = 3 | 4 | 5)
+  int gemm_stages = 5;     // operand ring depth of the tcgen05 GEMM (VRAG_GEMM_STAGES = 3 | 4 | 5)
   uint64_t launches = 0;   // kernels launched through this context (bench.py's gpu_launches)
   // pinned staging for the *_host entry points
   void* pinned = nullptr;

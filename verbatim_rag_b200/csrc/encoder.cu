@@ -39,7 +39,7 @@ struct vrag_encoder {
   std::vector<MLayer> ml;
   float *final_g = nullptr, *head_g = nullptr, *cls_w = nullptr, *cls_b = nullptr;
   __half* head_w = nullptr;
-  float *cos_g = nullptr, *sin_g = nullptr, *cos_l = nullptr, *sin_l = nullptr;
+  float *rope_g = nullptr, *rope_l = nullptr;  // [max_pos, 64] cos | sin tables (global / local theta)
   // BERT
   struct BLayer {
     __half* wqkv; float* bqkv; __half* wo; float* bo; float *g1, *b1; __half* wi; float* bi; __half* wo2; float* bo2;
@@ -106,19 +106,20 @@ __half* upload_f16(vrag_encoder* e, DevBuf& staging, const float* host, size_t r
   return d;
 }
 
-void make_rope(vrag_encoder* e, double theta, int max_pos, float** cos_out, float** sin_out) {
-  // cos/sin of pos * inv_freq[j], inv_freq[j] = theta^(-2j/64), fp32 like modeling_modernbert.py:138-172
-  std::vector<float> c(static_cast<size_t>(max_pos) * 32), s(c.size());
+void make_rope(vrag_encoder* e, double theta, int max_pos, float** tab_out) {
+  // row p = cos(p * inv_freq[0..32)) | sin(p * inv_freq[0..32)), inv_freq[j] = theta^(-2j/64), fp32 like
+  // modeling_modernbert.py:138-172.  One 256-byte row per position: the GEMM epilogue fetches the rows of 32
+  // consecutive positions with one TMA box each for cos and sin.
+  std::vector<float> t(static_cast<size_t>(max_pos) * 64);
   for (int j = 0; j < 32; ++j) {
     const float inv = 1.0f / powf(static_cast<float>(theta), static_cast<float>(2 * j) / 64.0f);
     for (int p = 0; p < max_pos; ++p) {
       const float f = static_cast<float>(p) * inv;
-      c[static_cast<size_t>(p) * 32 + j] = static_cast<float>(cos(static_cast<double>(f)));
-      s[static_cast<size_t>(p) * 32 + j] = static_cast<float>(sin(static_cast<double>(f)));
+      t[static_cast<size_t>(p) * 64 + j] = static_cast<float>(cos(static_cast<double>(f)));
+      t[static_cast<size_t>(p) * 64 + 32 + j] = static_cast<float>(sin(static_cast<double>(f)));
     }
   }
-  *cos_out = upload_f32(e, c.data(), c.size());
-  *sin_out = upload_f32(e, s.data(), s.size());
+  *tab_out = upload_f32(e, t.data(), t.size());
   VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
 }
 
@@ -177,8 +178,8 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
   e->cls_w = upload_f32(e, w.get("classifier.weight", 2LL * H), 2 * H);
   e->cls_b = upload_f32(e, w.get("classifier.bias", 2), 2);
-  make_rope(e, 160000.0, e->max_pos, &e->cos_g, &e->sin_g);
-  make_rope(e, 10000.0, e->max_pos, &e->cos_l, &e->sin_l);
+  make_rope(e, 160000.0, e->max_pos, &e->rope_g);
+  make_rope(e, 10000.0, e->max_pos, &e->rope_l);
   staging.release();
 }
 
@@ -318,8 +319,8 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     if (i > 0 && !dln) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false);
     GemmEpiParams p;
     p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.hidden = H; p.pos = e->pos.as<int32_t>();
-    p.rope_cos = global ? e->cos_g : e->cos_l;
-    p.rope_sin = global ? e->sin_g : e->sin_l;
+    p.rope_tab = global ? e->rope_g : e->rope_l;
+    p.rope_rows = e->max_pos;
     p.stats_in = stats;
     launch_gemm(ctx, (dln && i > 0) ? EPI_NORM_ROPE_QKV : EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);

@@ -21,7 +21,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 // to transpose the cos/sin rows of its 32 tokens into registers
 constexpr int EPI_BOX_BYTES = 4096;
 constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;
-constexpr int EPI_STATS_WARP_BYTES = 2 * EPI_BOX_BYTES + 2 * 2048;   // EPI_RESID_STATS: 2 x (fp32 box + fp16 half box)
+constexpr int STATS_FBOXES = 3;   // EPI_RESID_STATS: residual boxes in flight per warp (prefetch distance 2)
+constexpr int EPI_STATS_WARP_BYTES = STATS_FBOXES * EPI_BOX_BYTES + 2 * 2048;   // fp32 boxes + 2 fp16 half boxes
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
                               // scheduler cannot hide its own ALU / TMEM-load latency, two can
 constexpr int epi_warp_bytes(int epi) { return epi == EPI_RESID_STATS ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES; }
@@ -55,6 +56,37 @@ constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// GeLU for two values at once on the packed fp32x2 pipe.  gelu(x) = x Phi(x) = 0.5 (x + |x|) - 0.5 |x| P(t) exp(-x^2 / 2)
+// with erfc(z) ~ P(t) exp(-z^2), t = 1 / (1 + p z), z = |x| / sqrt(2) (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7;
+// the form above has no cancellation for x < 0).  Measured against the exact erf form over [-12, 12]: max abs error
+// 3.3e-7 -- three orders below the fp16 rounding of the GeGLU output.  ~10 issue slots per element instead of ~35 for
+// erff: the Wi epilogue was issue-bound on the activation (vrag_bench_gemm, profiles/README.md).
+__device__ __forceinline__ uint64_t gelu2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  float d0, d1;
+  f2_unpack(f2_fma(ax, f2_pack(0.23164189f, 0.23164189f), f2_pack(1.f, 1.f)), d0, d1);   // 1 + (p / sqrt 2) |x|
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  uint64_t q = f2_fma(t, f2_pack(1.061405429f, 1.061405429f), f2_pack(-1.453152027f, -1.453152027f));
+  q = f2_fma(q, t, f2_pack(1.421413741f, 1.421413741f));
+  q = f2_fma(q, t, f2_pack(-0.284496736f, -0.284496736f));
+  q = f2_fma(q, t, f2_pack(0.254829592f, 0.254829592f));
+  q = f2_mul(q, t);
+  float g0, g1;
+  f2_unpack(f2_mul(f2_mul(x2, f2_pack(-0.72134752f, -0.72134752f)), x2), g0, g1);   // -x^2 log2(e) / 2
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const uint64_t pe = f2_mul(q, f2_pack(e0, e1));
+  const uint64_t m = f2_mul(ax, f2_pack(0.5f, 0.5f));
+  const uint64_t base = f2_fma(x2, f2_pack(0.5f, 0.5f), m);
+  return f2_fma(f2_mul(ax, f2_pack(-0.5f, -0.5f)), pe, base);
+}
 
 __device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) {
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -191,8 +223,8 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
     // (rotate_half convention, fp32, modeling_modernbert.py:197-228).
     float w2[32];
     const int pos = valid ? __ldg(p.pos + row) : 0;
-    const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<size_t>(pos) * 32);
-    const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<size_t>(pos) * 32);
+    const float4* cs4 = reinterpret_cast<const float4*>(p.rope_tab + static_cast<size_t>(pos) * 64);
+    const float4* sn4 = cs4 + 8;
     const float rs = kNorm<EPI> ? row_rstd(p, row) : 1.f;
 #pragma unroll 1
     for (int h = 0; h < BN / 64; ++h) {
@@ -276,8 +308,9 @@ constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BI
 struct BoxStager {
   uint8_t* base;      // this warp's two boxes
   uint32_t issued;    // boxes submitted so far (same value in every lane)
+  int dbg = 0;        // timing experiments (debug_mode 7: no wait before box reuse, 8: no proxy fence)
   __device__ __forceinline__ uint8_t* acquire(int lane) {
-    if (issued >= 2) {                                  // the box submitted two steps ago has been read out
+    if (issued >= 2 && dbg != 7) {                      // the box submitted two steps ago has been read out
       if (elect_one()) bulk_wait_read<1>();             // (bulk groups belong to the issuing = elected lane)
     }
     __syncwarp();
@@ -285,7 +318,7 @@ struct BoxStager {
   }
   template <bool REDUCE>
   __device__ __forceinline__ void submit(const CUtensorMap* tm, uint8_t* box, int x, int y, int lane) {
-    fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
+    if (dbg != 8) fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
     __syncwarp();
     if (elect_one()) {
       if (REDUCE) tma_reduce_add_2d(tm, box, x, y);
@@ -321,8 +354,6 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   const int col0 = n_tile * BN;
   const int r = lane;  // row of this thread inside the warp's 32-row slab
   float v[32];
-  float rs = 1.f;      // deferred LayerNorm: 1 / sqrt(var + eps) of this thread's row
-  if constexpr (kNorm<EPI>) rs = row_rstd(p, m0 + lane);
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll 1
     for (int b = 2 * half; b < 2 * half + 2; ++b) {
@@ -346,73 +377,6 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
       }
       st.submit<false>(tmOut, box, col0 + b * 64, m0, lane);
     }
-  } else if constexpr (kRope<EPI>) {
-    const bool rotate = col0 < 2 * p.hidden;  // q / k tiles
-    float cs[32], sn[32];                     // this thread's (row's) cos / sin, kept in registers for the 4 heads
-    if (rotate) {
-      // Borrow the warp's two store boxes as a transpose buffer: coalesced 128-byte reads of the 32 tokens'
-      // cos / sin rows, swizzled so the thread == row read-back is conflict free.
-      if (elect_one()) bulk_wait_read<0>();   // no TMA store may still be reading the boxes
-      __syncwarp();
-      float* cs_s = reinterpret_cast<float*>(st.base);
-      float* sn_s = reinterpret_cast<float*>(st.base + EPI_BOX_BYTES);
-      const int row = m0 + lane;
-      const int my_pos = row < p.M ? __ldg(p.pos + row) : 0;
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const int ps = __shfl_sync(0xffffffffu, my_pos, rr);
-        const int o = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
-        cs_s[o] = __ldg(p.rope_cos + static_cast<size_t>(ps) * 32 + lane);
-        sn_s[o] = __ldg(p.rope_sin + static_cast<size_t>(ps) * 32 + lane);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 c = *reinterpret_cast<const float4*>(cs_s + r * 32 + ((i ^ (r & 7)) << 2));
-        const float4 s4 = *reinterpret_cast<const float4*>(sn_s + r * 32 + ((i ^ (r & 7)) << 2));
-        cs[4 * i] = c.x; cs[4 * i + 1] = c.y; cs[4 * i + 2] = c.z; cs[4 * i + 3] = c.w;
-        sn[4 * i] = s4.x; sn[4 * i + 1] = s4.y; sn[4 * i + 2] = s4.z; sn[4 * i + 3] = s4.w;
-      }
-      __syncwarp();
-      st.issued = 0;                          // both boxes are free again; restart the double-buffer bookkeeping
-    }
-    float w2[32];
-#pragma unroll 1
-    for (int h = 2 * half; h < 2 * half + 2; ++h) {
-      uint8_t* box = st.acquire(lane);
-      ld.load(2 * h, v);
-      ld.load(2 * h + 1, w2);
-      if constexpr (kNorm<EPI>) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) { v[e] *= rs; w2[e] *= rs; }
-      }
-      if (rotate) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x1 = v[e], x2 = w2[e];
-          v[e] = x1 * cs[e] - x2 * sn[e];
-          w2[e] = x2 * cs[e] + x1 * sn[e];
-        }
-      }
-      box_put_half32(box, r, 0, v);
-      box_put_half32(box, r, 1, w2);
-      st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
-    }
-  } else if constexpr (kGeglu<EPI>) {
-    float g[32];
-#pragma unroll 1
-    for (int b = half; b < half + 1; ++b) {
-      uint8_t* box = st.acquire(lane);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        ld.load(2 * b + h, v);
-        ld.load(4 + 2 * b + h, g);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = kNorm<EPI> ? gelu_erf(v[i] * rs) * (g[i] * rs) : gelu_erf(v[i]) * g[i];
-        box_put_half32(box, r, h, v);
-      }
-      st.submit<false>(tmOut, box, n_tile * 128 + b * 64, m0, lane);
-    }
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
     for (int c = 4 * half; c < 4 * half + 4; ++c) {
@@ -432,6 +396,181 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
       else { __syncwarp(); }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined epilogues of the two big ModernBERT GEMMs (Wqkv + RoPE, Wi + GeGLU).  Measured with vrag_bench_gemm: the
+// mainloop alone runs at ~1500 TFLOP/s, so the kernel time is the epilogue's whenever a tile's tail takes longer than
+// its 256x256xK MMAs (7.7 k clocks at K = 768), and the tail is a chain of long-latency hops (tcgen05.ld, global loads
+// of cos / sin / row moments, the TMA-store hand-off) that two warps per scheduler cannot hide.  So:
+//   * everything that does not need the accumulators (row rstd, the 32 tokens' cos / sin rows) is fetched BEFORE the
+//     warp waits for the accumulator barrier -- the cos / sin rows by ONE TMA box load from the interleaved
+//     [position][cos 32 | sin 32] table when the slab's 32 tokens have consecutive positions (always, except slabs
+//     that straddle a sequence boundary: those gather, all loads in flight at once);
+//   * TMEM is drained in 16-column steps into ping-pong registers: the tcgen05.ld of step s+1 is in flight while step
+//     s is rotated / activated, packed and staged;
+//   * the accumulator stage is released right after the last tcgen05.ld has landed, before the tail of the math.
+// ---------------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void reg_fence(uint32_t (&r)[N]) {  // pins uses of r[] after the preceding wait::ld
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+r"(r[i]));
+}
+
+__device__ __forceinline__ void box_put_half16(uint8_t* box, int r, int chunk0, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u;
+    u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(box + r * 128 + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+  }
+}
+
+struct AccRelease {   // hands the TMEM accumulator stage back to the MMA issuer (leader CTA's barrier)
+  uint64_t* bar;
+  int cta_rank;
+  __device__ __forceinline__ void operator()(int lane) const {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (cta_rank == 0) mbar_arrive(bar);
+      else mbar_arrive_remote(bar, 0);
+    }
+  }
+};
+
+// cos / sin rows of this warp's 32 tokens -> registers of thread == row.  Borrows the warp's two store boxes.
+__device__ __forceinline__ void rope_prefetch(const GemmEpiParams& p, const CUtensorMap* tmRope, BoxStager& st,
+                                              uint64_t* bar, uint32_t& bar_phase, int m0, int lane, float (&cs)[32],
+                                              float (&sn)[32]) {
+  const int r = lane, row = m0 + lane;
+  const int my_pos = row < p.M ? __ldg(p.pos + row) : 0;
+  const int pos0 = __shfl_sync(0xffffffffu, my_pos, 0);
+  const bool consecutive = __all_sync(0xffffffffu, row >= p.M || my_pos == pos0 + lane);
+  float* cs_s = reinterpret_cast<float*>(st.base);
+  float* sn_s = reinterpret_cast<float*>(st.base + EPI_BOX_BYTES);
+  if (elect_one()) bulk_wait_read<0>();   // no TMA store may still be reading the boxes
+  __syncwarp();
+  if (consecutive) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar, 2 * EPI_BOX_BYTES);
+      tma_load_2d(cs_s, tmRope, bar, 0, pos0);
+      tma_load_2d(sn_s, tmRope, bar, 32, pos0);
+    }
+    __syncwarp();
+    mbar_wait_tagged(bar, bar_phase, 16);
+    bar_phase ^= 1;
+  } else {
+    float c[32], s2[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const int ps = __shfl_sync(0xffffffffu, my_pos, rr);
+      c[rr] = __ldg(p.rope_tab + static_cast<size_t>(ps) * 64 + lane);
+      s2[rr] = __ldg(p.rope_tab + static_cast<size_t>(ps) * 64 + 32 + lane);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const int o = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+      cs_s[o] = c[rr];
+      sn_s[o] = s2[rr];
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 c = *reinterpret_cast<const float4*>(cs_s + r * 32 + ((i ^ (r & 7)) << 2));
+    const float4 s4 = *reinterpret_cast<const float4*>(sn_s + r * 32 + ((i ^ (r & 7)) << 2));
+    cs[4 * i] = c.x; cs[4 * i + 1] = c.y; cs[4 * i + 2] = c.z; cs[4 * i + 3] = c.w;
+    sn[4 * i] = s4.x; sn[4 * i + 1] = s4.y; sn[4 * i + 2] = s4.z; sn[4 * i + 3] = s4.w;
+  }
+  __syncwarp();
+  st.issued = 0;   // both boxes are free again; restart the double-buffer bookkeeping
+}
+
+// Wqkv tail.  Step s = 0..3: head 2*half + (s >> 1), dims [16j, 16j+16) and [32+16j, 32+16j+16), j = s & 1.
+template <int EPI>
+__device__ __forceinline__ void rope_body(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st, int m0,
+                                          int n_tile, uint32_t taddr, int lane, int half, float rs,
+                                          const float (&cs)[32], const float (&sn)[32], const AccRelease& release) {
+  const int col0 = n_tile * BN;
+  const bool rotate = col0 < 2 * p.hidden;  // q / k tiles
+  const int r = lane;
+  uint32_t a[2][16], b[2][16];
+  tmem_ld_32x32b_x16(taddr + (2 * half) * 64, a[0]);
+  tmem_ld_32x32b_x16(taddr + (2 * half) * 64 + 32, b[0]);
+  uint8_t* box = nullptr;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int h = 2 * half + (s >> 1), j = s & 1;
+    tmem_ld_wait();
+    reg_fence(a[s & 1]);
+    reg_fence(b[s & 1]);
+    if (s + 1 < 4) {
+      const int h1 = 2 * half + ((s + 1) >> 1), j1 = (s + 1) & 1;
+      tmem_ld_32x32b_x16(taddr + h1 * 64 + 16 * j1, a[(s + 1) & 1]);
+      tmem_ld_32x32b_x16(taddr + h1 * 64 + 32 + 16 * j1, b[(s + 1) & 1]);
+    } else {
+      release(lane);   // every accumulator column of this warp is in registers
+    }
+    if (j == 0) box = st.acquire(lane);
+    float o1[16], o2[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float x1 = __uint_as_float(a[s & 1][e]), x2 = __uint_as_float(b[s & 1][e]);
+      if constexpr (kNorm<EPI>) {
+        x1 *= rs;
+        x2 *= rs;
+      }
+      const float c = cs[16 * j + e], sv = sn[16 * j + e];
+      o1[e] = rotate ? x1 * c - x2 * sv : x1;
+      o2[e] = rotate ? x2 * c + x1 * sv : x2;
+    }
+    box_put_half16(box, r, 2 * j, o1);
+    box_put_half16(box, r, 4 + 2 * j, o2);
+    if (j == 1 && p.debug_mode != 4) st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
+  }
+}
+
+// Wi tail.  This warp owns output columns [64*half, 64*half+64) of the tile's 128: step s = 0..3 takes input columns
+// 64*half + 16s .. +16 and the matching gate columns 128 + 64*half + 16s.
+template <int EPI>
+__device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st, int m0,
+                                           int n_tile, uint32_t taddr, int lane, int half, float rs,
+                                           const AccRelease& release) {
+  const int r = lane;
+  uint32_t a[2][16], g[2][16];
+  tmem_ld_32x32b_x16(taddr + 64 * half, a[0]);
+  tmem_ld_32x32b_x16(taddr + 128 + 64 * half, g[0]);
+  uint8_t* box = st.acquire(lane);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    tmem_ld_wait();
+    reg_fence(a[s & 1]);
+    reg_fence(g[s & 1]);
+    if (s + 1 < 4) {
+      tmem_ld_32x32b_x16(taddr + 64 * half + 16 * (s + 1), a[(s + 1) & 1]);
+      tmem_ld_32x32b_x16(taddr + 128 + 64 * half + 16 * (s + 1), g[(s + 1) & 1]);
+    } else {
+      release(lane);
+    }
+    float o[16];
+    const uint64_t rs2 = f2_pack(rs, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      uint64_t x2 = f2_pack_bits(a[s & 1][2 * e], a[s & 1][2 * e + 1]);
+      uint64_t y2 = f2_pack_bits(g[s & 1][2 * e], g[s & 1][2 * e + 1]);
+      if constexpr (kNorm<EPI>) {
+        x2 = f2_mul(x2, rs2);
+        y2 = f2_mul(y2, rs2);
+      }
+      f2_unpack(f2_mul(gelu2(x2), y2), o[2 * e], o[2 * e + 1]);
+    }
+    if (p.debug_mode != 4) box_put_half16(box, r, 2 * s, o);
+  }
+  if (p.debug_mode != 4) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
 }
 
 // Launched as clusters of 2 CTAs (an SM pair) that cooperate on one 256 x 256 output tile with
@@ -455,8 +594,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint64_t* bar_x = bar_tempty + 2;                 // [EPI_WARPS][2]: residual boxes of EPI_RESID_STATS
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_x + 2 * EPI_WARPS);
+  uint64_t* bar_x = bar_tempty + 2;                 // [EPI_WARPS][3]: residual boxes (EPI_RESID_STATS), cos/sin box
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_x + STATS_FBOXES * EPI_WARPS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -473,7 +612,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(bar_tfull + a, 1);
       mbar_init(bar_tempty + a, 2 * EPI_WARPS);   // leader's barrier: epilogue warps of BOTH CTAs arrive
     }
-    for (int a = 0; a < 2 * EPI_WARPS; ++a) mbar_init(bar_x + a, 1);
+    for (int a = 0; a < STATS_FBOXES * EPI_WARPS; ++a) mbar_init(bar_x + a, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -554,10 +693,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     if constexpr (EPI == EPI_RESID_STATS) {
       // x = x_old + acc with x_old fetched by TMA: the warp's chunks (32 rows x 32 fp32 columns, four per tile) form
-      // one flat stream across tiles; chunk n lives in buffer n & 1 = {fp32 box (loaded, updated in place, stored),
-      // fp16 half box (stored)}; the load of chunk n + 1 is issued while chunk n is processed, as soon as the stores
-      // of chunk n - 1 (same buffer) have been read out of shared memory.
-      uint64_t* xb = bar_x + 2 * (warp - 2);
+      // one flat stream across tiles; chunk n lives in fp32 box n % 3 (loaded, updated in place, stored) and fp16
+      // half box n & 1 (stored).  The load of chunk n + 2 is issued when chunk n starts, once the stores of chunk
+      // n - 1 (same fp32 box) have been read out of shared memory: two residual boxes are always in flight per
+      // warp, which is what covers the HBM latency (one in flight: 17 k clocks per tile, measured).
+      uint64_t* xb = bar_x + STATS_FBOXES * (warp - 2);
       const int my_tiles = cluster_id < total_pairs ? (total_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
       const uint32_t n_chunks = 4u * static_cast<uint32_t>(my_tiles);
       if (lane == 0) {
@@ -572,8 +712,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       auto issue_load = [&](uint32_t n) {   // elected lane
         int x, y;
         chunk_xy(n, x, y);
-        mbar_arrive_expect_tx(xb + (n & 1), EPI_BOX_BYTES);
-        tma_load_2d(my_smem + (n & 1) * EPI_BOX_BYTES, &tmOut, xb + (n & 1), x, y);
+        const uint32_t b = n % STATS_FBOXES;
+        mbar_arrive_expect_tx(xb + b, EPI_BOX_BYTES);
+        tma_load_2d(my_smem + b * EPI_BOX_BYTES, &tmOut, xb + b, x, y);
       };
       if (elect_one()) {
         if (n_chunks > 0) issue_load(0);
@@ -581,7 +722,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       __syncwarp();
       const int r = lane;
-      uint32_t n = 0;
+      uint32_t n = 0, fb = 0, fb_use = 0;   // fb = n % 3, fb_use = n / 3 (phase of box fb's barrier)
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
         const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
         mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
@@ -590,18 +731,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc, ++n) {
-          uint8_t* fbox = my_smem + (n & 1) * EPI_BOX_BYTES;
-          uint8_t* hbox = my_smem + 2 * EPI_BOX_BYTES + (n & 1) * 2048;
+          uint8_t* fbox = my_smem + fb * EPI_BOX_BYTES;
+          uint8_t* hbox = my_smem + STATS_FBOXES * EPI_BOX_BYTES + (n & 1) * 2048;
+          // box (n + 2) % 3 was last stored from by chunk n - 1, half box n & 1 by chunk n - 2
+          if (elect_one()) {
+            bulk_wait_read<0>();
+            if (n + 2 < n_chunks) issue_load(n + 2);
+          }
+          __syncwarp();
           float v[32];
           ld.load(4 * half + cc, v);
-          if (n >= 1) {   // buffer (n + 1) & 1 was last stored from by chunk n - 1
-            if (elect_one()) {
-              bulk_wait_read<0>();
-              if (n + 1 < n_chunks) issue_load(n + 1);
-            }
-            __syncwarp();
-          }
-          mbar_wait_tagged(xb + (n & 1), (n >> 1) & 1, 15);
+          mbar_wait_tagged(xb + fb, fb_use & 1, 15);   // (debug_mode 4 / 6: timing experiments, wrong results)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4* xp = reinterpret_cast<float4*>(fbox + r * 128 + ((i ^ (r & 7)) << 4));
@@ -628,11 +768,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (elect_one()) {
             int x, y;
             chunk_xy(n, x, y);
-            tma_store_2d(&tmOut, fbox, x, y);
-            tma_store_2d(&tmOut2, hbox, x, y);
+            if (p.debug_mode != 4) tma_store_2d(&tmOut, fbox, x, y);
+            if (p.debug_mode != 4 && p.debug_mode != 6) tma_store_2d(&tmOut2, hbox, x, y);
             bulk_commit();
           }
           __syncwarp();
+          if (++fb == STATS_FBOXES) {
+            fb = 0;
+            ++fb_use;
+          }
         }
         const int row = m_idx * BM + quarter * 32 + lane;
         if (row < p.M)
@@ -650,24 +794,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (elect_one()) bulk_wait<0>();
       __syncwarp();
     } else {
-      BoxStager stager{my_smem, 0u};
+      BoxStager stager{my_smem, 0u, p.debug_mode};
       if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
+      if (kRope<EPI> && lane == 0) tma_prefetch_desc(&tmOut2);
+      uint64_t* rope_bar = bar_x + STATS_FBOXES * (warp - 2);
+      uint32_t rope_phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
         const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
-        mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
-        tc_fence_after();
-        TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
-        if (p.debug_mode == 3) {
-          // timing experiment: mainloop only
-        } else if constexpr (kStaged<EPI>)
-          staged_epilogue<EPI>(p, &tmOut, stager, m_idx * BM + quarter * 32, n_idx, ld, lane, half);
-        else
-          epilogue_row<EPI>(p, m_idx * BM + quarter * 32 + lane, n_idx, ld, 4 * half, 4 * half + 4);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
-          else mbar_arrive_remote(bar_tempty + acc, 0);
+        const int m0 = m_idx * BM + quarter * 32;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        const AccRelease release{bar_tempty + acc, cta_rank};
+        if constexpr (kRope<EPI> || kGeglu<EPI>) {
+          // phase 1 (no accumulators needed): row rstd, cos / sin rows
+          float rs = 1.f;
+          if constexpr (kNorm<EPI>) rs = row_rstd(p, m0 + lane);
+          float cs[32], sn[32];
+          if constexpr (kRope<EPI>) {
+            if (n_idx * BN < 2 * p.hidden && p.debug_mode != 5)
+              rope_prefetch(p, &tmOut2, stager, rope_bar, rope_phase, m0, lane, cs, sn);
+          }
+          mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
+          tc_fence_after();
+          if (p.debug_mode == 3) release(lane);   // timing experiment: mainloop only
+          else if constexpr (kRope<EPI>) rope_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, cs, sn, release);
+          else geglu_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, release);
+        } else {
+          mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
+          tc_fence_after();
+          TmemLoader ld{taddr};
+          if (p.debug_mode == 3) {
+            // timing experiment: mainloop only
+          } else if constexpr (kStaged<EPI>)
+            staged_epilogue<EPI>(p, &tmOut, stager, m0, n_idx, ld, lane, half);
+          else
+            epilogue_row<EPI>(p, m0 + lane, n_idx, ld, 4 * half, 4 * half + 4);
+          release(lane);
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -734,18 +895,21 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
       tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
     else if constexpr (kStaged<EPI>)
       tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
+    if constexpr (kRope<EPI>) {
+      VRAG_CHECK(p.rope_tab && p.rope_rows > 0 && p.pos, VRAG_ERR_ARG, "gemm: RoPE epilogue needs rope_tab / pos");
+      tmOut2 = make_tmap_2d(ctx, p.rope_tab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.rope_rows, 64, 64, 32, 32);
+    }
     if constexpr (EPI == EPI_RESID_STATS) {
       VRAG_CHECK(p.out16 && p.stats_out && p.ld16 == p.ld32, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / stats_out");
       tmOut2 = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 32,
                             CU_TENSOR_MAP_SWIZZLE_64B);
-      // 2 x 6 KB of residual staging per epilogue warp leave room for 3 or 4 operand stages
-      if (ctx->gemm_stages == 3) launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
-      else launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
+      // 16 KB of residual staging per epilogue warp leave room for 3 operand stages (the kernel is HBM-bound)
+      launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
     } else {
       switch (ctx->gemm_stages) {
         case 3: launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
-        case 5: launch_tc<EPI, 5>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
-        default: launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+        default: launch_tc<EPI, 5>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+        case 4: launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
       }
     }
   }

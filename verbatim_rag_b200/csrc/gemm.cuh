@@ -33,8 +33,8 @@ struct GemmEpiParams {
   int ld32 = 0;
   const float* bias = nullptr;
   const int32_t* pos = nullptr;       // [M] position of each token inside its sequence
-  const float* rope_cos = nullptr;    // [max_pos, 32]
-  const float* rope_sin = nullptr;
+  const float* rope_tab = nullptr;    // [rope_rows, 64]: cos(pos * inv_freq[0..32)) | sin(pos * inv_freq[0..32))
+  int rope_rows = 0;                  // positions in the table
   int hidden = 768;                   // H: q = cols [0,H), k = [H,2H), v = [2H,3H)
   const int32_t* seq_of_row = nullptr;  // [M] sequence index of each token (SPLADE pooling)
   float* splade_out = nullptr;        // [nseq, splade_ld], zero-initialised
