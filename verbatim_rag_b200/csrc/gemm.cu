@@ -21,8 +21,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 // to transpose the cos/sin rows of its 32 tokens into registers
 constexpr int EPI_BOX_BYTES = 4096;
 constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;
-constexpr int STATS_FBOXES = 3;   // EPI_RESID_STATS: residual boxes in flight per warp (prefetch distance 2)
-constexpr int EPI_STATS_WARP_BYTES = STATS_FBOXES * EPI_BOX_BYTES + 2 * 2048;   // fp32 boxes + 2 fp16 half boxes
+constexpr int STATS_BARS = 3;     // mbarriers reserved per epilogue warp (EPI_RESID_STATS uses 2, RoPE 1)
+constexpr int EPI_STATS_WARP_BYTES = 2 * 2 * EPI_BOX_BYTES;   // EPI_RESID_STATS: 2 buffers x (hi box + lo box), 32 rows x 64 cols fp16
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
                               // scheduler cannot hide its own ALU / TMEM-load latency, two can
 constexpr int epi_warp_bytes(int epi) { return epi == EPI_RESID_STATS ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES; }
@@ -197,19 +197,17 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
     for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
       if (valid) {
-        float4* x4 = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 x = x4[i];
-          v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-          x4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
+        __half* hp = p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
+        __half* lp = p.out16_lo + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          s += v[i];
-          q = fmaf(v[i], v[i], q);
+          const float x = v[i] + (__half2float(hp[i]) + __half2float(lp[i]));
+          s += x;
+          q = fmaf(x, x, q);
+          const __half h = __float2half_rn(x);
+          hp[i] = h;
+          lp[i] = __float2half_rn(x - __half2float(h));
         }
-        store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32, v);
         if ((c & 3) == 3) {
           reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(2 * n_tile + (c >> 2)) * p.M + row] =
               make_float2(s, q);
@@ -568,9 +566,23 @@ __device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtenso
       }
       f2_unpack(f2_mul(gelu2(x2), y2), o[2 * e], o[2 * e + 1]);
     }
-    if (p.debug_mode != 4) box_put_half16(box, r, 2 * s, o);
+    if (p.debug_mode == 10) {   // experiment: direct global stores (32 bytes per thread and step)
+      if (m0 + r < p.M) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out16 + static_cast<size_t>(m0 + r) * p.ld16 + n_tile * 128 +
+                                              half * 64 + 16 * s);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint4 u;
+          u.x = pack_half2(o[8 * i + 0], o[8 * i + 1]);
+          u.y = pack_half2(o[8 * i + 2], o[8 * i + 3]);
+          u.z = pack_half2(o[8 * i + 4], o[8 * i + 5]);
+          u.w = pack_half2(o[8 * i + 6], o[8 * i + 7]);
+          dst[i] = u;
+        }
+      }
+    } else if (p.debug_mode != 4) box_put_half16(box, r, 2 * s, o);
   }
-  if (p.debug_mode != 4) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
+  if (p.debug_mode != 4 && p.debug_mode != 10) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
 }
 
 // Launched as clusters of 2 CTAs (an SM pair) that cooperate on one 256 x 256 output tile with
@@ -595,7 +607,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint64_t* bar_x = bar_tempty + 2;                 // [EPI_WARPS][3]: residual boxes (EPI_RESID_STATS), cos/sin box
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_x + STATS_FBOXES * EPI_WARPS);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_x + STATS_BARS * EPI_WARPS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -612,7 +624,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(bar_tfull + a, 1);
       mbar_init(bar_tempty + a, 2 * EPI_WARPS);   // leader's barrier: epilogue warps of BOTH CTAs arrive
     }
-    for (int a = 0; a < STATS_FBOXES * EPI_WARPS; ++a) mbar_init(bar_x + a, 1);
+    for (int a = 0; a < STATS_BARS * EPI_WARPS; ++a) mbar_init(bar_x + a, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -692,102 +704,116 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     if constexpr (EPI == EPI_RESID_STATS) {
-      // x = x_old + acc with x_old fetched by TMA: the warp's chunks (32 rows x 32 fp32 columns, four per tile) form
-      // one flat stream across tiles; chunk n lives in fp32 box n % 3 (loaded, updated in place, stored) and fp16
-      // half box n & 1 (stored).  The load of chunk n + 2 is issued when chunk n starts, once the stores of chunk
-      // n - 1 (same fp32 box) have been read out of shared memory: two residual boxes are always in flight per
-      // warp, which is what covers the HBM latency (one in flight: 17 k clocks per tile, measured).
-      uint64_t* xb = bar_x + STATS_FBOXES * (warp - 2);
+      // x = x_old + acc on the two-plane residual stream: the warp's steps (32 rows x 64 columns, two per tile) form
+      // one flat stream across tiles; step n lives in buffer n & 1 = {hi box, lo box} (TMA-loaded, updated in place,
+      // TMA-stored).  The loads of step n + 1 are issued while step n is processed, as soon as the stores of step
+      // n - 1 (same buffer) have been read out of shared memory.  The kernel is HBM-bound (7.5 / 8.25 KB per token).
+      uint64_t* xb = bar_x + STATS_BARS * (warp - 2);
       const int my_tiles = cluster_id < total_pairs ? (total_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
-      const uint32_t n_chunks = 4u * static_cast<uint32_t>(my_tiles);
+      const uint32_t n_steps = 2u * static_cast<uint32_t>(my_tiles);
       if (lane == 0) {
         tma_prefetch_desc(&tmOut);
         tma_prefetch_desc(&tmOut2);
       }
-      auto chunk_xy = [&](uint32_t n, int& x, int& y) {
-        const int pair = cluster_id + static_cast<int>(n >> 2) * num_clusters;
-        x = (pair % n_tiles) * BN + (4 * half + static_cast<int>(n & 3)) * 32;
+      auto step_xy = [&](uint32_t n, int& x, int& y) {
+        const int pair = cluster_id + static_cast<int>(n >> 1) * num_clusters;
+        x = (pair % n_tiles) * BN + (2 * half + static_cast<int>(n & 1)) * 64;
         y = (2 * (pair / n_tiles) + cta_rank) * BM + quarter * 32;
+        if (p.debug_mode == 9) {   // timing experiment: block-major planes, every box = 4 KB contiguous
+          y = ((y >> 5) * (n_tiles * 4) + (x >> 6)) * 32;
+          x = 0;
+        }
       };
       auto issue_load = [&](uint32_t n) {   // elected lane
         int x, y;
-        chunk_xy(n, x, y);
-        const uint32_t b = n % STATS_FBOXES;
-        mbar_arrive_expect_tx(xb + b, EPI_BOX_BYTES);
-        tma_load_2d(my_smem + b * EPI_BOX_BYTES, &tmOut, xb + b, x, y);
+        step_xy(n, x, y);
+        uint8_t* buf = my_smem + (n & 1) * 2 * EPI_BOX_BYTES;
+        mbar_arrive_expect_tx(xb + (n & 1), 2 * EPI_BOX_BYTES);
+        tma_load_2d(buf, &tmOut, xb + (n & 1), x, y);
+        tma_load_2d(buf + EPI_BOX_BYTES, &tmOut2, xb + (n & 1), x, y);
       };
       if (elect_one()) {
-        if (n_chunks > 0) issue_load(0);
-        if (n_chunks > 1) issue_load(1);
+        if (n_steps > 0) issue_load(0);
+        if (n_steps > 1) issue_load(1);
       }
       __syncwarp();
       const int r = lane;
-      uint32_t n = 0, fb = 0, fb_use = 0;   // fb = n % 3, fb_use = n / 3 (phase of box fb's barrier)
+      uint32_t n = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
         const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
         mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
         tc_fence_after();
-        TmemLoader ld{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN};
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
         float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc, ++n) {
-          uint8_t* fbox = my_smem + fb * EPI_BOX_BYTES;
-          uint8_t* hbox = my_smem + STATS_FBOXES * EPI_BOX_BYTES + (n & 1) * 2048;
-          // box (n + 2) % 3 was last stored from by chunk n - 1, half box n & 1 by chunk n - 2
-          if (elect_one()) {
-            bulk_wait_read<0>();
-            if (n + 2 < n_chunks) issue_load(n + 2);
+        for (int stp = 0; stp < 2; ++stp, ++n) {
+          uint8_t* hbox = my_smem + (n & 1) * 2 * EPI_BOX_BYTES;
+          uint8_t* lbox = hbox + EPI_BOX_BYTES;
+          uint32_t ta[32], tb[32];
+          tmem_ld_32x32b_x32(taddr + (2 * half + stp) * 64, ta);
+          tmem_ld_32x32b_x32(taddr + (2 * half + stp) * 64 + 32, tb);
+          if (n >= 1) {   // the other buffer was last stored from by step n - 1
+            if (elect_one()) {
+              bulk_wait_read<0>();
+              if (n + 1 < n_steps) issue_load(n + 1);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          float v[32];
-          ld.load(4 * half + cc, v);
-          mbar_wait_tagged(xb + fb, fb_use & 1, 15);   // (debug_mode 4 / 6: timing experiments, wrong results)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4* xp = reinterpret_cast<float4*>(fbox + r * 128 + ((i ^ (r & 7)) << 4));
-            const float4 x = *xp;
-            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-            *xp = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          tmem_ld_wait();
+          if (stp == 1) {   // every accumulator column of this warp is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
+              else mbar_arrive_remote(bar_tempty + acc, 0);
+            }
           }
+          mbar_wait_tagged(xb + (n & 1), (n >> 1) & 1, 15);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            sum += v[i];
-            sq = fmaf(v[i], v[i], sq);
-          }
+          for (int i = 0; i < 8; ++i) {   // 16-byte chunk i of this thread's row = 8 columns
+            const int off = r * 128 + ((i ^ (r & 7)) << 4);
+            uint4 hv = *reinterpret_cast<const uint4*>(hbox + off);
+            uint4 lv = *reinterpret_cast<const uint4*>(lbox + off);
+            uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+            uint32_t* lw = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {   // 64-byte rows, SWIZZLE_64B: 16-byte chunk i of row r at i ^ ((r >> 1) & 3)
-            uint4 u;
-            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-            *reinterpret_cast<uint4*>(hbox + r * 64 + ((i ^ ((r >> 1) & 3)) << 4)) = u;
+            for (int e = 0; e < 4; ++e) {
+              const float2 ho = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+              const int c = 8 * i + 2 * e;
+              const float x0 = __uint_as_float(c < 32 ? ta[c & 31] : tb[c & 31]) + (ho.x + lo.x);
+              const float x1 = __uint_as_float(c < 32 ? ta[(c + 1) & 31] : tb[(c + 1) & 31]) + (ho.y + lo.y);
+              sum += x0;
+              sq = fmaf(x0, x0, sq);
+              sum += x1;
+              sq = fmaf(x1, x1, sq);
+              const __half2 nh = __floats2half2_rn(x0, x1);
+              const float2 nf = __half22float2(nh);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&nh);
+              lw[e] = pack_half2(x0 - nf.x, x1 - nf.y);
+            }
+            if (p.debug_mode != 4) {
+              *reinterpret_cast<uint4*>(hbox + off) = hv;
+              *reinterpret_cast<uint4*>(lbox + off) = lv;
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
             int x, y;
-            chunk_xy(n, x, y);
-            if (p.debug_mode != 4) tma_store_2d(&tmOut, fbox, x, y);
-            if (p.debug_mode != 4 && p.debug_mode != 6) tma_store_2d(&tmOut2, hbox, x, y);
+            step_xy(n, x, y);
+            if (p.debug_mode != 4) {
+              tma_store_2d(&tmOut, hbox, x, y);
+              tma_store_2d(&tmOut2, lbox, x, y);
+            }
             bulk_commit();
           }
           __syncwarp();
-          if (++fb == STATS_FBOXES) {
-            fb = 0;
-            ++fb_use;
-          }
         }
         const int row = m_idx * BM + quarter * 32 + lane;
         if (row < p.M)
           reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(2 * n_idx + half) * p.M + row] =
               make_float2(sum, sq);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (cta_rank == 0) mbar_arrive(bar_tempty + acc);
-          else mbar_arrive_remote(bar_tempty + acc, 0);
-        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -797,7 +823,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       BoxStager stager{my_smem, 0u, p.debug_mode};
       if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
       if (kRope<EPI> && lane == 0) tma_prefetch_desc(&tmOut2);
-      uint64_t* rope_bar = bar_x + STATS_FBOXES * (warp - 2);
+      uint64_t* rope_bar = bar_x + STATS_BARS * (warp - 2);
       uint32_t rope_phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
         const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
@@ -891,7 +917,7 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
     CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN / 2, BK);  // half W tile
     CUtensorMap tmOut = tmA;  // placeholder for the epilogues that write directly
     CUtensorMap tmOut2 = tmA;
-    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_RESID_STATS)
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32)
       tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
     else if constexpr (kStaged<EPI>)
       tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
@@ -900,9 +926,15 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
       tmOut2 = make_tmap_2d(ctx, p.rope_tab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.rope_rows, 64, 64, 32, 32);
     }
     if constexpr (EPI == EPI_RESID_STATS) {
-      VRAG_CHECK(p.out16 && p.stats_out && p.ld16 == p.ld32, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / stats_out");
-      tmOut2 = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 32,
-                            CU_TENSOR_MAP_SWIZZLE_64B);
+      VRAG_CHECK(p.out16 && p.out16_lo && p.stats_out, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / out16_lo / stats_out");
+      if (p.debug_mode == 9) {
+        const uint64_t rows = static_cast<uint64_t>((M + 31) / 32) * 32 * (N / 64);
+        tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, 64, 64, 32, 64);
+        tmOut2 = make_tmap_2d(ctx, p.out16_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, 64, 64, 32, 64);
+      } else {
+      tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
+      tmOut2 = make_tmap_2d(ctx, p.out16_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
+      }
       // 16 KB of residual staging per epilogue warp leave room for 3 operand stages (the kernel is HBM-bound)
       launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
     } else {

@@ -20,8 +20,11 @@ enum GemmEpi : int {
   // Deferred LayerNorm (ModernBERT pre-LN blocks).  LN(x) W^T = rstd(x) * (x W''^T) with
   // W''[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma) folded at load time, so the consumer GEMM reads the RAW residual
   // (fp16 copy) and only needs one scalar per row; the producer GEMM emits that copy and the row moments.
-  EPI_RESID_STATS = 11,   // x = out32 + acc; out32 = x; out16 = fp16(x); stats_out[slot][row] = (sum x, sum x^2)
-                          // over this warp's 128 columns (slot = 2 * n_tile + column half); N = 768 -> 6 slots
+  EPI_RESID_STATS = 11,   // residual stream as two fp16 planes, x = out16 (hi) + out16_lo (lo), ~22 significant bits:
+                          // x += acc; hi = fp16(x), lo = fp16(x - hi); stats_out[slot][row] = (sum x, sum x^2) over
+                          // this warp's 128 columns (slot = 2 * n_tile + column half; N = 768 -> 6 slots).  The hi
+                          // plane IS the next GEMM's A operand, so the stream costs 3 KB read + 3 KB written per token
+                          // and nothing else (a separate fp32 stream + fp16 copy: 3 + 4.5 KB).
   EPI_NORM_ROPE_QKV = 12, // EPI_ROPE_QKV on rstd[row] * acc
   EPI_NORM_GEGLU = 13,    // EPI_GEGLU on rstd[row] * acc
 };
@@ -29,6 +32,7 @@ enum GemmEpi : int {
 struct GemmEpiParams {
   __half* out16 = nullptr;
   int ld16 = 0;
+  __half* out16_lo = nullptr;         // EPI_RESID_STATS: low plane of the residual stream (same leading dimension)
   float* out32 = nullptr;
   int ld32 = 0;
   const float* bias = nullptr;
