@@ -2,7 +2,8 @@
 // (sequence, 128-query tile, head); TMEM / barriers are set up once per CTA and the TMA producer runs ahead into the
 // next item's Q / K / V while the current item is still in its softmax.
 //
-//   warp 0      : TMA producer  (Q tile; K/V blocks of 64 keys in a 2-stage ring, SWIZZLE_128B boxes)
+//   warp 0      : TMA producer  (Q tile; K blocks of 64 keys in a 3-stage ring, V blocks in a 2-stage ring, K issued one
+//                               block ahead of V; SWIZZLE_128B boxes)
 //   warp 1      : MMA issuer    S  = Q K^T  (tcgen05.mma 128x64x16, both operands K-major)        -> TMEM S
 //                               O += P V    (tcgen05.mma 128x64x16, A = P from smem, B = V MN-major) -> TMEM O
 //   warps 2..5  : softmax       one warp per TMEM lane quarter, thread == query row (all 64 columns of the block, so
@@ -31,14 +32,16 @@ namespace {
 
 constexpr int AQ = 128, AK = 64, AD = 64;
 constexpr int SOFT_WARPS = 4;
-constexpr int KVS = 2;                   // K/V ring depth
+constexpr int KS = 3;                    // K ring depth: K of block g+1 / g+2 loads while block g is in its softmax, so
+                                         // S = Q K^T of the next block never waits for an L2 round trip
+constexpr int VS = 2;                    // V ring depth (V is needed one softmax later than K)
 constexpr int ATT_CTAS_PER_SM = 3;
 constexpr int ATT_THREADS = 32 * (2 + SOFT_WARPS);
 constexpr uint32_t ATT_TMEM_COLS = 128;  // S [0,64)  O [64,128)
 constexpr int SQ_BYTES = AQ * AD * 2;    // 16384
 constexpr int SKV_BYTES = AK * AD * 2;   // 8192
 constexpr int SP_BYTES = AQ * AK * 2;    // 16384
-constexpr int ATT_SMEM = SQ_BYTES + KVS * 2 * SKV_BYTES + SP_BYTES + 1024 + 256;
+constexpr int ATT_SMEM = SQ_BYTES + (KS + VS) * SKV_BYTES + SP_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.f; // log2 units
 
 __device__ __forceinline__ float ex2(float x) {
@@ -106,19 +109,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                          // 16 KB
-  uint8_t* sKV = sQ + SQ_BYTES;                // slot s: K at sKV + s*16384, V at +8192
-  uint8_t* sP = sKV + KVS * 2 * SKV_BYTES;     // 16 KB
+  uint8_t* sK = sQ + SQ_BYTES;                 // K ring: slot s at sK + s*8192
+  uint8_t* sV = sK + KS * SKV_BYTES;           // V ring: slot s at sV + s*8192
+  uint8_t* sP = sV + VS * SKV_BYTES;           // 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + SP_BYTES);
   uint64_t* q_full = bars;                   // 1
   uint64_t* q_empty = q_full + 1;            // 1
-  uint64_t* kv_full = q_empty + 1;           // [KVS]
-  uint64_t* kv_empty = kv_full + KVS;        // [KVS]
-  uint64_t* s_full = kv_empty + KVS;         // 1
+  uint64_t* k_full = q_empty + 1;            // [KS]
+  uint64_t* k_empty = k_full + KS;           // [KS]
+  uint64_t* v_full = k_empty + KS;           // [VS]
+  uint64_t* v_empty = v_full + VS;           // [VS]
+  uint64_t* s_full = v_empty + VS;           // 1
   uint64_t* s_empty = s_full + 1;            // 1
   uint64_t* p_full = s_empty + 1;            // 1
   uint64_t* pv_done = p_full + 1;            // 1
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 1);
-  int4* info = reinterpret_cast<int4*>(bars + 16);  // [2] published items (16-byte aligned: bars is 1 KB aligned)
+  int4* info = reinterpret_cast<int4*>(bars + 20);  // [2] published items (16-byte aligned: bars is 1 KB aligned)
   const int n_work = n_pairs * heads;
   const uint32_t n_items = blockIdx.x < static_cast<unsigned>(n_work)
                                ? (static_cast<uint32_t>(n_work) - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
@@ -131,9 +137,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(s_empty, SOFT_WARPS);
-    for (int i = 0; i < KVS; ++i) {
-      mbar_init(kv_full + i, 1);
-      mbar_init(kv_empty + i, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
     }
     mbar_init(p_full, SOFT_WARPS);
     mbar_init(pv_done, 1);
@@ -156,6 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t g = 0;
+    int v_col = 0, v_row = 0;   // coordinates of the V tile whose load is still owed
     int pair = static_cast<int>(blockIdx.x) / heads, head = static_cast<int>(blockIdx.x) % heads;
     const int dq = static_cast<int>(gridDim.x) / heads, dr = static_cast<int>(gridDim.x) % heads;
     int4 entry = pair < n_pairs ? __ldg(work + pair) : make_int4(0, 0, 0, 0);
@@ -177,20 +188,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_2d(sQ, &tmQ, q_full, it.head * AD, it.s0 + it.q0);
       }
       __syncwarp();
+      // K runs one block ahead of V in issue order (K_g, V_{g-1}, K_{g+1}, V_g, ...): a full V ring never holds back
+      // the K of the next block, which the S MMA needs a whole softmax earlier than its V.
       for (int i = 0; i < it.nb; ++i, ++g) {
-        const int st = g % KVS;
-        mbar_wait_tagged(kv_empty + st, ((g / KVS) & 1) ^ 1, 3);
+        const int ks = g % KS;
+        mbar_wait_tagged(k_empty + ks, ((g / KS) & 1) ^ 1, 3);
         const int row = it.s0 + (it.j_lo + i) * AK;
         if (elect_one()) {
-          mbar_arrive_expect_tx(kv_full + st, 2 * SKV_BYTES);
-          tma_load_2d(sKV + st * 2 * SKV_BYTES, &tmKV, kv_full + st, hidden + it.head * AD, row);
-          tma_load_2d(sKV + st * 2 * SKV_BYTES + SKV_BYTES, &tmKV, kv_full + st, 2 * hidden + it.head * AD, row);
+          mbar_arrive_expect_tx(k_full + ks, SKV_BYTES);
+          tma_load_2d(sK + ks * SKV_BYTES, &tmKV, k_full + ks, hidden + it.head * AD, row);
         }
         __syncwarp();
+        if (g > 0) {   // V of the previous block of the flat stream
+          const uint32_t gv = g - 1;
+          const int vs = gv % VS;
+          mbar_wait_tagged(v_empty + vs, ((gv / VS) & 1) ^ 1, 10);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(v_full + vs, SKV_BYTES);
+            tma_load_2d(sV + vs * SKV_BYTES, &tmKV, v_full + vs, v_col, v_row);
+          }
+          __syncwarp();
+        }
+        v_col = 2 * hidden + it.head * AD;
+        v_row = row;
       }
       pair = npair;
       head = nhead;
       entry = entry_next;
+    }
+    if (g > 0) {   // V of the very last block
+      const uint32_t gv = g - 1;
+      const int vs = gv % VS;
+      mbar_wait_tagged(v_empty + vs, ((gv / VS) & 1) ^ 1, 10);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(v_full + vs, SKV_BYTES);
+        tma_load_2d(sV + vs * SKV_BYTES, &tmKV, v_full + vs, v_col, v_row);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -198,19 +232,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // before waiting for the current block's P, so the softmax warps never wait for a QK^T at an item boundary.
     constexpr uint32_t idesc_s = umma_idesc(0, AQ, AK);
     constexpr uint32_t idesc_pv = umma_idesc_major(0, AQ, AD, 0, 1);  // B = V is MN-major ([key][d] rows)
-    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), k_base = smem_u32(sK), v_base = smem_u32(sV);
     auto issue_s = [&](uint32_t G, bool last) {
-      const int st = G % KVS;
-      mbar_wait_tagged(kv_full + st, (G / KVS) & 1, 2);
+      const int ks = G % KS;
+      mbar_wait_tagged(k_full + ks, (G / KS) & 1, 2);
       mbar_wait_tagged(s_empty, (G & 1) ^ 1, 5);  // the softmax warps hold S_{G-1} in registers
       tc_fence_after();
-      const uint32_t k_addr = kv_addr + st * 2 * SKV_BYTES;
+      const uint32_t k_addr = k_base + ks * SKV_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AD / 16; ++k)
           umma_f16(tmem_base, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
                    k > 0 ? 1u : 0u);
         umma_commit(s_full);
+        umma_commit(k_empty + ks);                // the K slot is free once this S has completed
         if (last) umma_commit(q_empty);  // the Q tile is free once this item's last S has completed
       }
       __syncwarp();
@@ -233,17 +268,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           nb_next = read_item<LOCAL>(info, it_n + 1, window).nb;
           issue_s(G + 1, nb_next == 1);
         }
+        const int vs = G % VS;
+        mbar_wait_tagged(v_full + vs, (G / VS) & 1, 11);
         mbar_wait_tagged(p_full, G & 1, 6);
         tc_fence_after();
-        const int st = G % KVS;
-        const uint32_t v_addr = kv_addr + st * 2 * SKV_BYTES + SKV_BYTES;
+        const uint32_t v_addr = v_base + vs * SKV_BYTES;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < AK / 16; ++k)  // 16 keys per step = two 8-row groups of the V tile = 2048 bytes
             umma_f16(tmem_o, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128(v_addr + k * 2048), idesc_pv,
                      (i > 0 || k > 0) ? 1u : 0u);  // first block of the item overwrites O
           umma_commit(pv_done);
-          umma_commit(kv_empty + st);
+          umma_commit(v_empty + vs);
         }
         __syncwarp();
       }
