@@ -158,6 +158,12 @@ int vrag_index_set_id_base(vrag_index* idx, int64_t base);
 /* Tombstone rows (deleted rows never appear in results). rows: host array of row numbers. */
 int vrag_index_mark_deleted(vrag_index* idx, const int64_t* rows, int64_t n);
 
+/* Metadata-filter pushdown (reference: the `filter=` argument of BaseMilvusStore.query, milvus_base.py:189-259): rows
+ * with exclude[row] != 0 (host array of vrag_index_size(idx) bytes, aligned with the insertion order) are skipped by
+ * every following search, like deleted rows, until the filter is cleared with exclude == NULL or rows are added /
+ * deleted.  The host compiles the boolean expression to this mask; the scan kernels only consult one byte per row. */
+int vrag_index_set_filter(vrag_index* idx, const uint8_t* exclude, int64_t n);
+
 /* Exact top-k.  Order: score descending, row index ascending; score evaluated in fp64 from the stored fp32
  * values and reported both as fp32 (scores_out) and fp64 (scores64_out, nullable).  Results [nq, k]; when the
  * index holds fewer than k live rows the tail is filled with id -1 / score -inf.

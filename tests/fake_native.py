@@ -57,6 +57,7 @@ class FakeIndex:
         self.rows = np.zeros((0, dim), np.float32)
         self.indptr, self.indices, self.values = np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32)
         self.dead = set()
+        self.excluded = None
         self.id_base = 0
 
     def __len__(self):
@@ -66,9 +67,11 @@ class FakeIndex:
         self.id_base = b
 
     def add_dense(self, rows):
+        self.excluded = None
         self.rows = np.concatenate([self.rows, np.asarray(rows, np.float32)], axis=0)
 
     def add_sparse(self, indptr, indices, values):
+        self.excluded = None
         a, b = indptr[0], indptr[-1]
         self.indptr = np.concatenate([self.indptr, self.indptr[-1] + (np.asarray(indptr[1:]) - a)])
         self.indices = np.concatenate([self.indices, np.asarray(indices[a:b], np.int32)])
@@ -76,10 +79,18 @@ class FakeIndex:
 
     def mark_deleted(self, rows):
         self.dead.update(int(r) for r in rows)
+        self.excluded = None
+
+    def set_filter(self, exclude=None):
+        if exclude is not None:
+            assert len(exclude) == len(self), "mask length must equal the number of rows"
+        self.excluded = None if exclude is None else np.asarray(exclude, np.uint8).copy()
 
     def _finish(self, sc, k):
         if self.dead:
             sc[:, sorted(self.dead)] = -np.inf
+        if self.excluded is not None:
+            sc[:, self.excluded != 0] = -np.inf
         nq, n = sc.shape
         ids = np.full((nq, k), -1, np.int64)
         out = np.full((nq, k), -np.inf, np.float64)

@@ -136,3 +136,124 @@ def test_sharded_search_two_gpus():
                         os.path.join(HERE, "sharded_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK" in r.stdout
+
+
+def test_filter_pushdown_on_the_scan_kernels(tmp_path):
+    """the row mask of ``vrag_index_set_filter`` is honoured by every scan path (FMA scan for one
+    query, tensor-core scan for a batch, sparse scan) and equals post-filtered exact search; the same store reopened
+    from its on-disk form (8f-2) answers identically."""
+    from oracle import flat_topk
+    from verbatim_rag_b200 import B200VectorStore
+    from verbatim_rag_b200.synthetic import csr_to_dicts, make_dense_corpus, make_dense_queries, make_sparse_rows
+    n, k = 30000, 10
+    corpus = make_dense_corpus(n, 768, seed=77)
+    queries = make_dense_queries(20, 768, seed=78)
+    ip, ix, vl = make_sparse_rows(n, seed=79)
+    qip, qix, qvl = make_sparse_rows(6, seed=80, query=True)
+    ids = [f"c{i:06d}" for i in range(n)]
+    metas = [{"year": 1990 + i % 40, "document_id": f"d{i % 11}"} for i in range(n)]
+    path = str(tmp_path / "store")
+    store = B200VectorStore(db_path=path, dense_dim=768, enable_dense=True, enable_sparse=True)
+    for a in range(0, n, 10000):
+        b = a + 10000
+        store.add_csr(ids[a:b], ip[a:b + 1], ix, vl, ids[a:b], ids[a:b], metas[a:b], dense=corpus[a:b])
+    store.delete([ids[3], ids[17]])
+    expr = 'metadata["year"] >= 2020 and document_id != "d3"'
+    keep = np.array([(m["year"] >= 2020 and m["document_id"] != "d3") for m in metas])
+    keep[[3, 17]] = False
+    sc = flat_topk.dense_cosine_scores(corpus, queries)
+    sc[:, ~keep] = -np.inf
+    exp = np.argsort(-sc, axis=1, kind="stable")[:, :k]
+    qd = csr_to_dicts(qip, qix, qvl)
+    ssc = flat_topk.sparse_ip_scores(ip, ix, vl, 30522, qd)
+    ssc[:, ~keep] = -np.inf
+
+    def check(st):
+        one = st.query(dense_query=queries[0].tolist(), top_k=k, search_type="dense", filter=expr)      # FMA scan
+        assert [r.id for r in one] == [ids[j] for j in exp[0]]
+        batch = st.query_batch(dense_queries=queries, top_k=k, search_type="dense", filter=expr)        # tcgen05 scan
+        assert [[r.id for r in rs] for rs in batch] == [[ids[j] for j in row] for row in exp]
+        assert all(r.metadata["year"] >= 2020 for rs in batch for r in rs)
+        sp = st.query_batch(sparse_queries=qd, top_k=k, search_type="sparse", filter=expr)
+        for qi, rs in enumerate(sp):
+            order = np.lexsort((np.arange(n), -ssc[qi]))[:k]
+            order = [j for j in order if ssc[qi][j] > 0]
+            assert [r.id for r in rs] == [ids[j] for j in order]
+        free = st.query_batch(dense_queries=queries[:5], top_k=k, search_type="dense")                  # mask is gone
+        assert any(not keep[int(r.id[1:])] for rs in free for r in rs)
+
+    check(store)
+    check(B200VectorStore(db_path=path, dense_dim=768, enable_dense=True, enable_sparse=True))
+
+
+def test_dense_topk_full_size_properties():
+    """BASELINE config 4 at full size (1 M x 768): size-independent properties instead of a CPU oracle --
+    (1) a corpus row used as the query returns itself first with cosine 1; (2) scaling a row does not change its
+    cosine; (3) the 1000-query batch (tensor-core scan, 63 passes) equals the per-query FMA scan on a sample, ids bit
+    for bit; (4) two half-corpus shards merged equal the unsharded search (the multi-GPU merge rule on one GPU)."""
+    import torch
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.distributed import merge_host
+    ctx = _native.default_context(0)
+    n, dim, k = 1_000_000, 768, 10
+    g = torch.Generator(device="cuda").manual_seed(1004)
+    corpus = torch.randn(n, dim, device="cuda", generator=g)
+    corpus[123456] *= 37.5
+    full = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    full.add_dense(corpus)
+    probe_rows = [0, 123456, 999_999, 500_000]
+    q_self = corpus[probe_rows].cpu().numpy()
+    ids, s32 = full.search_dense(q_self, k)
+    assert ids[:, 0].tolist() == probe_rows
+    assert np.abs(s32[:, 0] - 1.0).max() <= 1e-6
+    queries = torch.randn(1000, dim, device="cuda", generator=g).cpu().numpy()
+    bid, bs32, bs64 = full.search_dense(queries, k, want64=True)
+    assert (np.diff(bs64, axis=1) <= 0).all()                       # sorted by score
+    for qi in (0, 499, 999):
+        oid, _, os64 = full.search_dense(queries[qi:qi + 1], k, want64=True)
+        assert np.array_equal(oid[0], bid[qi]) and np.array_equal(os64[0], bs64[qi])
+    half = n // 2
+    parts = []
+    for lo, hi in ((0, half), (half, n)):
+        sh = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+        sh.set_id_base(lo)
+        sh.add_dense(corpus[lo:hi].contiguous())
+        parts.append(sh.search_dense(queries[:64], k, want64=True))
+        sh.close()
+    cat_ids = np.concatenate([p[0] for p in parts], axis=1)
+    cat_s64 = np.concatenate([p[2] for p in parts], axis=1)
+    mid, _, ms64 = merge_host(cat_s64, cat_ids, k)
+    assert np.array_equal(mid, bid[:64]) and np.array_equal(ms64, bs64[:64])
+    full.close()
+
+
+def test_end_to_end_batch_pipeline_matches_per_query_plugins():
+    """BASELINE config 5 shape on the GPU (SPLADE retrieve top-k + span extraction) through the batched entry points
+    of verbatim_rag_b200.pipeline: the batch result equals the plugins called one query at a time."""
+    import types
+    import cases
+    from verbatim_rag_b200 import B200SpanExtractor, B200SpladeProvider, B200VectorStore
+    from verbatim_rag_b200.pipeline import index_query_batch
+    from verbatim_rag_b200.synthetic import BertSpec, ModernBertSpec, make_bert_mlm_weights, make_modernbert_weights
+    mspec, bspec = ModernBertSpec(layers=3), BertSpec(layers=2)
+    mtok, btok = cases.tokenizer("modernbert"), cases.tokenizer("bert")
+    ext = B200SpanExtractor(weights=make_modernbert_weights(5, mspec), tokenizer=mtok, num_layers=mspec.layers,
+                            vocab_size=mspec.vocab_size)
+    prov = B200SpladeProvider(weights=make_bert_mlm_weights(6, bspec, decoder_bias_sigmas=3.0), tokenizer=btok,
+                              num_layers=bspec.layers, vocab_size=bspec.vocab_size)
+    rng = np.random.default_rng(1005)
+    chunks = [btok.make_text(rng, 200) for _ in range(300)]
+    questions = [btok.make_question(rng, 14) for _ in range(24)]
+    store = B200VectorStore(enable_dense=False, enable_sparse=True)
+    cid = [f"k{i:04d}" for i in range(len(chunks))]
+    store.add_csr(cid, *prov.embed_batch_csr(chunks), chunks, chunks, [{} for _ in chunks])
+    index = types.SimpleNamespace(vector_store=store, sparse_provider=prov, dense_provider=None)
+    got = index_query_batch(index, questions, k=20)
+    for q, rs in zip(questions, got):
+        one = store.query(sparse_query=prov.embed_text(q), top_k=20, search_type="sparse")
+        assert [r.id for r in rs] == [r.id for r in one]
+        assert np.allclose([r.score for r in rs], [r.score for r in one], atol=1e-5)
+    spans_b = ext.extract_spans_batch(questions, got)
+    for q, rs, sb in zip(questions[:6], got[:6], spans_b[:6]):
+        assert ext.extract_spans(q, rs) == sb
+        assert all(s in text for text, sp in sb.items() for s in sp)

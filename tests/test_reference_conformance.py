@@ -151,3 +151,58 @@ def test_provider_output_types(ref_env):
     assert prov.get_dimension() == bspec.vocab_size
     assert all(type(k) is int and type(v) is float for d in batch for k, v in d.items())
     assert set(one) <= set(batch[0]) and all(abs(v) > 1e-6 for v in one.values())
+
+
+def test_batched_entry_points_equal_the_reference_per_query_calls(ref_env):
+    """``index_query_batch`` / ``rag_query_batch`` return exactly what the reference's own
+    ``VerbatimIndex.query`` / ``VerbatimRAG.query`` return one query at a time (index.py:552-655, core.py:210-277) --
+    with the B200 plugins (batched paths) and with reference-shaped plugins that have no batch methods (fallback)."""
+    from verbatim_rag import VerbatimIndex, VerbatimRAG
+    from verbatim_rag.schema import DocumentSchema
+    from verbatim_rag_b200 import B200SpanExtractor, B200SpladeProvider, B200VectorStore
+    from verbatim_rag_b200.pipeline import index_query_batch, rag_query_batch
+    from oracle.plugins import OracleFlatStore, OracleSpanExtractor, OracleSpladeProvider
+
+    mw, mtok, mspec, bw, btok, bspec = _small_models()
+    rng = np.random.default_rng(8)
+    docs = [DocumentSchema(content="\n\n".join(btok.make_text(rng, 50) for _ in range(3)), title=f"doc {i}",
+                           metadata={"year": 2000 + i})
+            for i in range(5)]
+    questions = [btok.make_question(rng, 6) for _ in range(5)]
+
+    def build(store, prov, ext):
+        index = VerbatimIndex(vector_store=store, sparse_provider=prov)
+        index.add_documents(docs)
+        return index, VerbatimRAG(index, extractor=ext, k=3, template_mode="static")
+
+    for index, rag in (
+        build(B200VectorStore(enable_dense=False, enable_sparse=True),
+              B200SpladeProvider(weights=bw, tokenizer=btok, num_layers=bspec.layers, vocab_size=bspec.vocab_size),
+              B200SpanExtractor(weights=mw, tokenizer=mtok, num_layers=mspec.layers, vocab_size=mspec.vocab_size)),
+        build(OracleFlatStore(enable_dense=False, enable_sparse=True, sparse_dim=bspec.vocab_size),
+              OracleSpladeProvider(bw, btok, bspec), OracleSpanExtractor(mw, mtok, mspec)),
+    ):
+        texts = questions + [None]          # None: the filter-only browse branch (index.py:582-589)
+        got = index_query_batch(index, texts, k=3)
+        exp = [index.query(text=t, k=3) for t in texts]
+        assert len(got) == len(exp)
+        for g, e in zip(got, exp):
+            assert [(r.id, r.text, r.metadata) for r in g] == [(r.id, r.text, r.metadata) for r in e]
+            assert np.allclose([r.score for r in g], [r.score for r in e], atol=1e-6)
+        if hasattr(index.vector_store, "query_batch"):   # (the oracle store has no hybrid_weights branch)
+            got_w = index_query_batch(index, questions[:2], k=2, hybrid_weights={"sparse": 1.0})
+            exp_w = [index.query(text=t, k=2, hybrid_weights={"sparse": 1.0}) for t in questions[:2]]
+            assert [[r.id for r in g] for g in got_w] == [[r.id for r in e] for e in exp_w]
+            got_f = index_query_batch(index, questions[:2], k=3, filter='metadata["year"] >= 2002')
+            exp_f = [index.query(text=t, k=3, filter='metadata["year"] >= 2002') for t in questions[:2]]
+            assert [[r.id for r in g] for g in got_f] == [[r.id for r in e] for e in exp_f]
+            assert all(r.metadata["year"] >= 2002 for g in got_f for r in g)
+
+        resp = rag_query_batch(rag, questions)
+        one = [rag.query(q) for q in questions]
+        for a, b in zip(resp, one):
+            assert a.answer == b.answer and a.question == b.question
+            assert [[(h.start, h.end) for h in d.highlights] for d in a.documents] == \
+                   [[(h.start, h.end) for h in d.highlights] for d in b.documents]
+        pairs = rag_query_batch(rag, questions[:2], k=2, return_search_results=True)
+        assert [len(sr) for _, sr in pairs] == [2, 2]

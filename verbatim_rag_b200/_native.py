@@ -26,7 +26,7 @@ EXPORTS = [
     "vrag_version", "vrag_profile", "vrag_profile_read", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
     "vrag_dense_forward", "vrag_selftest_gemm", "vrag_bench_gemm", "vrag_selftest_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
-    "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_search_dense", "vrag_index_search_sparse",
+    "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
 ]
 
@@ -86,6 +86,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_index_add_sparse": (i32, [vp, vp, vp, vp, i64]),
             "vrag_index_set_id_base": (i32, [vp, i64]),
             "vrag_index_mark_deleted": (i32, [vp, vp, i64]),
+            "vrag_index_set_filter": (i32, [vp, vp, i64]),
             "vrag_index_search_dense": (i32, [vp, vp, i32, i32, vp, vp, vp, i32]),
             "vrag_index_search_sparse": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
             "vrag_topk_merge": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
@@ -377,6 +378,14 @@ class Index:
     def mark_deleted(self, rows):
         r = _np(rows, np.int64)
         self.ctx.check(self.ctx.lib.vrag_index_mark_deleted(self.h, _ptr(r), len(r)))
+
+    def set_filter(self, exclude=None):
+        """Metadata-filter pushdown: rows with exclude[row] != 0 are skipped by the following searches (None clears)."""
+        if exclude is None:
+            self.ctx.check(self.ctx.lib.vrag_index_set_filter(self.h, None, 0))
+            return
+        m = _np(exclude, np.uint8)
+        self.ctx.check(self.ctx.lib.vrag_index_set_filter(self.h, _ptr(m), len(m)))
 
     def search_dense(self, queries: np.ndarray, k: int, want64: bool = False):
         q = _np(queries, np.float32).reshape(-1, self.dim)

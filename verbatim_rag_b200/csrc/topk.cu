@@ -804,13 +804,17 @@ struct vrag_index {
   int64_t n = 0, cap = 0;
   int64_t id_base = 0;  // added to row numbers in results (global id of this shard's row 0)
   DevBuf rows, norm64, inv32, deleted;
+  // metadata-filter pushdown (vrag_index_set_filter): masked = deleted | excluded, consulted instead of `deleted`
+  DevBuf masked, excl;
+  bool filter_on = false;
+  const uint8_t* skip() const { return filter_on ? masked.as<uint8_t>() : deleted.as<uint8_t>(); }
   // sparse
   DevBuf indptr, indices, values;
   int64_t nnz = 0, nnz_cap = 0;
   // work
   DevBuf scores, keys0, keys1, s64, crow, qdev, qnorm, qT, qip, qidx, qval, out_ids, out_s32, out_s64;
   ~vrag_index() {
-    for (DevBuf* b : {&rows, &norm64, &inv32, &deleted, &indptr, &indices, &values, &scores, &keys0, &keys1, &s64,
+    for (DevBuf* b : {&rows, &norm64, &inv32, &deleted, &masked, &excl, &indptr, &indices, &values, &scores, &keys0, &keys1, &s64,
                       &crow, &qdev, &qnorm, &qT, &qip, &qidx, &qval, &out_ids, &out_s32, &out_s64})
       b->release();
   }
@@ -956,6 +960,7 @@ extern "C" int vrag_index_add_dense(vrag_index* idx, const float* rows, int64_t 
   VRAG_CHECK(idx->kind == VRAG_INDEX_DENSE_COSINE, VRAG_ERR_ARG, "add_dense on a sparse index");
   VRAG_CHECK(n >= 0 && (rows || n == 0), VRAG_ERR_ARG, "add_dense: null rows");
   if (n == 0) return VRAG_OK;
+  idx->filter_on = false;   // a filter mask is row-aligned with the index it was built for
   VRAG_CHECK(idx->n + n < (1LL << 32) - 1, VRAG_ERR_ARG, "add_dense: more than 2^32-2 rows per shard");
   const size_t rb = static_cast<size_t>(idx->dim) * 4;
   grow(_ctx, idx->rows, idx->n * rb, (idx->n + n) * rb);
@@ -981,6 +986,7 @@ extern "C" int vrag_index_add_sparse(vrag_index* idx, const int64_t* indptr, con
   VRAG_CHECK(idx->kind == VRAG_INDEX_SPARSE_IP, VRAG_ERR_ARG, "add_sparse on a dense index");
   VRAG_CHECK(n >= 0 && (indptr || n == 0), VRAG_ERR_ARG, "add_sparse: null indptr");
   if (n == 0) return VRAG_OK;
+  idx->filter_on = false;
   VRAG_CHECK(idx->n + n < (1LL << 32) - 1, VRAG_ERR_ARG, "add_sparse: more than 2^32-2 rows per shard");
   const int64_t add_nnz = indptr[n] - indptr[0];
   VRAG_CHECK(add_nnz >= 0 && (add_nnz == 0 || (indices && values)), VRAG_ERR_ARG, "add_sparse: bad CSR");
@@ -1012,12 +1018,46 @@ extern "C" int vrag_index_mark_deleted(vrag_index* idx, const int64_t* rows, int
   if (!idx) return VRAG_ERR_ARG;
   VRAG_API_BEGIN(idx->ctx)
   VRAG_CHECK(n >= 0 && (rows || n == 0), VRAG_ERR_ARG, "mark_deleted: null rows");
+  idx->filter_on = false;
   const uint8_t one = 1;
   for (int64_t i = 0; i < n; ++i) {
     VRAG_CHECK(rows[i] >= 0 && rows[i] < idx->n, VRAG_ERR_ARG, "mark_deleted: row out of range");
     VRAG_CUDA(cudaMemcpyAsync(idx->deleted.as<uint8_t>() + rows[i], &one, 1, cudaMemcpyHostToDevice, _ctx->stream));
   }
   VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  VRAG_API_END()
+}
+
+namespace {
+__global__ void or_mask_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out,
+                               int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a[i] | b[i]) ? 1 : 0;
+}
+}  // namespace
+
+// Metadata-filter pushdown (reference: the `filter=` expression of BaseMilvusStore.query,
+// milvus_base.py:189-259).  The host evaluates the boolean expression over its payload columns once and hands the scan
+// a row mask: rows with exclude[row] != 0 score -inf in every following search of this index, exactly like deleted
+// rows, until the filter is cleared (exclude == NULL) or the index changes (add / delete).
+extern "C" int vrag_index_set_filter(vrag_index* idx, const uint8_t* exclude, int64_t n) {
+  if (!idx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(idx->ctx)
+  if (!exclude) {
+    idx->filter_on = false;
+    return VRAG_OK;
+  }
+  VRAG_CHECK(n == idx->n, VRAG_ERR_ARG, "set_filter: mask length must equal the number of rows in the index");
+  if (n == 0) return VRAG_OK;
+  idx->excl.reserve(static_cast<size_t>(n));
+  idx->masked.reserve(static_cast<size_t>(n));
+  VRAG_CUDA(cudaMemcpyAsync(idx->excl.p, exclude, static_cast<size_t>(n), cudaMemcpyHostToDevice, _ctx->stream));
+  or_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, _ctx->stream>>>(
+      idx->deleted.as<uint8_t>(), idx->excl.as<uint8_t>(), idx->masked.as<uint8_t>(), n);
+  VRAG_CUDA(cudaGetLastError());
+  _ctx->launches++;
+  VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));   // `exclude` is the caller's buffer
+  idx->filter_on = true;
   VRAG_API_END()
 }
 
@@ -1072,8 +1112,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       }
       const int tgrid = static_cast<int>(std::min<int64_t>((n + TC_ROWS - 1) / TC_ROWS, _ctx->num_sms));
       dense_scan_tc_kernel<<<tgrid, TC_THREADS, smem, _ctx->stream>>>(tmX, n, dim, qt, nt, idx->inv32.as<float>(), qn,
-                                                                      idx->deleted.as<uint8_t>(),
-                                                                      idx->scores.as<float>());
+                                                                      idx->skip(), idx->scores.as<float>());
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     } else {
@@ -1090,7 +1129,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   do {                                                                                                             \
     VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tma_kernel<V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     dense_scan_tma_kernel<V, Q><<<tgrid, 32 * (SCAN_CONSUMER_WARPS + 1), smem, _ctx->stream>>>(                     \
-        idx->rows.as<float>(), n, qt, idx->inv32.as<float>(), qn, idx->deleted.as<uint8_t>(),                       \
+        idx->rows.as<float>(), n, qt, idx->inv32.as<float>(), qn, idx->skip(),                                      \
         idx->scores.as<float>(), nstage, nt);                                                                      \
   } while (0)
 #define VRAG_SCAN_Q(V)                                \
@@ -1107,8 +1146,8 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
 #undef VRAG_SCAN_T
       } else {
         dense_scan_generic_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, dim, qt, nt,
-                                                                  idx->inv32.as<float>(), qn,
-                                                                  idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+                                                                  idx->inv32.as<float>(), qn, idx->skip(),
+                                                                  idx->scores.as<float>());
       }
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
@@ -1165,7 +1204,7 @@ extern "C" int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr
       ProfScope prof(_ctx, PROF_SCAN);
       sparse_scan_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->indptr.as<int64_t>(), idx->indices.as<int32_t>(),
                                                           idx->values.as<float>(), n, idx->qT.as<float>(), nt,
-                                                          idx->deleted.as<uint8_t>(), idx->scores.as<float>());
+                                                          idx->skip(), idx->scores.as<float>());
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     }

@@ -8,11 +8,23 @@ Vectors live in HBM (row-major fp32 dense block, CSR sparse block); exact top-k 
 metrics of milvus_local.py:111-125) runs through ``vrag_index_search_*``.  Payload (ids, texts, metadata) stays in
 host Python lists, row-aligned with the device blocks.  The hybrid branches reuse the reference's own weighted-RRF
 merge (vector_stores/hybrid_search.py:73-129) on top of the GPU top-k lists.
+
+``filter=`` (a Milvus boolean expression, milvus_base.py:189-259) is pushed down into the scan: the expression is
+evaluated once over the host payload columns, the resulting row mask goes to ``vrag_index_set_filter`` and the scan
+kernels skip masked rows like deleted ones.
+
+``db_path`` (the milvus-lite ``.db`` file of milvus_local.py:61-63) names a DIRECTORY holding an append-only store
+(SURVEY.md 8f-2): ``dense.f32`` (raw row-major fp32, mmap-able, loads straight into HBM), ``sparse.indptr.i64`` /
+``sparse.indices.i32`` / ``sparse.values.f32`` (CSR), ``payload.jsonl`` (id, texts, metadata per row),
+``tombstones.i64`` (deleted row numbers), ``documents.jsonl`` and ``manifest.json``.  Every ``add_vectors`` /
+``delete`` appends before it returns, so re-opening the same path restores the collection, as with the reference.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import logging
+import os
 import threading
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -59,7 +71,7 @@ class B200VectorStore(VectorStore):
             enable_full_text = False
         if not enable_dense and not enable_sparse:
             raise ValueError("At least one of enable_dense or enable_sparse must be True")
-        self.db_path = db_path  # accepted for signature compatibility; the index is memory (HBM) resident
+        self.db_path = db_path  # None: memory (HBM) only; else the directory of the append-only store (see module doc)
         self.collection_name = collection_name
         self.documents_collection_name = f"{collection_name}_documents"
         self.dense_dim = dense_dim
@@ -85,6 +97,43 @@ class B200VectorStore(VectorStore):
         self._row_of: Dict[str, int] = {}
         self._documents: Dict[str, Dict[str, Any]] = {}
         self._lock = threading.RLock()
+        self._mask_cache: Optional[tuple] = None   # (filter, rows, deletions) -> exclude mask
+        self._n_deleted = 0
+        self._store: Optional[_DiskStore] = None
+        if db_path:
+            self._store = _DiskStore(db_path, collection_name, dense_dim if enable_dense else 0,
+                                     sparse_dim if enable_sparse else 0, self._id_base)
+            self._restore()
+
+    # ------------------------------------------------------------------------------------------ persistence
+    def _restore(self):
+        st = self._store
+        n = st.rows
+        if n == 0:
+            return
+        payload = st.read_payload(n)
+        if self._dense is not None:
+            for a, b in st.dense_chunks(n):
+                self._dense.add_dense(st.dense_rows(a, b))
+        if self._sparse is not None:
+            self._sparse.add_sparse(*st.sparse_csr(n))
+        for i, row in enumerate(payload):
+            cid = row["id"]
+            self._row_of[cid] = i            # later rows with the same id win; the older ones are tombstoned on disk
+            self._ids.append(cid)
+            self._texts.append(row["text"])
+            self._enh.append(row["enhanced_text"])
+            self._meta.append(row["metadata"])
+            self._promoted.append(row["promoted"])
+            self._alive.append(True)
+        dead = [r for r in st.read_tombstones() if 0 <= r < n]
+        self._kill_rows(sorted(set(dead)), persist=False)
+        for r in dead:
+            if self._row_of.get(self._ids[r]) == r:
+                del self._row_of[self._ids[r]]
+        for doc in st.read_documents():
+            self._documents[doc["id"]] = doc
+        logger.info("Restored %d rows (%d live) from %s", n, sum(self._alive), self.db_path)
 
     # ------------------------------------------------------------------------------------------ insert
     def add_vectors(self, ids, dense_vectors, sparse_vectors, texts, enhanced_texts, metadatas):
@@ -121,6 +170,7 @@ class B200VectorStore(VectorStore):
                 if csr is None or len(csr[0]) != n + 1:
                     raise ValueError("sparse vectors missing / wrong row count")
                 self._sparse.add_sparse(*csr)
+            first_row = len(self._ids)
             for i in range(n):
                 promoted, cleaned = promote_metadata(metadatas[i])
                 cid = ids[i]
@@ -134,9 +184,14 @@ class B200VectorStore(VectorStore):
                 self._meta.append(json_serialize_safe(cleaned))
                 self._promoted.append(promoted)
                 self._alive.append(True)
+            if self._store is not None:
+                self._store.append_rows(
+                    dense if self._dense is not None else None, csr if self._sparse is not None else None,
+                    [{"id": self._ids[r], "text": self._texts[r], "enhanced_text": self._enh[r],
+                      "metadata": self._meta[r], "promoted": self._promoted[r]} for r in range(first_row, first_row + n)])
         logger.info("Added %d vectors to B200VectorStore", n)
 
-    def _kill_rows(self, rows: Sequence[int]):
+    def _kill_rows(self, rows: Sequence[int], persist: bool = True):
         rows = [r for r in rows if self._alive[r]]
         if not rows:
             return
@@ -145,6 +200,9 @@ class B200VectorStore(VectorStore):
                 ix.mark_deleted(rows)
         for r in rows:
             self._alive[r] = False
+        self._n_deleted += len(rows)
+        if persist and self._store is not None:
+            self._store.append_tombstones(rows)
 
     # ------------------------------------------------------------------------------------------ documents
     def add_documents(self, documents: List[Dict[str, Any]]):
@@ -160,6 +218,8 @@ class B200VectorStore(VectorStore):
             }
             with self._lock:
                 self._documents[row["id"]] = row
+                if self._store is not None:
+                    self._store.append_document(row)
 
     def add_document_schema(self, document_dict: Dict[str, Any], doc_id: str = None):
         if doc_id:
@@ -229,10 +289,7 @@ class B200VectorStore(VectorStore):
         """Same branch structure as BaseMilvusStore.query (milvus_base.py:189-313)."""
         has_dense = dense_query is not None and len(dense_query) > 0
         has_sparse = sparse_query is not None and len(sparse_query) > 0
-        if filter and (has_dense or has_sparse):
-            raise NotImplementedError("metadata filter pushdown into the GPU scan is not implemented (filter-only "
-                                      "browsing is); pass filter=None for vector search")
-        with self._lock:
+        with self._lock, self._filtered(filter if (has_dense or has_sparse) else None):
             if hybrid_weights is not None:
                 weights = sanitize_hybrid_weights(hybrid_weights)
                 weights = {k: v for k, v in weights.items() if k != "full_text"}
@@ -266,13 +323,41 @@ class B200VectorStore(VectorStore):
                                  f"dense={dense_query is not None}, sparse={sparse_query is not None}")
             return self._to_results(hits)
 
-    # -- batched search: many queries per corpus pass ---------------------------------
-    def query_batch_dense(self, queries: np.ndarray, top_k: int = 5) -> List[List[SearchResult]]:
-        with self._lock:
-            ids, sc = self._dense.search_dense(np.asarray(queries, np.float32), top_k)
-            return [self._to_results(self._hits(ids[i], sc[i], False)) for i in range(ids.shape[0])]
+    # -- metadata filter pushdown -------------------------------------------------------
+    def _exclude_mask(self, filter: Optional[str]) -> Optional[np.ndarray]:
+        """Row mask for the scan kernels: 1 = skip.  Evaluated on the host payload columns, cached per
+        (expression, store state)."""
+        if not filter or not filter.strip():
+            return None
+        key = (filter, len(self._ids), self._n_deleted)
+        if self._mask_cache is not None and self._mask_cache[0] == key:
+            return self._mask_cache[1]
+        pred = _compile_filter(filter)
+        mask = np.ones(len(self._ids), np.uint8)
+        for r in range(len(self._ids)):
+            if self._alive[r] and pred({"id": self._ids[r], **self._promoted[r]}, self._meta[r]):
+                mask[r] = 0
+        self._mask_cache = (key, mask)
+        return mask
 
-    def query_batch_sparse(self, queries: Sequence[Dict[int, float]], top_k: int = 5) -> List[List[SearchResult]]:
+    @contextlib.contextmanager
+    def _filtered(self, filter: Optional[str]):
+        mask = self._exclude_mask(filter)
+        live = [ix for ix in (self._dense, self._sparse) if ix is not None] if mask is not None else []
+        for ix in live:
+            ix.set_filter(mask)
+        try:
+            yield
+        finally:
+            for ix in live:
+                ix.set_filter(None)
+
+    # -- batched search (SURVEY.md 8f-1): many queries per corpus pass ---------------------------------
+    def _hits_dense_batch(self, queries, limit: int) -> List[List[Dict[str, Any]]]:
+        ids, sc = self._dense.search_dense(np.asarray(queries, np.float32).reshape(-1, self.dense_dim), limit)
+        return [self._hits(ids[i], sc[i], drop_zero=False) for i in range(ids.shape[0])]
+
+    def _hits_sparse_batch(self, queries: Sequence[Dict[int, float]], limit: int) -> List[List[Dict[str, Any]]]:
         indptr = np.zeros(len(queries) + 1, np.int64)
         idx: List[int] = []
         val: List[float] = []
@@ -281,9 +366,71 @@ class B200VectorStore(VectorStore):
             idx.extend(ks)
             val.extend(float(q[k]) for k in ks)
             indptr[i + 1] = len(idx)
-        with self._lock:
-            ids, sc = self._sparse.search_sparse(indptr, np.asarray(idx, np.int32), np.asarray(val, np.float32), top_k)
-            return [self._to_results(self._hits(ids[i], sc[i], True)) for i in range(ids.shape[0])]
+        ids, sc = self._sparse.search_sparse(indptr, np.asarray(idx, np.int32), np.asarray(val, np.float32), limit)
+        return [self._hits(ids[i], sc[i], drop_zero=True) for i in range(ids.shape[0])]
+
+    def query_batch_dense(self, queries: np.ndarray, top_k: int = 5, filter: Optional[str] = None
+                          ) -> List[List[SearchResult]]:
+        with self._lock, self._filtered(filter):
+            return [self._to_results(h) for h in self._hits_dense_batch(queries, top_k)]
+
+    def query_batch_sparse(self, queries: Sequence[Dict[int, float]], top_k: int = 5, filter: Optional[str] = None
+                           ) -> List[List[SearchResult]]:
+        with self._lock, self._filtered(filter):
+            return [self._to_results(h) for h in self._hits_sparse_batch(queries, top_k)]
+
+    def query_batch(
+        self,
+        dense_queries=None,
+        sparse_queries: Optional[Sequence[Dict[int, float]]] = None,
+        text_queries: Optional[Sequence[str]] = None,
+        top_k: int = 5,
+        search_type: str = "hybrid",
+        filter: Optional[str] = None,
+        search_params: Optional[Dict[str, Any]] = None,
+        hybrid_weights: Optional[Dict[str, float]] = None,
+        rrf_k: int = 60,
+    ) -> List[List[SearchResult]]:
+        """``[self.query(dense_queries[i], sparse_queries[i], ...) for i]`` with one corpus scan per 16 queries instead
+        of one per query: same branch structure as ``query`` / BaseMilvusStore.query (milvus_base.py:189-313)."""
+        nq = len(dense_queries) if dense_queries is not None else (len(sparse_queries) if sparse_queries is not None else 0)
+        has_dense = dense_queries is not None and nq > 0
+        has_sparse = sparse_queries is not None and nq > 0
+        if not has_dense and not has_sparse:
+            n = len(text_queries) if text_queries is not None else 0
+            return [self.query(top_k=top_k, filter=filter) for _ in range(n)]
+        with self._lock, self._filtered(filter):
+            if hybrid_weights is not None:
+                weights = sanitize_hybrid_weights(hybrid_weights)
+                weights = {k: v for k, v in weights.items() if k != "full_text"}
+                if not weights:
+                    raise ValueError("No valid search methods in hybrid_weights")
+                by_method = {}
+                if "dense" in weights and has_dense and self._dense is not None:
+                    by_method["dense"] = self._hits_dense_batch(dense_queries, top_k * 2)
+                if "sparse" in weights and has_sparse and self._sparse is not None:
+                    by_method["sparse"] = self._hits_sparse_batch(sparse_queries, top_k * 2)
+                if not by_method:
+                    logger.warning("Hybrid search: no valid methods executed after validation")
+                    return [[] for _ in range(nq)]
+                if len(by_method) == 1:
+                    return [self._to_results(h[:top_k]) for h in list(by_method.values())[0]]
+                return [self._to_results(merge_hybrid_results({m: by_method[m][i] for m in by_method}, top_k, weights,
+                                                              rrf_k, log_label=self.__class__.__name__))
+                        for i in range(nq)]
+            if search_type == "dense" and has_dense:
+                hits = self._hits_dense_batch(dense_queries, top_k)
+            elif search_type == "sparse" and has_sparse:
+                hits = self._hits_sparse_batch(sparse_queries, top_k)
+            elif search_type == "hybrid" and has_dense and has_sparse:
+                d = self._hits_dense_batch(dense_queries, top_k * 2)
+                sp = self._hits_sparse_batch(sparse_queries, top_k * 2)
+                hits = [merge_hybrid_results({"dense": d[i], "sparse": sp[i]}, top_k, {"dense": 0.5, "sparse": 0.5},
+                                             rrf_k=rrf_k, log_label=self.__class__.__name__) for i in range(nq)]
+            else:
+                raise ValueError(f"Invalid search configuration: type={search_type}, "
+                                 f"dense={dense_queries is not None}, sparse={sparse_queries is not None}")
+            return [self._to_results(h) for h in hits]
 
     # ------------------------------------------------------------------------------------------ browse / delete
     def _filter_only_query(self, filter: Optional[str], limit: int) -> List[SearchResult]:
@@ -328,6 +475,147 @@ class B200VectorStore(VectorStore):
 
     def __len__(self) -> int:
         return sum(self._alive)
+
+
+class _DiskStore:
+    """Append-only on-disk form of one collection (module docstring).  All files only ever grow; a torn tail (crash
+    in the middle of an append) is cut back to the last complete row on open."""
+
+    FORMAT = "vrag-b200-store"
+    VERSION = 1
+    CHUNK_ROWS = 1 << 16   # dense rows per host->device copy on restore
+
+    def __init__(self, path: str, collection: str, dense_dim: int, sparse_dim: int, id_base: int):
+        self.dir = path
+        self.dense_dim, self.sparse_dim = int(dense_dim), int(sparse_dim)
+        os.makedirs(path, exist_ok=True)
+        man = os.path.join(path, "manifest.json")
+        want = {"format": self.FORMAT, "version": self.VERSION, "collection_name": collection,
+                "dense_dim": self.dense_dim, "sparse_dim": self.sparse_dim, "id_base": int(id_base)}
+        if os.path.exists(man):
+            with open(man) as f:
+                have = json.load(f)
+            for k in ("format", "version", "dense_dim", "sparse_dim"):
+                if have.get(k) != want[k]:
+                    raise ValueError(f"{path}: stored {k}={have.get(k)!r} does not match this store's {want[k]!r}")
+        else:
+            with open(man, "w") as f:
+                json.dump(want, f, indent=1)
+        self.rows = self._count_rows()
+
+    def _p(self, name: str) -> str:
+        return os.path.join(self.dir, name)
+
+    def _size(self, name: str) -> int:
+        return os.path.getsize(self._p(name)) if os.path.exists(self._p(name)) else 0
+
+    def _count_rows(self) -> int:
+        n = 0
+        if os.path.exists(self._p("payload.jsonl")):
+            with open(self._p("payload.jsonl"), "rb") as f:
+                data = f.read()
+            n = data.count(b"\n")
+        if self.dense_dim:
+            n = min(n, self._size("dense.f32") // (4 * self.dense_dim))
+        if self.sparse_dim:
+            n = min(n, self._size("sparse.indptr.i64") // 8)
+            if n:
+                ip = np.memmap(self._p("sparse.indptr.i64"), np.int64, "r", shape=(n,))
+                nnz_have = min(self._size("sparse.indices.i32"), self._size("sparse.values.f32")) // 4
+                while n and int(ip[n - 1]) > nnz_have:
+                    n -= 1
+        return n
+
+    # -- read
+    def read_payload(self, n: int) -> List[Dict[str, Any]]:
+        out = []
+        with open(self._p("payload.jsonl"), encoding="utf-8") as f:
+            for line in f:
+                if len(out) == n:
+                    break
+                out.append(json.loads(line))
+        return out
+
+    def dense_chunks(self, n: int):
+        for a in range(0, n, self.CHUNK_ROWS):
+            yield a, min(n, a + self.CHUNK_ROWS)
+
+    def dense_rows(self, a: int, b: int) -> np.ndarray:
+        mm = np.memmap(self._p("dense.f32"), np.float32, "r", offset=a * self.dense_dim * 4,
+                       shape=(b - a, self.dense_dim))
+        return np.ascontiguousarray(mm)
+
+    def sparse_csr(self, n: int):
+        ends = np.fromfile(self._p("sparse.indptr.i64"), np.int64, count=n)
+        indptr = np.concatenate([np.zeros(1, np.int64), ends])
+        nnz = int(indptr[-1])
+        idx = np.fromfile(self._p("sparse.indices.i32"), np.int32, count=nnz) if nnz else np.zeros(0, np.int32)
+        val = np.fromfile(self._p("sparse.values.f32"), np.float32, count=nnz) if nnz else np.zeros(0, np.float32)
+        return indptr, idx, val
+
+    def read_tombstones(self) -> List[int]:
+        if not os.path.exists(self._p("tombstones.i64")):
+            return []
+        return np.fromfile(self._p("tombstones.i64"), np.int64).tolist()
+
+    def read_documents(self) -> List[Dict[str, Any]]:
+        if not os.path.exists(self._p("documents.jsonl")):
+            return []
+        with open(self._p("documents.jsonl"), encoding="utf-8") as f:
+            return [json.loads(line) for line in f if line.strip()]
+
+    # -- append
+    def _truncate_to_rows(self):
+        """Cut every file back to `self.rows` complete rows before appending (drops a torn tail)."""
+        n = self.rows
+        if self.dense_dim and self._size("dense.f32") != n * 4 * self.dense_dim:
+            with open(self._p("dense.f32"), "ab") as f:
+                f.truncate(n * 4 * self.dense_dim)
+        if self.sparse_dim and self._size("sparse.indptr.i64") != n * 8:
+            nnz = 0
+            if n:
+                nnz = int(np.memmap(self._p("sparse.indptr.i64"), np.int64, "r", shape=(n,))[n - 1])
+            for name, item in (("sparse.indptr.i64", n * 8), ("sparse.indices.i32", nnz * 4), ("sparse.values.f32", nnz * 4)):
+                with open(self._p(name), "ab") as f:
+                    f.truncate(item)
+        if os.path.exists(self._p("payload.jsonl")):
+            with open(self._p("payload.jsonl"), "rb") as f:
+                data = f.read()
+            pos, seen = 0, 0
+            while seen < n:
+                pos = data.index(b"\n", pos) + 1
+                seen += 1
+            if pos != len(data):
+                with open(self._p("payload.jsonl"), "ab") as f:
+                    f.truncate(pos)
+
+    def append_rows(self, dense: Optional[np.ndarray], csr, payload: List[Dict[str, Any]]):
+        self._truncate_to_rows()
+        if self.dense_dim:
+            with open(self._p("dense.f32"), "ab") as f:
+                np.ascontiguousarray(dense, np.float32).tofile(f)
+        if self.sparse_dim:
+            indptr, idx, val = (np.asarray(x) for x in csr)
+            a, b = int(indptr[0]), int(indptr[-1])
+            base = self._size("sparse.indices.i32") // 4
+            with open(self._p("sparse.indices.i32"), "ab") as f:
+                np.ascontiguousarray(idx[a:b], np.int32).tofile(f)
+            with open(self._p("sparse.values.f32"), "ab") as f:
+                np.ascontiguousarray(val[a:b], np.float32).tofile(f)
+            with open(self._p("sparse.indptr.i64"), "ab") as f:
+                (np.asarray(indptr[1:], np.int64) - a + base).tofile(f)
+        with open(self._p("payload.jsonl"), "a", encoding="utf-8") as f:   # last: a row counts once its payload line is complete
+            for row in payload:
+                f.write(json.dumps(row, ensure_ascii=False, default=str) + "\n")
+        self.rows += len(payload)
+
+    def append_tombstones(self, rows: Sequence[int]):
+        with open(self._p("tombstones.i64"), "ab") as f:
+            np.asarray(list(rows), np.int64).tofile(f)
+
+    def append_document(self, doc: Dict[str, Any]):
+        with open(self._p("documents.jsonl"), "a", encoding="utf-8") as f:
+            f.write(json.dumps(doc, ensure_ascii=False, default=str) + "\n")
 
 
 def _compile_filter(expr: Optional[str]):
