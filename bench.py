@@ -129,6 +129,10 @@ def cpu_extract(weights, ids, cu, tok_cs, tok_ce, ctx_indptr, nseq):
 
 def time_cpu(nseq_sample: int, steps: int, warmup: int):
     import torch
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core this process may run on
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        pass
     from verbatim_rag_b200.synthetic import make_modernbert_weights
     weights = {k: torch.from_numpy(v) for k, v in make_modernbert_weights(1001).items()}
     ids, cu, tcs, tce, cip = make_batch(nseq_sample, 1003)
@@ -141,11 +145,11 @@ def time_cpu(nseq_sample: int, steps: int, warmup: int):
     return nseq_sample / dt, dt, torch.get_num_threads()
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
+    sample = 24   # ~5-10 s of host work per step
     rate, dt, cores = time_cpu(sample, args.steps, min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -158,7 +162,8 @@ def run_reference_arm(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -254,7 +259,7 @@ def secondary_metrics(ctx, peaks, rank, world, device):
     return out
 
 
-def run_gpu_arm(args):
+def run_gpu_arm(args, out):
     import torch
     import torch.distributed as dist
     from verbatim_rag_b200 import _native
@@ -263,7 +268,6 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner there)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -408,7 +412,8 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -419,14 +424,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs-per-step", type=int, default=SEQS_PER_STEP)
     ap.add_argument("--max-tokens", type=int, default=131072)  # pass-size sweep: profiles/README.md
-    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=96)   # ~10-30 s of host work
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries print while the run is in progress (NCCL's version
+    # banner, torch warnings) goes to stderr instead
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(out_fd, "w")
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
     else:
-        run_gpu_arm(args)
+        run_gpu_arm(args, out)
 
 
 if __name__ == "__main__":

@@ -51,13 +51,13 @@ struct vrag_encoder {
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work, stats, xl16;
+      pooled, work, stats, xl8;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
-                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &xl16})
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &xl8})
       b->release();
   }
   template <typename T>
@@ -250,7 +250,7 @@ void reserve_workspace(vrag_encoder* e) {
   e->logits.reserve(T * 8);
   if (e->kind == VRAG_ENC_MODERNBERT_TOKCLS && e->deferred_ln) {
     e->stats.reserve(T * 6 * 8);
-    e->xl16.reserve(T * H * 2);
+    e->xl8.reserve(T * H);
   }
 }
 
@@ -305,13 +305,13 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
   const int ref = e->use_reference_gemm ? 1 : 0;
   float* x32 = e->x32.as<float>();
   __half *h16 = e->h16.as<__half>(), *qkv = e->qkv16.as<__half>(), *o16 = e->o16.as<__half>(), *g16 = e->w16.as<__half>();
-  // Deferred LayerNorm: the residual stream is the pair of fp16 planes (h16 = hi, xl16 = lo); x32 is only
+  // Deferred LayerNorm: the residual stream is the pair of planes (h16 = hi, fp16; xl8 = lo, e5m2); x32 is only
   // materialised for the debug dump.
   const bool dln = e->deferred_ln;
-  __half* xl16 = e->xl16.as<__half>();
+  uint8_t* xl8 = e->xl8.as<uint8_t>();
   auto dump = [&](int slot) {
     if (!hidden_dbg_host) return;
-    if (dln) launch_hilo_to_f32(ctx, h16, xl16, T, x32);
+    if (dln) launch_hilo_to_f32(ctx, h16, xl8, T, x32);
     VRAG_CUDA(cudaMemcpyAsync(hidden_dbg_host + static_cast<size_t>(slot) * T * H, x32,
                               static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
   };
@@ -319,7 +319,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
   // residual stream (deferred LayerNorm: row moments in `stats`, gamma and the mean folded into the weights).
   float* stats = e->stats.as<float>();
   launch_embed_ln(ctx, e->ids.as<int32_t>(), T, e->vocab, e->emb, e->emb_g, 1e-5f, dln ? nullptr : x32, h16,
-                  dln ? xl16 : nullptr);
+                  dln ? xl8 : nullptr);
   dump(0);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->ml[i];
@@ -333,8 +333,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     launch_gemm(ctx, (dln && i > 0) ? EPI_NORM_ROPE_QKV : EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);
     GemmEpiParams r;
-    r.M = T; r.out32 = x32; r.ld32 = H; r.out16 = h16; r.out16_lo = xl16; r.ld16 = H; r.stats_out = stats;
-    { const char* dm = getenv("VRAG_DEBUG_RESID"); r.debug_mode = dm ? atoi(dm) : 0; }
+    r.M = T; r.out32 = x32; r.ld32 = H; r.out16 = h16; r.out8_lo = xl8; r.ld16 = H; r.stats_out = stats;
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
     if (!dln) launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
     GemmEpiParams g;
@@ -343,7 +342,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
     dump(i + 1);
   }
-  if (dln) launch_layernorm_hilo(ctx, h16, xl16, T, e->final_g, 1e-5f, h16);
+  if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, 1e-5f, h16);
   else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false);
   GemmEpiParams hd;
   hd.M = T; hd.out32 = e->buf32.as<float>(); hd.ld32 = H;

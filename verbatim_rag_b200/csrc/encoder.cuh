@@ -20,13 +20,13 @@ void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const in
 // rowops.cu  (one warp per token row, H = 768)
 void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, int total, int32_t* pos,
                        int32_t* seq_of_row);
-// x32 (nullable) = LN(emb[ids]) * gamma, h16 = fp16 of it, lo16 (nullable) = fp16 of the rounding remainder.
+// x32 (nullable) = LN(emb[ids]) * gamma, h16 = fp16 of it, lo8 (nullable) = e5m2 of the rounding remainder.
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
-                     float eps, float* x32, __half* h16, __half* lo16);
-// Two-plane residual stream (x = fp16 hi + fp16 lo, deferred-LayerNorm path): final LayerNorm, fp32 reconstruction.
-void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const __half* lo, int T, const float* gamma, float eps,
+                     float eps, float* x32, __half* h16, uint8_t* lo8);
+// Two-plane residual stream (x = fp16 hi + e5m2 lo, deferred-LayerNorm path): final LayerNorm, fp32 reconstruction.
+void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma, float eps,
                            __half* h16);
-void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const __half* lo, int T, float* x32);
+void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32);
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
                           const float* beta, float eps, float* x32, __half* h16);

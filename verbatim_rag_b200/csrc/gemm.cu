@@ -22,7 +22,9 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_BOX_BYTES = 4096;
 constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;
 constexpr int STATS_BARS = 3;     // mbarriers reserved per epilogue warp (EPI_RESID_STATS uses 2, RoPE 1)
-constexpr int EPI_STATS_WARP_BYTES = 2 * 2 * EPI_BOX_BYTES;   // EPI_RESID_STATS: 2 buffers x (hi box + lo box), 32 rows x 64 cols fp16
+constexpr int EPI_LO_BOX_BYTES = 2048;                        // 32 rows x 64 e5m2 bytes, SWIZZLE_64B
+// EPI_RESID_STATS: 2 buffers x (hi box: 32 rows x 64 fp16, lo box: 32 rows x 64 e5m2); layout [hi0][hi1][lo0][lo1]
+constexpr int EPI_STATS_WARP_BYTES = 2 * (EPI_BOX_BYTES + EPI_LO_BOX_BYTES);
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
                               // scheduler cannot hide its own ALU / TMEM-load latency, two can
 constexpr int epi_warp_bytes(int epi) { return epi == EPI_RESID_STATS ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES; }
@@ -198,15 +200,15 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
       ld.load(c, v);
       if (valid) {
         __half* hp = p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
-        __half* lp = p.out16_lo + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
+        uint8_t* lp = p.out8_lo + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = v[i] + (__half2float(hp[i]) + __half2float(lp[i]));
+          const float x = v[i] + (__half2float(hp[i]) + unpack_e5m2x2<0>(lp[i]).x);
           s += x;
           q = fmaf(x, x, q);
           const __half h = __float2half_rn(x);
           hp[i] = h;
-          lp[i] = __float2half_rn(x - __half2float(h));
+          lp[i] = static_cast<uint8_t>(pack_e5m2x2(x - __half2float(h), 0.f));
         }
         if ((c & 3) == 3) {
           reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(2 * n_tile + (c >> 2)) * p.M + row] =
@@ -705,12 +707,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     if constexpr (EPI == EPI_RESID_STATS) {
       // x = x_old + acc on the two-plane residual stream: the warp's steps (32 rows x 64 columns, two per tile) form
-      // one flat stream across tiles; step n lives in buffer n & 1 = {hi box, lo box} (TMA-loaded, updated in place,
-      // TMA-stored).  The loads of step n + 1 are issued while step n is processed, as soon as the stores of step
-      // n - 1 (same buffer) have been read out of shared memory.  Measured (vrag_bench_gemm): deeper prefetch (three
-      // boxes in flight), an L2 prefetch two tiles ahead and block-major planes all leave the time unchanged -- the
-      // kernel runs at ~4.5 TB/s of HBM traffic with its shared-memory port shared between the operand ring and the
-      // four passes (TMA in, LDS, STS, TMA out) over the residual boxes.
+      // one flat stream across tiles; step n lives in buffer n & 1 = {hi box (fp16, SWIZZLE_128B), lo box (e5m2,
+      // SWIZZLE_64B)} (TMA-loaded, updated in place, TMA-stored).  The loads of step n + 1 are issued while step n is
+      // processed, as soon as the stores of step n - 1 (same buffer) have been read out of shared memory.  Measured
+      // (vrag_bench_gemm) with an fp16 low plane: deeper prefetch (three boxes in flight), an L2 prefetch two tiles
+      // ahead and block-major planes all left the time unchanged -- the kernel ran at ~4.5 TB/s of HBM traffic with
+      // its shared-memory port shared between the operand ring and the four passes (TMA in, LDS, STS, TMA out) over
+      // the residual boxes; the e5m2 low plane removes a fifth of those bytes and frees a fourth operand stage.
       uint64_t* xb = bar_x + STATS_BARS * (warp - 2);
       const int my_tiles = cluster_id < total_pairs ? (total_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
       const uint32_t n_steps = 2u * static_cast<uint32_t>(my_tiles);
@@ -722,18 +725,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int pair = cluster_id + static_cast<int>(n >> 1) * num_clusters;
         x = (pair % n_tiles) * BN + (2 * half + static_cast<int>(n & 1)) * 64;
         y = (2 * (pair / n_tiles) + cta_rank) * BM + quarter * 32;
-        if (p.debug_mode == 9) {   // timing experiment: block-major planes, every box = 4 KB contiguous
-          y = ((y >> 5) * (n_tiles * 4) + (x >> 6)) * 32;
-          x = 0;
-        }
       };
       auto issue_load = [&](uint32_t n) {   // elected lane
         int x, y;
         step_xy(n, x, y);
-        uint8_t* buf = my_smem + (n & 1) * 2 * EPI_BOX_BYTES;
-        mbar_arrive_expect_tx(xb + (n & 1), 2 * EPI_BOX_BYTES);
-        tma_load_2d(buf, &tmOut, xb + (n & 1), x, y);
-        tma_load_2d(buf + EPI_BOX_BYTES, &tmOut2, xb + (n & 1), x, y);
+        mbar_arrive_expect_tx(xb + (n & 1), EPI_BOX_BYTES + EPI_LO_BOX_BYTES);
+        tma_load_2d(my_smem + (n & 1) * EPI_BOX_BYTES, &tmOut, xb + (n & 1), x, y);
+        tma_load_2d(my_smem + 2 * EPI_BOX_BYTES + (n & 1) * EPI_LO_BOX_BYTES, &tmOut2, xb + (n & 1), x, y);
       };
       if (elect_one()) {
         if (n_steps > 0) issue_load(0);
@@ -750,8 +748,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int stp = 0; stp < 2; ++stp, ++n) {
-          uint8_t* hbox = my_smem + (n & 1) * 2 * EPI_BOX_BYTES;
-          uint8_t* lbox = hbox + EPI_BOX_BYTES;
+          uint8_t* hbox = my_smem + (n & 1) * EPI_BOX_BYTES;
+          uint8_t* lbox = my_smem + 2 * EPI_BOX_BYTES + (n & 1) * EPI_LO_BOX_BYTES;
           uint32_t ta[32], tb[32];
           tmem_ld_32x32b_x32(taddr + (2 * half + stp) * 64, ta);
           tmem_ld_32x32b_x32(taddr + (2 * half + stp) * 64 + 32, tb);
@@ -773,32 +771,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           mbar_wait_tagged(xb + (n & 1), (n >> 1) & 1, 15);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {   // 16-byte chunk i of this thread's row = 8 columns
-            const int off = r * 128 + ((i ^ (r & 7)) << 4);
-            uint4 hv = *reinterpret_cast<const uint4*>(hbox + off);
-            uint4 lv = *reinterpret_cast<const uint4*>(lbox + off);
-            uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+          for (int j = 0; j < 4; ++j) {   // 16-byte chunk j of this thread's lo row = 16 columns = hi chunks 2j, 2j+1
+            const int loff = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+            uint4 lv = *reinterpret_cast<const uint4*>(lbox + loff);
             uint32_t* lw = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 ho = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-              const int c = 8 * i + 2 * e;
-              const float x0 = __uint_as_float(c < 32 ? ta[c & 31] : tb[c & 31]) + (ho.x + lo.x);
-              const float x1 = __uint_as_float(c < 32 ? ta[(c + 1) & 31] : tb[(c + 1) & 31]) + (ho.y + lo.y);
-              sum += x0;
-              sq = fmaf(x0, x0, sq);
-              sum += x1;
-              sq = fmaf(x1, x1, sq);
-              const __half2 nh = __floats2half2_rn(x0, x1);
-              const float2 nf = __half22float2(nh);
-              hw[e] = *reinterpret_cast<const uint32_t*>(&nh);
-              lw[e] = pack_half2(x0 - nf.x, x1 - nf.y);
+            for (int hh = 0; hh < 2; ++hh) {
+              const int i = 2 * j + hh;   // hi chunk: columns [8i, 8i + 8)
+              const int hoff = r * 128 + ((i ^ (r & 7)) << 4);
+              uint4 hv = *reinterpret_cast<const uint4*>(hbox + hoff);
+              uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+              float d[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 ho = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                const uint32_t lword = lw[2 * hh + (e >> 1)];
+                const float2 lo = (e & 1) ? unpack_e5m2x2<1>(lword) : unpack_e5m2x2<0>(lword);
+                const int c = 8 * i + 2 * e;
+                const float x0 = __uint_as_float(c < 32 ? ta[c & 31] : tb[c & 31]) + (ho.x + lo.x);
+                const float x1 = __uint_as_float(c < 32 ? ta[(c + 1) & 31] : tb[(c + 1) & 31]) + (ho.y + lo.y);
+                sum += x0;
+                sq = fmaf(x0, x0, sq);
+                sum += x1;
+                sq = fmaf(x1, x1, sq);
+                const __half2 nh = __floats2half2_rn(x0, x1);
+                const float2 nf = __half22float2(nh);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&nh);
+                d[2 * e] = x0 - nf.x;
+                d[2 * e + 1] = x1 - nf.y;
+              }
+              lw[2 * hh] = pack_e5m2x4(d[0], d[1], d[2], d[3]);
+              lw[2 * hh + 1] = pack_e5m2x4(d[4], d[5], d[6], d[7]);
+              if (p.debug_mode != 4) *reinterpret_cast<uint4*>(hbox + hoff) = hv;
             }
-            if (p.debug_mode != 4) {
-              *reinterpret_cast<uint4*>(hbox + off) = hv;
-              *reinterpret_cast<uint4*>(lbox + off) = lv;
-            }
+            if (p.debug_mode != 4) *reinterpret_cast<uint4*>(lbox + loff) = lv;
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -929,17 +935,12 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
       tmOut2 = make_tmap_2d(ctx, p.rope_tab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.rope_rows, 64, 64, 32, 32);
     }
     if constexpr (EPI == EPI_RESID_STATS) {
-      VRAG_CHECK(p.out16 && p.out16_lo && p.stats_out, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / out16_lo / stats_out");
-      if (p.debug_mode == 9) {
-        const uint64_t rows = static_cast<uint64_t>((M + 31) / 32) * 32 * (N / 64);
-        tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, 64, 64, 32, 64);
-        tmOut2 = make_tmap_2d(ctx, p.out16_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, 64, 64, 32, 64);
-      } else {
+      VRAG_CHECK(p.out16 && p.out8_lo && p.stats_out, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / out8_lo / stats_out");
       tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
-      tmOut2 = make_tmap_2d(ctx, p.out16_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
-      }
-      // 16 KB of residual staging per epilogue warp leave room for 3 operand stages (the kernel is HBM-bound)
-      launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
+      tmOut2 = make_tmap_2d(ctx, p.out8_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, p.ld16, p.ld16, 32, 64,
+                            CU_TENSOR_MAP_SWIZZLE_64B);
+      // 12 KB of residual staging per epilogue warp leave room for 4 operand stages (the kernel is HBM-bound)
+      launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
     } else {
       switch (ctx->gemm_stages) {
         case 3: launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;

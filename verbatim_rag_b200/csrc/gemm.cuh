@@ -20,11 +20,12 @@ enum GemmEpi : int {
   // Deferred LayerNorm (ModernBERT pre-LN blocks).  LN(x) W^T = rstd(x) * (x W''^T) with
   // W''[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma) folded at load time, so the consumer GEMM reads the RAW residual
   // (fp16 copy) and only needs one scalar per row; the producer GEMM emits that copy and the row moments.
-  EPI_RESID_STATS = 11,   // residual stream as two fp16 planes, x = out16 (hi) + out16_lo (lo), ~22 significant bits:
-                          // x += acc; hi = fp16(x), lo = fp16(x - hi); stats_out[slot][row] = (sum x, sum x^2) over
-                          // this warp's 128 columns (slot = 2 * n_tile + column half; N = 768 -> 6 slots).  The hi
-                          // plane IS the next GEMM's A operand, so the stream costs 3 KB read + 3 KB written per token
-                          // and nothing else (a separate fp32 stream + fp16 copy: 3 + 4.5 KB).
+  EPI_RESID_STATS = 11,   // residual stream as two planes, x = out16 (hi, fp16) + out8_lo (lo, e5m2: ptx.cuh), >= 14
+                          // significant bits: x += acc; hi = fp16(x), lo = e5m2(x - hi); stats_out[slot][row] =
+                          // (sum x, sum x^2) over this warp's 128 columns (slot = 2 * n_tile + column half; N = 768 ->
+                          // 6 slots).  The hi plane IS the next GEMM's A operand, so the stream costs 2.25 KB read +
+                          // 2.25 KB written per token and nothing else (a separate fp32 stream + fp16 copy: 3 + 4.5 KB;
+                          // an fp16 low plane, the first version: 3 + 3 KB -- these two GEMMs are HBM-bound).
   EPI_NORM_ROPE_QKV = 12, // EPI_ROPE_QKV on rstd[row] * acc
   EPI_NORM_GEGLU = 13,    // EPI_GEGLU on rstd[row] * acc
 };
@@ -32,7 +33,7 @@ enum GemmEpi : int {
 struct GemmEpiParams {
   __half* out16 = nullptr;
   int ld16 = 0;
-  __half* out16_lo = nullptr;         // EPI_RESID_STATS: low plane of the residual stream (same leading dimension)
+  uint8_t* out8_lo = nullptr;         // EPI_RESID_STATS: low plane of the residual stream, e5m2 [M, ld16]
   float* out32 = nullptr;
   int ld32 = 0;
   const float* bias = nullptr;

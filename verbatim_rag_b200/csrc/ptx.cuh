@@ -400,4 +400,23 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- e5m2 (the high byte of an fp16: 5 exponent bits like fp16, 2 mantissa bits) ----------------------------------
+// The low plane of the two-plane residual stream (gemm.cuh EPI_RESID_STATS) stores the rounding remainder x - fp16(x)
+// in this format: |remainder| <= ulp(hi) / 2, so 3 significant bits of it extend the stream to >= 14 bits
+// (relative error <= 2^-14, rms ~2^-16: an order below the fp16 rounding of every GEMM operand) at 1 byte per value.
+__device__ __forceinline__ uint32_t pack_e5m2x2(float a, float b) {   // byte 0 = e5m2(a), byte 1 = e5m2(b), rn
+  uint16_t r;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+  return pack_e5m2x2(a, b) | (pack_e5m2x2(c, d) << 16);
+}
+// bytes 2k, 2k+1 of w (k = 0 / 1) -> two floats (exact)
+template <int K>
+__device__ __forceinline__ float2 unpack_e5m2x2(uint32_t w) {
+  const uint32_t h = __byte_perm(w, 0u, K == 0 ? 0x1404u : 0x3424u);   // [0, b_2k, 0, b_2k+1] = two fp16 bit patterns
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+
 }  // namespace vrag

@@ -43,10 +43,10 @@ __device__ __forceinline__ void ln_row(float4 (&v)[VEC], const float* __restrict
   }
 }
 
-// lo16_row (optional): the rounding remainder v - fp16(v), so that fp16 hi + fp16 lo carries the row to ~22 bits
+// lo8_row (optional): the rounding remainder v - fp16(v) as e5m2, so that hi + lo carries the row to >= 14 bits
 // (the two-plane residual stream of the deferred-LayerNorm path, gemm.cuh EPI_RESID_STATS).
 __device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row, __half* h16_row, int lane,
-                                          __half* lo16_row = nullptr) {
+                                          uint8_t* lo8_row = nullptr) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     if (x32_row) reinterpret_cast<float4*>(x32_row)[i * 32 + lane] = v[i];
@@ -56,26 +56,23 @@ __device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row
       u.x = *reinterpret_cast<const uint32_t*>(&h0);
       u.y = *reinterpret_cast<const uint32_t*>(&h1);
       reinterpret_cast<uint2*>(h16_row)[i * 32 + lane] = u;
-      if (lo16_row) {
+      if (lo8_row) {
         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        uint2 w;
-        w.x = pack_half2(v[i].x - f0.x, v[i].y - f0.y);
-        w.y = pack_half2(v[i].z - f1.x, v[i].w - f1.y);
-        reinterpret_cast<uint2*>(lo16_row)[i * 32 + lane] = w;
+        reinterpret_cast<uint32_t*>(lo8_row)[i * 32 + lane] =
+            pack_e5m2x4(v[i].x - f0.x, v[i].y - f0.y, v[i].z - f1.x, v[i].w - f1.y);
       }
     }
   }
 }
 // row of the two-plane residual stream -> fp32 registers
-__device__ __forceinline__ void load_row_hilo(float4 (&v)[VEC], const __half* hi_row, const __half* lo_row, int lane) {
+__device__ __forceinline__ void load_row_hilo(float4 (&v)[VEC], const __half* hi_row, const uint8_t* lo_row, int lane) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const uint2 a = reinterpret_cast<const uint2*>(hi_row)[i * 32 + lane];
-    const uint2 b = reinterpret_cast<const uint2*>(lo_row)[i * 32 + lane];
+    const uint32_t b = reinterpret_cast<const uint32_t*>(lo_row)[i * 32 + lane];
     const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
     const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x));
-    const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+    const float2 b0 = unpack_e5m2x2<0>(b), b1 = unpack_e5m2x2<1>(b);
     v[i] = make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
   }
 }
@@ -94,7 +91,7 @@ __global__ void token_meta_kernel(const int32_t* __restrict__ cu, int nseq, int3
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* __restrict__ emb,
                 const float* __restrict__ gamma, float eps, float* __restrict__ x32, __half* __restrict__ h16,
-                __half* __restrict__ lo16) {
+                uint8_t* __restrict__ lo8) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   int id = ids[row];
@@ -105,12 +102,12 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* 
   for (int i = 0; i < VEC; ++i) v[i] = __ldg(e + i * 32 + lane);
   ln_row(v, gamma, nullptr, eps, lane);
   store_row(v, x32 ? x32 + static_cast<size_t>(row) * H : nullptr, h16 + static_cast<size_t>(row) * H, lane,
-            lo16 ? lo16 + static_cast<size_t>(row) * H : nullptr);
+            lo8 ? lo8 + static_cast<size_t>(row) * H : nullptr);
 }
 
 // LayerNorm of the two-plane residual stream (final norm of the deferred-LayerNorm path); h16 may alias hi.
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
-layernorm_hilo_kernel(const __half* hi, const __half* __restrict__ lo, int T, const float* __restrict__ gamma,
+layernorm_hilo_kernel(const __half* hi, const uint8_t* __restrict__ lo, int T, const float* __restrict__ gamma,
                       float eps, __half* h16) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -121,7 +118,7 @@ layernorm_hilo_kernel(const __half* hi, const __half* __restrict__ lo, int T, co
 }
 
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
-hilo_to_f32_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int T, float* __restrict__ x32) {
+hilo_to_f32_kernel(const __half* __restrict__ hi, const uint8_t* __restrict__ lo, int T, float* __restrict__ x32) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   float4 v[VEC];
@@ -307,19 +304,19 @@ void launch_token_meta(vrag_ctx* ctx, const int32_t* cu, int nseq, int total, in
   VRAG_LAUNCHED(ctx);
 }
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
-                     float eps, float* x32, __half* h16, __half* lo16) {
+                     float eps, float* x32, __half* h16, uint8_t* lo8) {
   ProfScope prof(ctx, PROF_ROWOPS);
   embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, T, vocab, tok_emb, gamma, eps, x32, h16,
-                                                                           lo16);
+                                                                           lo8);
   VRAG_LAUNCHED(ctx);
 }
-void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const __half* lo, int T, const float* gamma, float eps,
+void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma, float eps,
                            __half* h16) {
   ProfScope prof(ctx, PROF_ROWOPS);
   layernorm_hilo_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(hi, lo, T, gamma, eps, h16);
   VRAG_LAUNCHED(ctx);
 }
-void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const __half* lo, int T, float* x32) {
+void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32) {
   ProfScope prof(ctx, PROF_ROWOPS);
   hilo_to_f32_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(hi, lo, T, x32);
   VRAG_LAUNCHED(ctx);
