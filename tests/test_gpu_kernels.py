@@ -165,6 +165,42 @@ def test_modernbert_multi_pass_equals_single_pass(ctx):
     assert np.array_equal(l1, l2) and np.array_equal(p1, p2)
 
 
+def test_span_forward_bench_shape_properties(ctx):
+    """BASELINE configs[2] shape (22 layers, sequences of exactly 512 tokens, two 131 072-token passes, the tile
+    schedule bench.py measures) through size-independent properties: (1) idempotence -- a second run is bit-identical;
+    (2) batch-composition invariance -- a sequence taken out of the 320-sequence batch and run in a batch of 3 gives
+    bit-identical logits (rows are independent in every kernel; only the tile / pass schedule differs); (3) sampled
+    sequences agree with the fp32 oracle within the stated tolerance; (4) probabilities are softmax outputs in [0, 1]."""
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import ModernBertSpec, make_modernbert_weights
+    from oracle.modernbert import modernbert_forward_varlen, relevant_prob
+    spec = ModernBertSpec(layers=22)
+    w = make_modernbert_weights(1001, spec)
+    nseq, L = 320, 512
+    rng = np.random.default_rng(1003)
+    ids2 = rng.integers(5, 50279, size=(nseq, L), dtype=np.int64)
+    ids2[:, 0], ids2[:, 30], ids2[:, -1] = spec.cls_id, spec.sep_id, spec.sep_id
+    seqs = [ids2[i] for i in range(nseq)]
+    ids, cu = _native.Encoder._pack(seqs)
+    enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, w, spec.layers, spec.vocab_size, max_tokens=131072)
+    p1, l1 = enc.span_forward(ids, cu, want_logits=True)
+    p2, l2 = enc.span_forward(ids, cu, want_logits=True)
+    assert np.array_equal(l1, l2) and np.array_equal(p1, p2)
+    assert np.isfinite(l1).all() and (p1 >= 0).all() and (p1 <= 1).all()
+    pick = [0, 255, 256, 319]   # last sequence of the first pass, first of the second, both ends
+    sub_ids, sub_cu = _native.Encoder._pack([seqs[i] for i in pick[:3]])
+    ps, ls = enc.span_forward(sub_ids, sub_cu, want_logits=True)
+    enc.close()
+    for j, i in enumerate(pick[:3]):
+        assert np.array_equal(ls[j * L:(j + 1) * L], l1[i * L:(i + 1) * L]), i
+        assert np.array_equal(ps[j * L:(j + 1) * L], p1[i * L:(i + 1) * L]), i
+    ref = modernbert_forward_varlen(w, [seqs[i] for i in pick], spec, batch=1)
+    err = max(float(np.abs(l1[i * L:(i + 1) * L] - r).max()) for i, r in zip(pick, ref))
+    perr = max(float(np.abs(p1[i * L:(i + 1) * L] - relevant_prob(r)).max()) for i, r in zip(pick, ref))
+    _diag(test="span_forward_bench_shape", nseq=nseq, logit_max_err=err, prob_max_err=perr)
+    assert err < 5e-3 and perr < 2e-3, (err, perr)
+
+
 # ------------------------------------------------------------------------------------------ SPLADE
 @pytest.mark.parametrize("use_ref_gemm,legacy_attn", [(True, True), (False, False)])
 def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):

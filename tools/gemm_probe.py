@@ -21,10 +21,10 @@ def main():
             out["selftest"].append({"epi": epi, "M": M, "N": N, "K": K, "error": str(e)})
         print(out["selftest"][-1], flush=True)
     M = int(os.environ.get("PROBE_M", "131072"))
-    plan = [("wqkv", 1, 2304, 768, (0, 3)), ("wqkv_norm", 12, 2304, 768, (0,)),
-            ("wi", 3, 2304, 768, (0,)), ("wi_norm", 13, 2304, 768, (0,)),
-            ("wo", 2, 768, 768, (0, 3)), ("wo_stats", 11, 768, 768, (0, 4, 12)),
-            ("wo2", 2, 768, 1152, (0, 3)), ("wo2_stats", 11, 768, 1152, (0, 4, 12))]
+    plan = [("wqkv", 1, 2304, 768, (0, 3)), ("wqkv_norm", 12, 2304, 768, (0, 3, 4)),
+            ("wi", 3, 2304, 768, (0,)), ("wi_norm", 13, 2304, 768, (0, 3, 4)),
+            ("wo", 2, 768, 768, (0, 3)), ("wo_stats", 11, 768, 768, (0, 4)),
+            ("wo2", 2, 768, 1152, (0, 3)), ("wo2_stats", 11, 768, 1152, (0, 4))]
     for name, epi, N, K, modes in plan:
         for dbg in modes:
             try:

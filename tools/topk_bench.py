@@ -20,7 +20,8 @@ def main():
     ix.add_dense(corpus)
     del corpus
     out = {"n": n, "dim": dim}
-    q = torch.randn(256, dim, device="cuda", generator=g)
+    q = torch.randn(1000, dim, device="cuda", generator=g)
+    st = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
 
     def search(qq):
         nq = qq.shape[0]
@@ -36,9 +37,18 @@ def main():
     sc_fma = torch.cat([search(q[i:i + 4].contiguous())[1] for i in range(0, 64, 4)])
     out["tc_vs_fma_ids_equal"] = bool((ids_tc == ids_fma).all().item())
     out["tc_vs_fma_score_maxdiff"] = float((sc_tc - sc_fma).abs().max().item())
-    for nq in (1, 2, 4, 8, 16, 64, 256):
+    for nq in (1, 2, 4, 8, 16, 64, 256, 1000):
         qq = q[:nq].contiguous()
         search(qq)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ids = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+        sc = torch.empty(nq, k, dtype=torch.float32, device="cuda")
+        e0.record(st)
+        for _ in range(3):
+            ix.search_dense_device(qq, nq, k, ids, sc)
+        e1.record(st)
+        ctx.sync()
+        wall = e0.elapsed_time(e1) / 3
         ctx.profile(True)
         for _ in range(3):
             search(qq)
@@ -48,7 +58,8 @@ def main():
         passes = prof["scan"]["launches"] / 3
         tot = sum(v["ms"] for v in prof.values()) / 3
         out[f"q{nq}"] = {"scan_ms": scan_ms, "passes": passes, "scan_GBps": passes * n * dim * 4 / scan_ms / 1e6,
-                         "device_ms_total": tot, "qps": nq / tot * 1e3}
+                         "device_ms_sum_of_kernels": tot, "search_ms": wall, "qps": nq / wall * 1e3,
+                         "search_GBps": passes * n * dim * 4 / wall / 1e6}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     print(json.dumps(out, indent=1))
 

@@ -110,17 +110,18 @@ CUtensorMap make_tmap_2d(vrag_ctx* ctx, const void* base, CUtensorMapDataType dt
 struct ProfScope {
   vrag_ctx* c;
   int cls;
+  cudaStream_t st;   // the stream the bracketed kernels are launched on (default: the context's main stream)
   size_t e0 = 0;
-  ProfScope(vrag_ctx* ctx, int k) : c(ctx), cls(k) {
+  ProfScope(vrag_ctx* ctx, int k, cudaStream_t stream = nullptr) : c(ctx), cls(k), st(stream ? stream : ctx->stream) {
     if (c->prof.on) {
       e0 = c->prof.used;
-      cudaEventRecord(c->prof.get(), c->stream);
+      cudaEventRecord(c->prof.get(), st);
     }
   }
   ~ProfScope() {
     if (c->prof.on) {
       size_t e1 = c->prof.used;
-      cudaEventRecord(c->prof.get(), c->stream);
+      cudaEventRecord(c->prof.get(), st);
       c->prof.recs.push_back({cls, e0, e1});
     }
   }

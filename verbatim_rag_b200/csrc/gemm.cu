@@ -308,9 +308,8 @@ constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BI
 struct BoxStager {
   uint8_t* base;      // this warp's two boxes
   uint32_t issued;    // boxes submitted so far (same value in every lane)
-  int dbg = 0;        // timing experiments (debug_mode 7: no wait before box reuse, 8: no proxy fence)
   __device__ __forceinline__ uint8_t* acquire(int lane) {
-    if (issued >= 2 && dbg != 7) {                      // the box submitted two steps ago has been read out
+    if (issued >= 2) {                                  // the box submitted two steps ago has been read out
       if (elect_one()) bulk_wait_read<1>();             // (bulk groups belong to the issuing = elected lane)
     }
     __syncwarp();
@@ -318,7 +317,7 @@ struct BoxStager {
   }
   template <bool REDUCE>
   __device__ __forceinline__ void submit(const CUtensorMap* tm, uint8_t* box, int x, int y, int lane) {
-    if (dbg != 8) fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
+    fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the async (TMA) proxy
     __syncwarp();
     if (elect_one()) {
       if (REDUCE) tma_reduce_add_2d(tm, box, x, y);
@@ -391,9 +390,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
         }
       }
       box_put_float32(box, r, v);
-      if (p.debug_mode == 0) st.submit<true>(tmOut, box, col0 + c * 32, m0, lane);
-      else if (p.debug_mode == 1) st.submit<false>(tmOut, box, col0 + c * 32, m0, lane);
-      else { __syncwarp(); }
+      st.submit<true>(tmOut, box, col0 + c * 32, m0, lane);
     }
   }
 }
@@ -568,23 +565,9 @@ __device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtenso
       }
       f2_unpack(f2_mul(gelu2(x2), y2), o[2 * e], o[2 * e + 1]);
     }
-    if (p.debug_mode == 10) {   // experiment: direct global stores (32 bytes per thread and step)
-      if (m0 + r < p.M) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out16 + static_cast<size_t>(m0 + r) * p.ld16 + n_tile * 128 +
-                                              half * 64 + 16 * s);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          uint4 u;
-          u.x = pack_half2(o[8 * i + 0], o[8 * i + 1]);
-          u.y = pack_half2(o[8 * i + 2], o[8 * i + 3]);
-          u.z = pack_half2(o[8 * i + 4], o[8 * i + 5]);
-          u.w = pack_half2(o[8 * i + 6], o[8 * i + 7]);
-          dst[i] = u;
-        }
-      }
-    } else if (p.debug_mode != 4) box_put_half16(box, r, 2 * s, o);
+    box_put_half16(box, r, 2 * s, o);   // (debug_mode 4 keeps the math and the smem staging, drops the TMA store)
   }
-  if (p.debug_mode != 4 && p.debug_mode != 10) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
+  if (p.debug_mode != 4) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
 }
 
 // Launched as clusters of 2 CTAs (an SM pair) that cooperate on one 256 x 256 output tile with
@@ -829,7 +812,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (elect_one()) bulk_wait<0>();
       __syncwarp();
     } else {
-      BoxStager stager{my_smem, 0u, p.debug_mode};
+      BoxStager stager{my_smem, 0u};
       if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
       if (kRope<EPI> && lane == 0) tma_prefetch_desc(&tmOut2);
       uint64_t* rope_bar = bar_x + STATS_BARS * (warp - 2);
@@ -845,7 +828,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (kNorm<EPI>) rs = row_rstd(p, m0 + lane);
           float cs[32], sn[32];
           if constexpr (kRope<EPI>) {
-            if (n_idx * BN < 2 * p.hidden && p.debug_mode != 5)
+            if (n_idx * BN < 2 * p.hidden)
               rope_prefetch(p, &tmOut2, stager, rope_bar, rope_phase, m0, lane, cs, sn);
           }
           mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);

@@ -51,8 +51,8 @@ struct GemmEpiParams {
   float ln_eps = 1e-5f;
   float inv_dim = 1.0f / 768.0f;      // 1 / (number of columns the moments were taken over)
   int M = 0;                          // valid rows
-  int debug_mode = 0;                 // timing experiments only (VRAG_DEBUG_RESID): 1 = plain store instead of
-                                      // reduce-add (wrong values), 2 = no store at all
+  int debug_mode = 0;                 // timing experiments of vrag_bench_gemm only: 3 = mainloop only (the epilogue
+                                      // releases the accumulators at once), 4 = epilogue without its TMA stores
 };
 
 constexpr int GEMM_BM = 128;

@@ -26,6 +26,9 @@ constexpr int QT = 8;          // queries per corpus pass
 constexpr int MARGIN = 16;     // extra candidates kept for the fp64 re-ranking
 constexpr int MAX_K = 1024;
 constexpr int SEL_WARPS = 8;
+constexpr int FIN_WARPS = 32;               // warps of the fused finish kernel: one fp64 re-score per warp
+constexpr int SEL_UNROLL = 8;               // loads in flight per lane of the register-list selection
+constexpr int64_t SEL_REG_BLOCK = 16384;    // scores per block (2048 per warp list) of the register-list selection
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;
@@ -654,26 +657,41 @@ select_reg_kernel(const float* __restrict__ scores, const uint64_t* __restrict__
   const int64_t b0 = per_block * blockIdx.x, b1 = min(n, b0 + per_block);
   const int64_t per_warp = (b1 - b0 + SEL_WARPS - 1) / SEL_WARPS;
   const int64_t w0 = b0 + per_warp * warp, w1 = min(b1, w0 + per_warp);
+  // SEL_UNROLL independent coalesced loads per lane are in flight before anything is compared: the stream is bound
+  // by memory latency and by the ~kp ln(m / kp) list insertions per warp, not by bandwidth.
   uint64_t mine = 0, thr = 0;
-  for (int64_t i0 = w0; i0 < w1; i0 += 32) {
-    const int64_t i = i0 + lane;
-    uint64_t key = 0;
-    if (i < w1) {
-      if (FROM_SCORES) {
-        const float s = scores[static_cast<size_t>(q) * n + i];
-        key = (s == -INFINITY) ? 0 : make_key(s, static_cast<uint32_t>(i));
-      } else {
-        key = keys_in[static_cast<size_t>(q) * n + i];
-      }
+  for (int64_t i0 = w0; i0 < w1; i0 += 32 * SEL_UNROLL) {
+    // unconditional loads from clamped indices (a guarded load compiles to a branch around load + use, which
+    // serialises the eight round trips: measured 150 us instead of 25 us per 8 192 scores); tail lanes are masked after
+    uint64_t key[SEL_UNROLL];
+    float sc[SEL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SEL_UNROLL; ++u) {
+      const int64_t i = min(i0 + u * 32 + lane, w1 - 1);
+      if (FROM_SCORES) sc[u] = __ldcs(scores + static_cast<size_t>(q) * n + i);
+      else key[u] = __ldcs(keys_in + static_cast<size_t>(q) * n + i);
     }
-    unsigned m = __ballot_sync(0xffffffffu, key > thr);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const uint64_t x = __shfl_sync(0xffffffffu, key, src);
-      if (x > thr) {
-        mine = reg_list_insert(mine, x, kp, lane);
-        thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+#pragma unroll
+    for (int u = 0; u < SEL_UNROLL; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      if (FROM_SCORES) key[u] = (sc[u] == -INFINITY) ? 0 : make_key(sc[u], static_cast<uint32_t>(i));
+      if (i >= w1) key[u] = 0;
+    }
+    bool hit = false;
+#pragma unroll
+    for (int u = 0; u < SEL_UNROLL; ++u) hit |= key[u] > thr;
+    if (!__any_sync(0xffffffffu, hit)) continue;
+#pragma unroll
+    for (int u = 0; u < SEL_UNROLL; ++u) {
+      unsigned m = __ballot_sync(0xffffffffu, key[u] > thr);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t x = __shfl_sync(0xffffffffu, key[u], src);
+        if (x > thr) {
+          mine = reg_list_insert(mine, x, kp, lane);
+          thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+        }
       }
     }
   }
@@ -783,6 +801,104 @@ rank_kernel(const double* __restrict__ score64, const int64_t* __restrict__ ids,
   }
 }
 
+// ---------------------------------------------------------------------------------- fused finish (dense, kp <= 32)
+// One block per query: (A) merge the per-block candidate lists of the streaming selection into the best kp keys,
+// (B) re-score those kp rows in fp64 (same summation order as dense_rescore_kernel), (C) rank by (score desc, row asc)
+// and write the k results -- the work of select_reg_kernel<false> + dense_rescore_kernel + rank_kernel in one launch
+// (three dependent ~10 us launches per query tile were a fifth of a 16-query search over 1 M rows).
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+dense_finish_kernel(const uint64_t* __restrict__ keys_in, int64_t n_keys, int kp, int k, const float* __restrict__ rows,
+                    int dim, const double* __restrict__ norm64, const float* __restrict__ queries, int64_t id_base,
+                    int64_t* __restrict__ ids_out, float* __restrict__ scores_out, double* __restrict__ scores64_out) {
+  __shared__ uint64_t lists[FIN_WARPS][32];
+  __shared__ double s64[32];
+  __shared__ int64_t crow[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
+  // (A)
+  const int64_t per_warp = (n_keys + FIN_WARPS - 1) / FIN_WARPS;
+  const int64_t w0 = per_warp * warp, w1 = min(n_keys, w0 + per_warp);
+  uint64_t mine = 0, thr = 0;
+  for (int64_t i0 = w0; i0 < w1; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const uint64_t key = i < w1 ? keys_in[static_cast<size_t>(q) * n_keys + i] : 0;
+    unsigned m = __ballot_sync(0xffffffffu, key > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t x = __shfl_sync(0xffffffffu, key, src);
+      if (x > thr) {
+        mine = reg_list_insert(mine, x, kp, lane);
+        thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+      }
+    }
+  }
+  lists[warp][lane] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < FIN_WARPS; ++w) {
+      for (int j = 0; j < kp; ++j) {
+        const uint64_t x = lists[w][j];
+        if (x <= thr) break;  // sorted descending
+        mine = reg_list_insert(mine, x, kp, lane);
+        thr = __shfl_sync(0xffffffffu, mine, kp - 1);
+      }
+    }
+    lists[0][lane] = mine;
+  }
+  __syncthreads();
+  // (B)
+  const float* qv = queries + static_cast<size_t>(q) * dim;
+  for (int c = warp; c < kp; c += FIN_WARPS) {   // one candidate per warp
+    const uint64_t key = lists[0][c];
+    if (key == 0) {
+      if (lane == 0) { s64[c] = -INFINITY; crow[c] = -1; }
+      continue;
+    }
+    const int64_t row = key_row(key);
+    const float* r = rows + row * dim;
+    double dot = 0.0, qq = 0.0;
+    for (int i = lane; i < dim; i += 32) {
+      const double a = static_cast<double>(r[i]), b = static_cast<double>(qv[i]);
+      dot += a * b;
+      qq += b * b;
+    }
+    dot = warp_sum_d(dot);
+    qq = warp_sum_d(qq);
+    if (lane == 0) {
+      const double den = sqrt(qq) * norm64[row];
+      s64[c] = den > 0.0 ? dot / den : 0.0;
+      crow[c] = row;
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {  // default fill (fewer than k live rows)
+    ids_out[static_cast<size_t>(q) * k + j] = -1;
+    scores_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+    if (scores64_out) scores64_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  // (C)
+  if (threadIdx.x < kp) {
+    const int i = threadIdx.x;
+    const int64_t idi = crow[i];
+    if (idi >= 0) {
+      const double si = s64[i];
+      int rank = 0;
+      for (int j = 0; j < kp; ++j) {
+        const int64_t idj = crow[j];
+        if (idj < 0 || j == i) continue;
+        const double sj = s64[j];
+        rank += (sj > si) || (sj == si && (idj < idi || (idj == idi && j < i)));
+      }
+      if (rank < k) {
+        ids_out[static_cast<size_t>(q) * k + rank] = idi + id_base;
+        scores_out[static_cast<size_t>(q) * k + rank] = static_cast<float>(si);
+        if (scores64_out) scores64_out[static_cast<size_t>(q) * k + rank] = si;
+      }
+    }
+  }
+}
+
 __global__ void query_norm_kernel(const float* __restrict__ queries, int dim, float* __restrict__ inv_norm_q) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
@@ -835,13 +951,17 @@ void grow(vrag_ctx* ctx, DevBuf& b, size_t used_bytes, size_t need_bytes) {
 }
 
 // scores [nq_tile][n] on device -> final top-k for the tile written at out offsets
-void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float* queries_dev /*dense*/,
-                     int64_t* ids_out, float* s32_out, double* s64_out /*device, tile offset applied*/) {
+void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bool dense,
+                     const float* queries_dev /*dense*/, int64_t* ids_out, float* s32_out,
+                     double* s64_out /*device, tile offset applied*/, cudaStream_t st) {
   vrag_ctx* ctx = ix->ctx;
   const int64_t n = ix->n;
   const int kp = static_cast<int>(std::min<int64_t>(k + MARGIN, std::max<int64_t>(n, 1)));
-  // 8192 scores per block (1024 per warp list): list insertions stay a small fraction of the streaming compares
-  const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 8191) / 8192, ctx->num_sms * 4)));
+  // scores per block: 16 384 with register lists (2 048 per warp = 8 rounds of 8 loads in flight per lane; ~110
+  // insertions, 5 % of the keys; 16 queries x 62 blocks at 1 M rows are one wave of the GPU), 8 192 with
+  // shared-memory lists (k > 16)
+  const int64_t per_blk = kp <= 32 ? SEL_REG_BLOCK : 8192;
+  const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + per_blk - 1) / per_blk, ctx->num_sms * 4)));
   const size_t smem = static_cast<size_t>(SEL_WARPS) * kp * 8;
   static bool smem_attr = false;
   if (!smem_attr) {
@@ -851,22 +971,31 @@ void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float
   }
   ix->keys0.reserve(static_cast<size_t>(nq_tile) * nblk0 * kp * 8);
   ix->keys1.reserve(static_cast<size_t>(nq_tile) * kp * 8);
-  ProfScope prof(ctx, PROF_SELECT);
+  ProfScope prof(ctx, PROF_SELECT, st);
   if (kp <= 32)
-    select_reg_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, 0, ctx->stream>>>(
-        ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
+    select_reg_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, 0, st>>>(
+        scores, nullptr, n, kp, ix->keys0.as<uint64_t>());
   else
-    select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
-        ix->scores.as<float>(), nullptr, n, kp, ix->keys0.as<uint64_t>());
+    select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, st>>>(
+        scores, nullptr, n, kp, ix->keys0.as<uint64_t>());
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
+  if (dense && kp <= 32) {   // merge + fp64 re-score + rank in one launch
+    dense_finish_kernel<<<nq_tile, 32 * FIN_WARPS, 0, st>>>(ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp,
+                                                            kp, k, ix->rows.as<float>(), ix->dim,
+                                                            ix->norm64.as<double>(), queries_dev, ix->id_base, ids_out,
+                                                            s32_out, s64_out);
+    VRAG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return;
+  }
   const uint64_t* final_keys = ix->keys0.as<uint64_t>();
   if (nblk0 > 1) {
     if (kp <= 32)
-      select_reg_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, 0, ctx->stream>>>(
+      select_reg_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, 0, st>>>(
           nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
     else
-      select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, ctx->stream>>>(
+      select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, st>>>(
           nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
     VRAG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -876,16 +1005,16 @@ void select_and_rank(vrag_index* ix, int nq_tile, int k, bool dense, const float
   ix->crow.reserve(static_cast<size_t>(nq_tile) * kp * 8);
   dim3 g((kp + 7) / 8, nq_tile);
   if (dense)
-    dense_rescore_kernel<<<g, 256, 0, ctx->stream>>>(ix->rows.as<float>(), ix->dim, ix->norm64.as<double>(),
+    dense_rescore_kernel<<<g, 256, 0, st>>>(ix->rows.as<float>(), ix->dim, ix->norm64.as<double>(),
                                                       queries_dev, final_keys, kp, ix->s64.as<double>(),
                                                       ix->crow.as<int64_t>());
   else
-    sparse_rescore_kernel<<<g, 256, 0, ctx->stream>>>(ix->indptr.as<int64_t>(), ix->indices.as<int32_t>(),
+    sparse_rescore_kernel<<<g, 256, 0, st>>>(ix->indptr.as<int64_t>(), ix->indices.as<int32_t>(),
                                                        ix->values.as<float>(), ix->qT.as<float>(), -1, final_keys, kp,
                                                        ix->s64.as<double>(), ix->crow.as<int64_t>());
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
-  rank_kernel<<<nq_tile, 256, 0, ctx->stream>>>(ix->s64.as<double>(), ix->crow.as<int64_t>(), kp, k, ix->id_base,
+  rank_kernel<<<nq_tile, 256, 0, st>>>(ix->s64.as<double>(), ix->crow.as<int64_t>(), kp, k, ix->id_base,
                                                 ids_out, s32_out, s64_out);
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1093,6 +1222,9 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   const char* tc_env = getenv("VRAG_SCAN_TC_MIN");  // debug: 0 forces the FMA path, else the smallest tile for TC
   const int tc_min = tc_env ? atoi(tc_env) : TC_MIN_Q;
   const bool tc_ok = tc_min > 0 && dim % 32 == 0 && dim <= 768 && n < (int64_t(1) << 31) - TC_ROWS;
+  // (Tried: running the selection of tile t on a low-priority side stream under the scan of tile t + 1.  The scan is
+  // a finely balanced HBM-bound pipeline with one CTA per SM; co-resident selection blocks slowed it by more than the
+  // selection costs when serialised -- 42.7 ms vs 41.0 ms per 1000 queries over 1 M rows -- so tiles run back to back.)
   idx->scores.reserve(static_cast<size_t>(tc_ok ? TCQ : QT) * n * 4);
   const int grid = static_cast<int>(std::min<int64_t>((n + 31) / 32, static_cast<int64_t>(_ctx->num_sms) * 2));
   for (int q0 = 0; q0 < nq;) {
@@ -1100,6 +1232,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     const int nt = std::min(use_tc ? TCQ : QT, nq - q0);
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
+    float* scores = idx->scores.as<float>();
     if (use_tc) {
       ProfScope prof(_ctx, PROF_SCAN);
       const CUtensorMap tmX = make_tmap_2d(_ctx, idx->rows.as<float>(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
@@ -1112,7 +1245,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       }
       const int tgrid = static_cast<int>(std::min<int64_t>((n + TC_ROWS - 1) / TC_ROWS, _ctx->num_sms));
       dense_scan_tc_kernel<<<tgrid, TC_THREADS, smem, _ctx->stream>>>(tmX, n, dim, qt, nt, idx->inv32.as<float>(), qn,
-                                                                      idx->skip(), idx->scores.as<float>());
+                                                                      idx->skip(), scores);
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     } else {
@@ -1130,7 +1263,7 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
     VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tma_kernel<V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     dense_scan_tma_kernel<V, Q><<<tgrid, 32 * (SCAN_CONSUMER_WARPS + 1), smem, _ctx->stream>>>(                     \
         idx->rows.as<float>(), n, qt, idx->inv32.as<float>(), qn, idx->skip(),                                      \
-        idx->scores.as<float>(), nstage, nt);                                                                      \
+        scores, nstage, nt);                                                                      \
   } while (0)
 #define VRAG_SCAN_Q(V)                                \
   do {                                                \
@@ -1147,13 +1280,14 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       } else {
         dense_scan_generic_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->rows.as<float>(), n, dim, qt, nt,
                                                                   idx->inv32.as<float>(), qn, idx->skip(),
-                                                                  idx->scores.as<float>());
+                                                                  scores);
       }
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     }
-    select_and_rank(idx, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
-                    d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
+    select_and_rank(idx, scores, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k,
+                    d_s32 + static_cast<size_t>(q0) * k, d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr,
+                    _ctx->stream);
     q0 += nt;
   }
   if (!on_device) {
@@ -1208,9 +1342,10 @@ extern "C" int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     }
-    select_and_rank(idx, nt, k, false, nullptr, idx->out_ids.as<int64_t>() + static_cast<size_t>(q0) * k,
+    select_and_rank(idx, idx->scores.as<float>(), nt, k, false, nullptr,
+                    idx->out_ids.as<int64_t>() + static_cast<size_t>(q0) * k,
                     idx->out_s32.as<float>() + static_cast<size_t>(q0) * k,
-                    idx->out_s64.as<double>() + static_cast<size_t>(q0) * k);
+                    idx->out_s64.as<double>() + static_cast<size_t>(q0) * k, _ctx->stream);
   }
   VRAG_CUDA(cudaMemcpyAsync(ids_out, idx->out_ids.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
   VRAG_CUDA(cudaMemcpyAsync(scores_out, idx->out_s32.p, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, _ctx->stream));
