@@ -1225,14 +1225,22 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   // (Tried: running the selection of tile t on a low-priority side stream under the scan of tile t + 1.  The scan is
   // a finely balanced HBM-bound pipeline with one CTA per SM; co-resident selection blocks slowed it by more than the
   // selection costs when serialised -- 42.7 ms vs 41.0 ms per 1000 queries over 1 M rows -- so tiles run back to back.)
-  idx->scores.reserve(static_cast<size_t>(tc_ok ? TCQ : QT) * n * 4);
+  // Selection groups: the score rows of up to `group_max` consecutive full tensor-core tiles (16 queries each) are kept
+  // and selected by ONE select + finish launch pair.  The selection is latency-bound (8 dependent load rounds per warp
+  // list, then a one-block-per-query finish), so its cost per launch barely grows with the number of queries, and on
+  // small shards (125 k rows per GPU at 8 GPUs: 80 us of scan per tile) a per-tile selection would cost as much as the
+  // scan.  Score buffer: group x 16 x n floats, capped at 512 MB.
+  const size_t tile_scores = static_cast<size_t>(tc_ok ? TCQ : QT) * n;
+  const int group_max = tc_ok ? static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (size_t(512) << 20) / (tile_scores * 4)))) : 1;
+  idx->scores.reserve(static_cast<size_t>(group_max) * tile_scores * 4);
   const int grid = static_cast<int>(std::min<int64_t>((n + 31) / 32, static_cast<int64_t>(_ctx->num_sms) * 2));
+  int g_tiles = 0, g_q0 = 0;   // tiles / first query of the open selection group
   for (int q0 = 0; q0 < nq;) {
     const bool use_tc = tc_ok && nq - q0 >= tc_min;
     const int nt = std::min(use_tc ? TCQ : QT, nq - q0);
     const float* qt = qd + static_cast<size_t>(q0) * dim;
     const float* qn = idx->qnorm.as<float>() + q0;
-    float* scores = idx->scores.as<float>();
+    float* scores = idx->scores.as<float>() + static_cast<size_t>(g_tiles) * tile_scores;
     if (use_tc) {
       ProfScope prof(_ctx, PROF_SCAN);
       const CUtensorMap tmX = make_tmap_2d(_ctx, idx->rows.as<float>(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
@@ -1285,10 +1293,18 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     }
-    select_and_rank(idx, scores, nt, k, true, qt, d_ids + static_cast<size_t>(q0) * k,
-                    d_s32 + static_cast<size_t>(q0) * k, d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr,
-                    _ctx->stream);
+    if (g_tiles == 0) g_q0 = q0;
+    ++g_tiles;
     q0 += nt;
+    // close the group: it is full, the queries are exhausted, this tile is partial (its rows would not be contiguous
+    // with a following tile's), or the next tile takes the FMA path (different tile stride)
+    const bool next_tc = tc_ok && nq - q0 >= tc_min;
+    if (g_tiles == group_max || q0 >= nq || nt < TCQ || !use_tc || !next_tc) {
+      select_and_rank(idx, idx->scores.as<float>(), q0 - g_q0, k, true, qd + static_cast<size_t>(g_q0) * dim,
+                      d_ids + static_cast<size_t>(g_q0) * k, d_s32 + static_cast<size_t>(g_q0) * k,
+                      d_s64 ? d_s64 + static_cast<size_t>(g_q0) * k : nullptr, _ctx->stream);
+      g_tiles = 0;
+    }
   }
   if (!on_device) {
     VRAG_CUDA(cudaMemcpyAsync(ids_out, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
