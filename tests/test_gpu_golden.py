@@ -257,3 +257,11 @@ def test_end_to_end_batch_pipeline_matches_per_query_plugins():
     for q, rs, sb in zip(questions[:6], got[:6], spans_b[:6]):
         assert ext.extract_spans(q, rs) == sb
         assert all(s in text for text, sp in sb.items() for s in sp)
+    # sliced host pipelines (tokenise slice i + 1 while the GPU runs slice i) give bit-identical outputs
+    whole = ext.extract_spans_batch(questions, got)
+    ext.pipeline_pairs = 64
+    assert ext.extract_spans_batch(questions, got) == whole
+    ip, ix, vl = prov.embed_batch_csr(chunks)
+    prov.pipeline_texts = 77
+    ip2, ix2, vl2 = prov.embed_batch_csr(chunks)
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and np.array_equal(vl, vl2)

@@ -84,6 +84,7 @@ class B200SpanExtractor(SpanExtractor):
         self._enc = _native.Encoder(self._ctx, _native.ENC_MODERNBERT_TOKCLS, weights, int(num_layers),
                                     int(vocab_size), max_tokens=max_tokens)
         self._lock = threading.Lock()  # shared across to_thread workers (extractors.py:48-54)
+        self.pipeline_pairs = 512      # pairs per slice of the tokenise / forward / post-process pipeline
 
     # -- reference interface -------------------------------------------------------------------------
     def extract_spans(self, question: str, search_results: List[Any]) -> Dict[str, List[str]]:
@@ -116,10 +117,31 @@ class B200SpanExtractor(SpanExtractor):
     def extract_detailed(self, pairs: Sequence[Tuple[str, str]]) -> List[List[Dict[str, Any]]]:
         """Spans with offsets and scores for each (question, context) pair:
         ``{"text", "start", "end", "score", "tok_start", "tok_end"}`` (char offsets into the context)."""
-        plan = self._tokenize(pairs)
+        pairs = list(pairs)
+        step = self.pipeline_pairs
+        if len(pairs) <= step:
+            plan = self._tokenize(pairs)
+            return self._postprocess(pairs, plan, self._forward(plan))
+        # Large batches: host tokenisation of slice i + 1 and span post-processing of slice i - 1 overlap the GPU forward
+        # of slice i (one worker thread owns the encoder; the tokenizers library and the ctypes call release the GIL).
+        # Every (question, context) pair is independent in every kernel, so slicing does not change any result.
+        from concurrent.futures import ThreadPoolExecutor
+        out: List[List[Dict[str, Any]]] = []
+        with ThreadPoolExecutor(max_workers=1) as gpu:
+            pending = None
+            for a in range(0, len(pairs), step):
+                sl = pairs[a:a + step]
+                plan = self._tokenize(sl)
+                fut = gpu.submit(self._forward, plan)
+                if pending is not None:
+                    out.extend(self._postprocess(pending[0], pending[1], pending[2].result()))
+                pending = (sl, plan, fut)
+            out.extend(self._postprocess(pending[0], pending[1], pending[2].result()))
+        return out
+
+    def _forward(self, plan: Dict[str, Any]) -> np.ndarray:
         with self._lock:
-            probs = self._enc.span_forward(plan["ids"], plan["cu"])
-        return self._postprocess(pairs, plan, probs)
+            return self._enc.span_forward(plan["ids"], plan["cu"])
 
     # -- internals -----------------------------------------------------------------------------------------
     def _tokenize(self, pairs: Sequence[Tuple[str, str]]) -> Dict[str, Any]:

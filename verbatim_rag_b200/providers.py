@@ -64,6 +64,7 @@ class B200SpladeProvider(SparseEmbeddingProvider):
         self.device = device
         self._te = _BertTextEncoder(model_name, device, _native.ENC_BERT_MLM, max_seq_length, max_tokens, weights,
                                     tokenizer, num_layers, vocab_size)
+        self.pipeline_texts = 1024   # texts per slice of the tokenise / encode pipeline of embed_batch_csr
 
     def embed_text(self, text: str) -> Dict[int, float]:
         ip, idx, val = self.embed_batch_csr([text], min_abs=1e-6)
@@ -79,10 +80,28 @@ class B200SpladeProvider(SparseEmbeddingProvider):
         building Python dicts."""
         if len(texts) == 0:
             return np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32)
-        ids, cu = self._te.tokenize(texts)
-        with self._te._lock:
-            out = self._te._enc.splade_forward(ids, cu, min_abs=min_abs)
-        return out["indptr"], out["indices"], out["values"]
+        texts = list(texts)
+        step = self.pipeline_texts
+
+        def forward(ids, cu):
+            with self._te._lock:
+                return self._te._enc.splade_forward(ids, cu, min_abs=min_abs)
+
+        if len(texts) <= step:
+            out = forward(*self._te.tokenize(texts))
+            return out["indptr"], out["indices"], out["values"]
+        # index builds: tokenisation of slice i + 1 overlaps the GPU encode of slice i (texts are independent)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as gpu:
+            futs = [gpu.submit(forward, *self._te.tokenize(texts[a:a + step])) for a in range(0, len(texts), step)]
+            parts = [f.result() for f in futs]
+        indptr = [np.zeros(1, np.int64)]
+        base = 0
+        for o in parts:
+            indptr.append(o["indptr"][1:].astype(np.int64) + base)
+            base += int(o["indptr"][-1])
+        return (np.concatenate(indptr), np.concatenate([o["indices"] for o in parts]),
+                np.concatenate([o["values"] for o in parts]))
 
     def get_dimension(self) -> int:
         return self._te.vocab_size
