@@ -379,7 +379,7 @@ def run_gpu_arm(args, out):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "seqs_per_step_per_gpu": nseq, "seq_len": SEQ_LEN, "layers": LAYERS,
-                   "precision": "fp16 tensor-core operands, fp32 accumulate + fp32 residual stream",
+                   "precision": "fp16 tensor-core operands, fp32 accumulate, two-plane residual stream (fp16 + e5m2, >= 14 bits)",
                    "max_tokens_per_pass": args.max_tokens,
                    "l2": "working set per step (>= 11.5 KB of activations per token, %.1f GB) exceeds the 126 MB L2"
                          % (11.5e3 * T / 1e9),

@@ -73,6 +73,45 @@ def test_span_extractor_config1_vs_golden():
     assert d[c["pairs"][3][1]] == [s["text"] for s in got[3]]
 
 
+def test_span_extractor_long_documents_windows_vs_oracle():
+    """Documents longer than max_length: overlapping windows (doc_stride), max P(relevant) over the windows that hold a
+    token, ragged document lengths incl. a 1-token and an exactly-window-sized one -- B200SpanExtractor against the
+    reference-shaped CPU plugin (oracle/plugins.py OracleSpanExtractor, restating the v2 process() contract,
+    SURVEY.md App. B.2) on a 4-layer model (one global + three local-window layers)."""
+    import cases
+    from verbatim_rag_b200 import B200SpanExtractor
+    from verbatim_rag_b200.synthetic import ModernBertSpec, make_modernbert_weights
+    from oracle.plugins import OracleSpanExtractor
+    spec = ModernBertSpec(layers=4)
+    w = make_modernbert_weights(31, spec)
+    tok = cases.tokenizer("modernbert")
+    rng = np.random.default_rng(32)
+    q = tok.make_question(rng, 9)
+    max_length, stride = 160, 48          # 148 context tokens per window
+    docs = [tok.make_text(rng, n) for n in (1, 40, 148, 149, 400, 1033)]
+    kw = dict(max_length=max_length, doc_stride=stride)
+    ext = B200SpanExtractor(weights=w, tokenizer=tok, num_layers=spec.layers, vocab_size=spec.vocab_size,
+                            max_tokens=4096, **kw)
+    ora = OracleSpanExtractor(w, tok, spec, **kw)
+    plan = ext._tokenize([(q, d) for d in docs])
+    assert len(plan["win_pair"]) > len(docs) + 5 and int(np.diff(plan["cu"]).max()) <= max_length
+    got = ext.extract_detailed([(q, d) for d in docs])
+    n_span, n_diff = 0, 0
+    for d, spans in zip(docs, got):
+        ref = ora.process(q, d)["spans"]
+        mine = [(s["start"], s["end"]) for s in spans]
+        exp = [(s["start"], s["end"]) for s in ref]
+        n_span += len(exp)
+        if mine != exp:   # only a token within the probability tolerance of the threshold may differ
+            n_diff += 1
+            probs = np.asarray(ora.process(q, d).get("token_probs", []), dtype=np.float32)
+            assert probs.size == 0 or (np.abs(probs - np.float32(0.2)) < PROB_TOL).any(), (mine, exp)
+        assert all(s["text"] == d[s["start"]:s["end"]] for s in spans)
+    _diag(test="span_long_documents", docs=len(docs), windows=len(plan["win_pair"]), oracle_spans=n_span,
+          docs_with_span_mismatch=n_diff)
+    assert n_span > 0 and n_diff <= 1
+
+
 def test_splade_provider_vs_golden():
     import cases
     from verbatim_rag_b200 import B200SpladeProvider
