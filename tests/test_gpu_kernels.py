@@ -9,6 +9,7 @@ import pytest
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
+BERT_DEFERRED = os.environ.get("VRAG_BERT_DEFERRED_LN") == "1"
 
 
 def _diag(**kw):
@@ -34,17 +35,31 @@ def test_tcgen05_gemm_matches_simt_reference(ctx, M, N, K):
 
 
 @pytest.mark.parametrize("epi,name", [(0, "f16"), (1, "rope_qkv"), (2, "resid_f32"), (3, "geglu"),
-                                      (11, "resid_stats"), (12, "norm_rope_qkv"), (13, "norm_geglu")])
+                                      (11, "resid_stats"), (12, "norm_rope_qkv"), (13, "norm_geglu"),
+                                      (14, "norm_bias_f16"), (15, "norm_bias_gelu_f16"), (16, "resid_stats_ln")])
 @pytest.mark.parametrize("M", [128, 300, 5000, 1001])
 def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
     """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel.
     Token positions in the self test: even M = sequences of 200 tokens (RoPE slabs fetch cos / sin by TMA, the ones
     straddling a sequence boundary gather), odd M = hashed positions (every slab gathers)."""
+    if epi >= 14 and not BERT_DEFERRED:
+        pytest.skip("BERT deferred-LayerNorm epilogues: opt-in (VRAG_BERT_DEFERRED_LN=1)")
     N, K = 2304, 768
     diff, ref_max = ctx.selftest_gemm(M, N, K, epi)
     _diag(test="gemm_epilogue_selftest", epilogue=name, M=M, max_abs_diff=diff, ref_abs_max=ref_max)
     tol = 2e-3 if epi != 2 else 1e-4   # fp16 outputs: one rounding of slightly different fp32 sums
     assert diff <= tol * max(ref_max, 1.0), (name, diff, ref_max)
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 768, 768), (20000, 768, 3072)])
+def test_residual_stats_ln_epilogue_bert_shapes(ctx, M, N, K):
+    """BERT attention.output / output dense of the deferred-LayerNorm path: the old stream is normalised on the fly
+    ((hi + lo - mean) * rstd * gamma + beta + bias) from moments in one buffer while the new moments go to another."""
+    if not BERT_DEFERRED:
+        pytest.skip("BERT deferred-LayerNorm epilogues: opt-in (VRAG_BERT_DEFERRED_LN=1)")
+    diff, ref_max = ctx.selftest_gemm(M, N, K, 16)
+    _diag(test="gemm_resid_stats_ln", M=M, N=N, K=K, max_abs_diff=diff, ref_abs_max=ref_max)
+    assert diff <= 2e-3 * max(ref_max, 1.0), (diff, ref_max)
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 768, 768), (129, 768, 1152), (40000, 768, 768), (33000, 768, 1152)])

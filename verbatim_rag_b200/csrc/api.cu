@@ -279,12 +279,14 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
     VRAG_CUDA(cudaSetDevice(ctx->device));
-    const bool stats = epilogue == EPI_RESID_STATS;
+    const bool stats = epilogue == EPI_RESID_STATS || epilogue == EPI_RESID_STATS_LN;
+    const bool norm_bias = epilogue == EPI_NORM_BIAS_F16 || epilogue == EPI_NORM_BIAS_GELU_F16;
     const bool f32_out = epilogue == EPI_F32 || epilogue == EPI_RESID_F32;
     const bool rope = epilogue == EPI_ROPE_QKV || epilogue == EPI_NORM_ROPE_QKV;
     const bool geglu = epilogue == EPI_GEGLU || epilogue == EPI_NORM_GEGLU;
-    VRAG_CHECK(epilogue == EPI_F32 || epilogue == EPI_F16 || epilogue == EPI_RESID_F32 || rope || geglu || stats,
-               VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3, 11, 12, 13");
+    VRAG_CHECK(epilogue == EPI_F32 || epilogue == EPI_F16 || epilogue == EPI_RESID_F32 || rope || geglu || stats ||
+                   norm_bias,
+               VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3, 11, 12, 13, 14, 15, 16");
     VRAG_CHECK(!rope || N % 192 == 0, VRAG_ERR_ARG, "selftest_gemm: ROPE needs N = 3 * hidden");
     const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
@@ -292,7 +294,10 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     const int max_pos = 512;
     const int slots = N / 128;   // EPI_RESID_STATS writes one (sum, sumsq) pair per row and 128 columns
     const size_t st_pairs = static_cast<size_t>(M) * (stats ? slots : 6);
-    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS;
+    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS, SIN, BIAS, GAMMA;
+    SIN.reserve(static_cast<size_t>(M) * 6 * 8);
+    BIAS.reserve(static_cast<size_t>(N) * 4);
+    GAMMA.reserve(static_cast<size_t>(N) * 4);
     A.reserve(static_cast<size_t>(M) * K * 2);
     W.reserve(static_cast<size_t>(N) * K * 2);
     C0.reserve(out_bytes);
@@ -322,6 +327,9 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, out_bytes, st));  // NaN pattern: unwritten outputs are detected
       VRAG_CUDA(cudaMemsetAsync(C1.p, 0, out_bytes, st));
     }
+    fill_float_kernel<<<blocks_for(N), 256, 0, st>>>(BIAS.as<float>(), N, 71u, 0.5f);
+    fill_float_kernel<<<blocks_for(N), 256, 0, st>>>(GAMMA.as<float>(), N, 72u, 1.0f);
+    fill_stats_kernel<<<blocks_for(static_cast<size_t>(M) * 6), 256, 0, st>>>(SIN.as<float>(), static_cast<size_t>(M) * 6, 9u);
     if (stats) {
       VRAG_CUDA(cudaMemsetAsync(S0.p, 0xff, st_pairs * 8, st));
       VRAG_CUDA(cudaMemsetAsync(S1.p, 0, st_pairs * 8, st));
@@ -338,8 +346,10 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       p.out8_lo = (ref ? H1 : H0).as<uint8_t>();
       p.pos = POS.as<int32_t>(); p.rope_tab = CS.as<float>(); p.rope_rows = max_pos;
       p.hidden = N / 3;
-      p.stats_in = S0.as<float>();
+      p.stats_in = stats ? SIN.as<float>() : S0.as<float>();   // EPI_RESID_STATS_LN reads the old moments, writes new ones
       p.stats_out = stats ? (ref ? S1 : S0).as<float>() : nullptr;
+      p.bias = BIAS.as<float>();
+      p.gamma = GAMMA.as<float>();
       p.stats_slots = 6;
       launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, ref);
     }
@@ -368,7 +378,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     }
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
-    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS}) b->release();
+    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS, &SIN, &BIAS, &GAMMA}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();
@@ -389,9 +399,10 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
   try {
     VRAG_CUDA(cudaSetDevice(ctx->device));
     VRAG_CHECK(epilogue == EPI_F16 || epilogue == EPI_ROPE_QKV || epilogue == EPI_RESID_F32 || epilogue == EPI_GEGLU ||
-                   epilogue == EPI_RESID_STATS || epilogue == EPI_NORM_ROPE_QKV || epilogue == EPI_NORM_GEGLU,
+                   epilogue == EPI_RESID_STATS || epilogue == EPI_NORM_ROPE_QKV || epilogue == EPI_NORM_GEGLU ||
+                   epilogue == EPI_NORM_BIAS_F16 || epilogue == EPI_NORM_BIAS_GELU_F16 || epilogue == EPI_RESID_STATS_LN,
                VRAG_ERR_ARG, "bench_gemm: unsupported epilogue");
-    const bool f32_out = epilogue == EPI_RESID_F32 || epilogue == EPI_RESID_STATS;
+    const bool f32_out = epilogue == EPI_RESID_F32 || epilogue == EPI_RESID_STATS || epilogue == EPI_RESID_STATS_LN;
     const bool geglu = epilogue == EPI_GEGLU || epilogue == EPI_NORM_GEGLU;
     const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
@@ -403,7 +414,7 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     C16.reserve(out_n * 2);
     POS.reserve(static_cast<size_t>(M) * 4);
     CS.reserve(static_cast<size_t>(max_pos) * 64 * 4);
-    ST.reserve(static_cast<size_t>(M) * 12 * 4);
+    ST.reserve(static_cast<size_t>(M) * 24 * 4);
     cudaStream_t st = ctx->stream;
     fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
     fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
@@ -416,13 +427,15 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     p.ld32 = out_cols; p.ld16 = out_cols;
     p.out32 = C.as<float>();
     p.out16 = f32_out ? C16.as<__half>() : C.as<__half>();
-    if (epilogue == EPI_RESID_STATS) {   // two planes: C (first half) = hi, C16 = lo (e5m2)
+    if (f32_out && epilogue != EPI_RESID_F32) {   // two planes: C (first half) = hi, C16 = lo (e5m2)
       p.out16 = C.as<__half>();
       p.out8_lo = C16.as<uint8_t>();
     }
     p.pos = POS.as<int32_t>(); p.rope_tab = CS.as<float>(); p.rope_rows = max_pos;
     p.hidden = N / 3;
     p.stats_in = ST.as<float>(); p.stats_out = ST.as<float>(); p.stats_slots = 6;
+    if (epilogue == EPI_RESID_STATS_LN) p.stats_out = ST.as<float>() + static_cast<size_t>(M) * 12;
+    p.bias = CS.as<float>(); p.gamma = CS.as<float>() + 4096;   // any finite per-column vectors (N <= 4096)
     p.debug_mode = debug_mode;
     if (stages >= 3 && stages <= 5) ctx->gemm_stages = stages;
     cudaEvent_t e0, e1;

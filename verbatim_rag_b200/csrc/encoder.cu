@@ -44,6 +44,9 @@ struct vrag_encoder {
   struct BLayer {
     __half* wqkv; float* bqkv; __half* wo; float* bo; float *g1, *b1; __half* wi; float* bi; __half* wo2; float* bo2;
     float *g2, *b2;
+    // deferred-LayerNorm path: folded biases of the consumer GEMMs (beta . W + b) and, for the two residual GEMMs, the
+    // LayerNorm weight / (beta + dense bias) that normalise the OLD stream (the LayerNorm that precedes the sublayer)
+    float *cqkv = nullptr, *ci = nullptr, *ra_g = nullptr, *ra_b = nullptr, *rb_g = nullptr, *rb_b = nullptr;
   };
   std::vector<BLayer> bl;
   float *pos_emb = nullptr, *type_emb = nullptr;
@@ -51,13 +54,13 @@ struct vrag_encoder {
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work, stats, xl8;
+      pooled, work, stats, stats2, xl8;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
-                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &xl8})
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &stats2, &xl8})
       b->release();
   }
   template <typename T>
@@ -135,6 +138,15 @@ void fold_layernorm(const float* w, const float* gamma, size_t rows, size_t cols
   }
 }
 
+// bias seen by a consumer of LN(z) * gamma + beta:  c[n] = sum_k beta[k] W[n,k] + b[n]
+void fold_layernorm_bias(const float* w, const float* beta, const float* b, size_t rows, size_t cols, float* out) {
+  for (size_t n = 0; n < rows; ++n) {
+    double acc = b ? static_cast<double>(b[n]) : 0.0;
+    for (size_t k = 0; k < cols; ++k) acc += static_cast<double>(w[n * cols + k]) * beta[k];
+    out[n] = static_cast<float>(acc);
+  }
+}
+
 void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   const int H = HIDDEN, I = 1152;
   e->ffn = I;
@@ -195,7 +207,7 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
   e->type_emb = upload_f32(e, w.get(em + "token_type_embeddings.weight", 2LL * H), 2 * H);
   e->emb_g = upload_f32(e, w.get(em + "LayerNorm.weight", H), H);
   e->emb_b = upload_f32(e, w.get(em + "LayerNorm.bias", H), H);
-  std::vector<float> cat(static_cast<size_t>(3 * H) * H), bcat(3 * H);
+  std::vector<float> cat(static_cast<size_t>(3 * H) * H), bcat(3 * H), folded(static_cast<size_t>(I) * H), cbias(I);
   for (int i = 0; i < e->layers; ++i) {
     const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
     vrag_encoder::BLayer L{};
@@ -205,15 +217,50 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
              sizeof(float) * H * H);
       memcpy(&bcat[static_cast<size_t>(j) * H], w.get(p + "attention.self." + nm[j] + ".bias", H), sizeof(float) * H);
     }
-    L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H);
+    // LayerNorm that produced this layer's input: the embedding LayerNorm (layer 0) or the previous output.LayerNorm
+    const float* ga = i == 0 ? w.get(em + "LayerNorm.weight", H)
+                             : w.get("bert.encoder.layer." + std::to_string(i - 1) + ".output.LayerNorm.weight", H);
+    const float* ba = i == 0 ? w.get(em + "LayerNorm.bias", H)
+                             : w.get("bert.encoder.layer." + std::to_string(i - 1) + ".output.LayerNorm.bias", H);
+    if (e->deferred_ln) {
+      fold_layernorm_bias(cat.data(), ba, bcat.data(), 3 * H, H, cbias.data());
+      L.cqkv = upload_f32(e, cbias.data(), 3 * H);
+      fold_layernorm(cat.data(), ga, 3 * H, H, folded.data());
+      L.wqkv = upload_f16(e, staging, folded.data(), 3 * H, H);
+    } else {
+      L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H);
+    }
     L.bqkv = upload_f32(e, bcat.data(), 3 * H);
-    VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // bcat reused next layer
+    VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // bcat / cbias / folded reused next layer
     L.wo = upload_f16(e, staging, w.get(p + "attention.output.dense.weight", (int64_t)H * H), H, H);
     L.bo = upload_f32(e, w.get(p + "attention.output.dense.bias", H), H);
     L.g1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.weight", H), H);
     L.b1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.bias", H), H);
-    L.wi = upload_f16(e, staging, w.get(p + "intermediate.dense.weight", (int64_t)I * H), I, H);
-    L.bi = upload_f32(e, w.get(p + "intermediate.dense.bias", I), I);
+    const float* wi = w.get(p + "intermediate.dense.weight", (int64_t)I * H);
+    const float* bi = w.get(p + "intermediate.dense.bias", I);
+    const float* g1 = w.get(p + "attention.output.LayerNorm.weight", H);
+    const float* b1 = w.get(p + "attention.output.LayerNorm.bias", H);
+    if (e->deferred_ln) {
+      fold_layernorm_bias(wi, b1, bi, I, H, cbias.data());
+      L.ci = upload_f32(e, cbias.data(), I);
+      fold_layernorm(wi, g1, I, H, folded.data());
+      L.wi = upload_f16(e, staging, folded.data(), I, H);
+      // residual GEMMs: old stream normalised with (ga, ba) before attention.output, with (g1, b1) before output
+      const float* bo = w.get(p + "attention.output.dense.bias", H);
+      const float* bo2 = w.get(p + "output.dense.bias", H);
+      std::vector<float> t(H);
+      L.ra_g = upload_f32(e, ga, H);
+      for (int k = 0; k < H; ++k) t[k] = ba[k] + bo[k];
+      L.ra_b = upload_f32(e, t.data(), H);
+      VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
+      L.rb_g = upload_f32(e, g1, H);
+      for (int k = 0; k < H; ++k) t[k] = b1[k] + bo2[k];
+      L.rb_b = upload_f32(e, t.data(), H);
+      VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    } else {
+      L.wi = upload_f16(e, staging, wi, I, H);
+    }
+    L.bi = upload_f32(e, bi, I);
     L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I);
     L.bo2 = upload_f32(e, w.get(p + "output.dense.bias", H), H);
     L.g2 = upload_f32(e, w.get(p + "output.LayerNorm.weight", H), H);
@@ -248,9 +295,10 @@ void reserve_workspace(vrag_encoder* e) {
   e->buf32.reserve(T * H * 4);
   e->probs.reserve(T * 4);
   e->logits.reserve(T * 8);
-  if (e->kind == VRAG_ENC_MODERNBERT_TOKCLS && e->deferred_ln) {
+  if (e->deferred_ln) {
     e->stats.reserve(T * 6 * 8);
     e->xl8.reserve(T * H);
+    if (e->kind != VRAG_ENC_MODERNBERT_TOKCLS) e->stats2.reserve(T * 6 * 8);   // post-LN: moments are read and rewritten
   }
 }
 
@@ -342,7 +390,7 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
     dump(i + 1);
   }
-  if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, 1e-5f, h16);
+  if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, nullptr, 1e-5f, nullptr, h16);
   else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false);
   GemmEpiParams hd;
   hd.M = T; hd.out32 = e->buf32.as<float>(); hd.ld32 = H;
@@ -358,6 +406,38 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
   const int ref = e->use_reference_gemm ? 1 : 0;
   float* x32 = e->x32.as<float>();
   __half *h16 = e->h16.as<__half>(), *qkv = e->qkv16.as<__half>(), *o16 = e->o16.as<__half>(), *f16 = e->w16.as<__half>();
+  if (e->deferred_ln) {
+    // The stream holds the PRE-LayerNorm sums z (fp16 hi = the consumers' A operand, e5m2 lo, row moments); every
+    // LayerNorm of the stack lives in folded weights / biases and in the epilogues (gemm.cuh EPI_NORM_BIAS_* and
+    // EPI_RESID_STATS_LN).  Moments ping-pong between two buffers: a residual GEMM reads the old moments of a row in
+    // every N tile while other tiles already write the new ones.
+    uint8_t* xl8 = e->xl8.as<uint8_t>();
+    float* st[2] = {e->stats.as<float>(), e->stats2.as<float>()};
+    int cur = 0;
+    launch_bert_embed_raw(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
+                          e->type_emb, h16, xl8, st[cur], 6);
+    for (int i = 0; i < e->layers; ++i) {
+      const auto& L = e->bl[i];
+      GemmEpiParams p;
+      p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.bias = L.cqkv; p.stats_in = st[cur]; p.ln_eps = 1e-12f;
+      launch_gemm(ctx, EPI_NORM_BIAS_F16, h16, L.wqkv, T, 3 * H, H, p, ref);
+      e->attention(qkv, o16, ns, T, ps.max_len, -1);
+      GemmEpiParams r;
+      r.M = T; r.out16 = h16; r.out8_lo = xl8; r.ld16 = H; r.ln_eps = 1e-12f;
+      r.gamma = L.ra_g; r.bias = L.ra_b; r.stats_in = st[cur]; r.stats_out = st[cur ^ 1];
+      launch_gemm(ctx, EPI_RESID_STATS_LN, o16, L.wo, T, H, H, r, ref);
+      cur ^= 1;
+      GemmEpiParams f;
+      f.M = T; f.out16 = f16; f.ld16 = I; f.bias = L.ci; f.stats_in = st[cur]; f.ln_eps = 1e-12f;
+      launch_gemm(ctx, EPI_NORM_BIAS_GELU_F16, h16, L.wi, T, I, H, f, ref);
+      r.gamma = L.rb_g; r.bias = L.rb_b; r.stats_in = st[cur]; r.stats_out = st[cur ^ 1];
+      launch_gemm(ctx, EPI_RESID_STATS_LN, f16, L.wo2, T, H, I, r, ref);
+      cur ^= 1;
+    }
+    const auto& last = e->bl.back();
+    launch_layernorm_hilo(ctx, h16, xl8, T, last.g2, last.b2, 1e-12f, x32, h16);
+    return;
+  }
   launch_bert_embed_ln(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
                        e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16);
   for (int i = 0; i < e->layers; ++i) {
@@ -420,6 +500,10 @@ extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int 
   e->legacy_attention = leg && leg[0] == '1';
   const char* dl = getenv("VRAG_DEFERRED_LN");   // "0": separate LayerNorm kernels (cross-check path)
   e->deferred_ln = !(dl && dl[0] == '0');
+  if (kind != VRAG_ENC_MODERNBERT_TOKCLS) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=1 opts in until validated on the GPU
+    const char* bd = getenv("VRAG_BERT_DEFERRED_LN");
+    e->deferred_ln = e->deferred_ln && bd && bd[0] == '1';
+  }
   WeightSet w(tensors, num_tensors);
   if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
   else build_bert(e.get(), w);

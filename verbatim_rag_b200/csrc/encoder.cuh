@@ -24,8 +24,12 @@ void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, i
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
                      float eps, float* x32, __half* h16, uint8_t* lo8);
 // Two-plane residual stream (x = fp16 hi + e5m2 lo, deferred-LayerNorm path): final LayerNorm, fp32 reconstruction.
-void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma, float eps,
-                           __half* h16);
+void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma,
+                           const float* beta /*nullable*/, float eps, float* x32 /*nullable*/, __half* h16);
+// BERT deferred-LayerNorm path: raw embedding sum as the two-plane stream + row moments ([slots][T] float2, slot 0).
+void launch_bert_embed_raw(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
+                           const float* word_emb, const float* pos_emb, const float* type_emb0, __half* h16,
+                           uint8_t* lo8, float* stats, int slots);
 void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32);
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,

@@ -27,7 +27,9 @@ constexpr int EPI_LO_BOX_BYTES = 2048;                        // 32 rows x 64 e5
 constexpr int EPI_STATS_WARP_BYTES = 2 * (EPI_BOX_BYTES + EPI_LO_BOX_BYTES);
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter (each takes half of the tile's columns): one warp per
                               // scheduler cannot hide its own ALU / TMEM-load latency, two can
-constexpr int epi_warp_bytes(int epi) { return epi == EPI_RESID_STATS ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES; }
+constexpr int epi_warp_bytes(int epi) {
+  return (epi == EPI_RESID_STATS || epi == EPI_RESID_STATS_LN) ? EPI_STATS_WARP_BYTES : EPI_WARP_BYTES;
+}
 constexpr int smem_bytes(int stages, int epi) {
   return stages * STAGE_BYTES + EPI_WARPS * epi_warp_bytes(epi) + 1024 /*align slack*/ + 512 /*barriers*/;
 }
@@ -54,6 +56,24 @@ __device__ __forceinline__ float row_rstd(const GemmEpiParams& p, int row) {
   const float var = fmaxf(q * p.inv_dim - mean * mean, 0.f);
   return rsqrtf(var + p.ln_eps);
 }
+// mean and 1 / sqrt(var + eps) of row `row` from the same partial moments (EPI_RESID_STATS_LN normalises the old stream)
+__device__ __forceinline__ float2 row_mean_rstd(const GemmEpiParams& p, int row) {
+  if (row >= p.M) return make_float2(0.f, 0.f);
+  const float2* st = reinterpret_cast<const float2*>(p.stats_in);
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < p.stats_slots; ++j) {
+    const float2 v = __ldg(st + static_cast<size_t>(j) * p.M + row);
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * p.inv_dim;
+  const float var = fmaxf(q * p.inv_dim - mean * mean, 0.f);
+  return make_float2(mean, rsqrtf(var + p.ln_eps));
+}
+template <int EPI>
+constexpr bool kResidStats = (EPI == EPI_RESID_STATS || EPI == EPI_RESID_STATS_LN);
+template <int EPI>
+constexpr bool kNormBias = (EPI == EPI_NORM_BIAS_F16 || EPI == EPI_NORM_BIAS_GELU_F16);
 constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -143,10 +163,15 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
   const bool valid = row < p.M;
   const int col0 = n_tile * BN;
   float v[32];
-  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kNormBias<EPI>) {
+    const float rs = kNormBias<EPI> ? row_rstd(p, row) : 1.f;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
+      if constexpr (kNormBias<EPI>) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= rs;
+      }
       if constexpr (EPI != EPI_F16) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
 #pragma unroll
@@ -155,7 +180,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
           v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
       }
-      if constexpr (EPI == EPI_BIAS_GELU_F16) {
+      if constexpr (EPI == EPI_BIAS_GELU_F16 || EPI == EPI_NORM_BIAS_GELU_F16) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       }
@@ -193,8 +218,10 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         }
       }
     }
-  } else if constexpr (EPI == EPI_RESID_STATS) {
+  } else if constexpr (kResidStats<EPI>) {
     float s = 0.f, q = 0.f;
+    const float2 mr = EPI == EPI_RESID_STATS_LN ? row_mean_rstd(p, row) : make_float2(0.f, 1.f);
+    const float ra = mr.y, rb = -mr.x * mr.y;   // (x - mean) * rstd = x * ra + rb
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
@@ -203,7 +230,10 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         uint8_t* lp = p.out8_lo + static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = v[i] + (__half2float(hp[i]) + unpack_e5m2x2<0>(lp[i]).x);
+          float xo = __half2float(hp[i]) + unpack_e5m2x2<0>(lp[i]).x;
+          if constexpr (EPI == EPI_RESID_STATS_LN)
+            xo = fmaf(fmaf(xo, ra, rb), __ldg(p.gamma + col0 + c * 32 + i), __ldg(p.bias + col0 + c * 32 + i));
+          const float x = v[i] + xo;
           s += x;
           q = fmaf(x, x, q);
           const __half h = __float2half_rn(x);
@@ -317,7 +347,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 // double-buffered per warp; cp.async.bulk.wait_group.read gates buffer reuse.
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
-constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kRope<EPI> ||
+constexpr bool kStaged = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kNormBias<EPI> || kRope<EPI> ||
                           kGeglu<EPI> || EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32);
 
 struct BoxStager {
@@ -368,13 +398,18 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   const int col0 = n_tile * BN;
   const int r = lane;  // row of this thread inside the warp's 32-row slab
   float v[32];
-  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+  if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kNormBias<EPI>) {
+    const float rs = kNormBias<EPI> ? row_rstd(p, m0 + lane) : 1.f;
 #pragma unroll 1
     for (int b = 2 * half; b < 2 * half + 2; ++b) {
       uint8_t* box = st.acquire(lane);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         ld.load(2 * b + h, v);
+        if constexpr (kNormBias<EPI>) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rs;
+        }
         if constexpr (EPI != EPI_F16) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + (2 * b + h) * 32);
 #pragma unroll
@@ -383,7 +418,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
             v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
         }
-        if constexpr (EPI == EPI_BIAS_GELU_F16) {   // packed fp32x2 GeLU (gelu2: |error| <= 3.3e-7), 10 vs 35 issue slots
+        if constexpr (EPI == EPI_BIAS_GELU_F16 || EPI == EPI_NORM_BIAS_GELU_F16) {   // packed fp32x2 GeLU (gelu2: |error| <= 3.3e-7), 10 vs 35 issue slots
 #pragma unroll
           for (int i = 0; i < 16; ++i) f2_unpack(gelu2(f2_pack(v[2 * i], v[2 * i + 1])), v[2 * i], v[2 * i + 1]);
         }
@@ -703,7 +738,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* my_smem = epi_smem + (warp - 2) * EPI_WB;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if constexpr (EPI == EPI_RESID_STATS) {
+    if constexpr (kResidStats<EPI>) {
       // x = x_old + acc on the two-plane residual stream: the warp's steps (32 rows x 64 columns, two per tile) form
       // one flat stream across tiles; step n lives in buffer n & 1 = {hi box (fp16, SWIZZLE_128B), lo box (e5m2,
       // SWIZZLE_64B)} (TMA-loaded, updated in place, TMA-stored).  The loads of step n + 1 are issued while step n is
@@ -744,6 +779,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
         float sum = 0.f, sq = 0.f;
+        float ra = 1.f, rb = 0.f;   // EPI_RESID_STATS_LN: (x_old - mean) * rstd = x_old * ra + rb for this thread's row
+        if constexpr (EPI == EPI_RESID_STATS_LN) {
+          const float2 mr = row_mean_rstd(p, m_idx * BM + quarter * 32 + lane);
+          ra = mr.y;
+          rb = -mr.x * mr.y;
+        }
 #pragma unroll 1
         for (int stp = 0; stp < 2; ++stp, ++n) {
           uint8_t* hbox = my_smem + (n & 1) * EPI_BOX_BYTES;
@@ -780,14 +821,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint4 hv = *reinterpret_cast<const uint4*>(hbox + hoff);
               uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
               float d[8];
+              float gm[8], bt[8];   // EPI_RESID_STATS_LN: LayerNorm weight / (beta + dense bias) of these 8 columns
+              if constexpr (EPI == EPI_RESID_STATS_LN) {
+                const int gc = n_idx * BN + (2 * half + stp) * 64 + 8 * i;
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + gc));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + gc) + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + gc) + 1);
+                gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+                bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 ho = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
                 const uint32_t lword = lw[2 * hh + (e >> 1)];
                 const float2 lo = (e & 1) ? unpack_e5m2x2<1>(lword) : unpack_e5m2x2<0>(lword);
                 const int c = 8 * i + 2 * e;
-                const float x0 = __uint_as_float(c < 32 ? ta[c & 31] : tb[c & 31]) + (ho.x + lo.x);
-                const float x1 = __uint_as_float(c < 32 ? ta[(c + 1) & 31] : tb[(c + 1) & 31]) + (ho.y + lo.y);
+                float xo0 = ho.x + lo.x, xo1 = ho.y + lo.y;
+                if constexpr (EPI == EPI_RESID_STATS_LN) {
+                  xo0 = fmaf(fmaf(xo0, ra, rb), gm[2 * e], bt[2 * e]);
+                  xo1 = fmaf(fmaf(xo1, ra, rb), gm[2 * e + 1], bt[2 * e + 1]);
+                }
+                const float x0 = __uint_as_float(c < 32 ? ta[c & 31] : tb[c & 31]) + xo0;
+                const float x1 = __uint_as_float(c < 32 ? ta[(c + 1) & 31] : tb[(c + 1) & 31]) + xo1;
                 sum += x0;
                 sq = fmaf(x0, x0, sq);
                 sum += x1;
@@ -932,8 +988,11 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
       VRAG_CHECK(p.rope_tab && p.rope_rows > 0 && p.pos, VRAG_ERR_ARG, "gemm: RoPE epilogue needs rope_tab / pos");
       tmOut2 = make_tmap_2d(ctx, p.rope_tab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.rope_rows, 64, 64, 32, 32);
     }
-    if constexpr (EPI == EPI_RESID_STATS) {
+    if constexpr (kResidStats<EPI>) {
       VRAG_CHECK(p.out16 && p.out8_lo && p.stats_out, VRAG_ERR_ARG, "gemm: RESID_STATS needs out16 / out8_lo / stats_out");
+      if constexpr (EPI == EPI_RESID_STATS_LN)
+        VRAG_CHECK(p.gamma && p.bias && p.stats_in && p.stats_in != p.stats_out, VRAG_ERR_ARG,
+                   "gemm: RESID_STATS_LN needs gamma / bias and separate stats_in / stats_out buffers");
       tmOut = make_tmap_2d(ctx, p.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
       tmOut2 = make_tmap_2d(ctx, p.out8_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, p.ld16, p.ld16, 32, 64,
                             CU_TENSOR_MAP_SWIZZLE_64B);
@@ -972,6 +1031,9 @@ void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M
     VRAG_CASE(EPI_RESID_STATS)
     VRAG_CASE(EPI_NORM_ROPE_QKV)
     VRAG_CASE(EPI_NORM_GEGLU)
+    VRAG_CASE(EPI_NORM_BIAS_F16)
+    VRAG_CASE(EPI_NORM_BIAS_GELU_F16)
+    VRAG_CASE(EPI_RESID_STATS_LN)
 #undef VRAG_CASE
     default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
   }

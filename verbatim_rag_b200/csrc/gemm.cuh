@@ -28,6 +28,13 @@ enum GemmEpi : int {
                           // an fp16 low plane, the first version: 3 + 3 KB -- these two GEMMs are HBM-bound).
   EPI_NORM_ROPE_QKV = 12, // EPI_ROPE_QKV on rstd[row] * acc
   EPI_NORM_GEGLU = 13,    // EPI_GEGLU on rstd[row] * acc
+  // The same treatment of BERT's post-LN blocks, y = LN(z) * gamma + beta with z = y_prev + sublayer(y_prev): the
+  // stream holds the PRE-norm sum z (two planes + row moments); consumers read its hi plane against weights folded with
+  // gamma (and beta folded into their bias), the residual GEMM normalises the old stream on the fly.
+  EPI_NORM_BIAS_F16 = 14,       // out16 = rstd[row] * acc + bias                     (BERT q|k|v)
+  EPI_NORM_BIAS_GELU_F16 = 15,  // out16 = gelu(rstd[row] * acc + bias)               (BERT intermediate)
+  EPI_RESID_STATS_LN = 16,      // EPI_RESID_STATS with x_old = ((hi + lo) - mean[row]) * rstd[row] * gamma[col] + bias[col]
+                                // (bias = beta + the dense bias); reads stats_in, writes stats_out (different buffers)
 };
 
 struct GemmEpiParams {
@@ -37,6 +44,7 @@ struct GemmEpiParams {
   float* out32 = nullptr;
   int ld32 = 0;
   const float* bias = nullptr;
+  const float* gamma = nullptr;       // EPI_RESID_STATS_LN: LayerNorm weight applied to the old stream
   const int32_t* pos = nullptr;       // [M] position of each token inside its sequence
   const float* rope_tab = nullptr;    // [rope_rows, 64]: cos(pos * inv_freq[0..32)) | sin(pos * inv_freq[0..32))
   int rope_rows = 0;                  // positions in the table

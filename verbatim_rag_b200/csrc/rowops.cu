@@ -108,13 +108,13 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* 
 // LayerNorm of the two-plane residual stream (final norm of the deferred-LayerNorm path); h16 may alias hi.
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 layernorm_hilo_kernel(const __half* hi, const uint8_t* __restrict__ lo, int T, const float* __restrict__ gamma,
-                      float eps, __half* h16) {
+                      const float* __restrict__ beta, float eps, float* __restrict__ x32, __half* h16) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   float4 v[VEC];
   load_row_hilo(v, hi + static_cast<size_t>(row) * H, lo + static_cast<size_t>(row) * H, lane);
-  ln_row(v, gamma, nullptr, eps, lane);
-  store_row(v, nullptr, h16 + static_cast<size_t>(row) * H, lane);
+  ln_row(v, gamma, beta, eps, lane);
+  store_row(v, x32 ? x32 + static_cast<size_t>(row) * H : nullptr, h16 + static_cast<size_t>(row) * H, lane);
 }
 
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
@@ -148,6 +148,38 @@ bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict_
   }
   ln_row(v, gamma, beta, eps, lane);
   store_row(v, x32 + static_cast<size_t>(row) * H, h16 + static_cast<size_t>(row) * H, lane);
+}
+
+// Deferred-LayerNorm BERT path: z = word + position + type embedding, NOT normalised -- written as the two-plane
+// stream with its row moments (slot 0 = (sum z, sum z^2), slots 1..5 = 0); the embedding LayerNorm is folded into the
+// first layer's GEMMs like every other LayerNorm of the stack.
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
+bert_embed_raw_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int T, int vocab, int max_pos,
+                      const float* __restrict__ wemb, const float* __restrict__ pemb, const float* __restrict__ temb0,
+                      __half* __restrict__ h16, uint8_t* __restrict__ lo8, float* __restrict__ stats, int slots) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int p = pos[row];
+  p = p >= max_pos ? max_pos - 1 : p;
+  const float4* e = reinterpret_cast<const float4*>(wemb + static_cast<size_t>(id) * H);
+  const float4* pe = reinterpret_cast<const float4*>(pemb + static_cast<size_t>(p) * H);
+  const float4* te = reinterpret_cast<const float4*>(temb0);
+  float4 v[VEC];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 a = __ldg(e + i * 32 + lane), b = __ldg(pe + i * 32 + lane), c = __ldg(te + i * 32 + lane);
+    v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  store_row(v, nullptr, h16 + static_cast<size_t>(row) * H, lane, lo8 + static_cast<size_t>(row) * H);
+  if (lane < slots)
+    reinterpret_cast<float2*>(stats)[static_cast<size_t>(lane) * T + row] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
@@ -310,10 +342,19 @@ void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const 
                                                                            lo8);
   VRAG_LAUNCHED(ctx);
 }
-void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma, float eps,
-                           __half* h16) {
+void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma,
+                           const float* beta, float eps, float* x32, __half* h16) {
   ProfScope prof(ctx, PROF_ROWOPS);
-  layernorm_hilo_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(hi, lo, T, gamma, eps, h16);
+  layernorm_hilo_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(hi, lo, T, gamma, beta, eps, x32, h16);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_bert_embed_raw(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
+                           const float* word_emb, const float* pos_emb, const float* type_emb0, __half* h16,
+                           uint8_t* lo8, float* stats, int slots) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  bert_embed_raw_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
+                                                                                 pos_emb, type_emb0, h16, lo8, stats,
+                                                                                 slots);
   VRAG_LAUNCHED(ctx);
 }
 void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32) {
