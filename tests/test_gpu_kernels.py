@@ -9,7 +9,6 @@ import pytest
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
-BERT_DEFERRED = os.environ.get("VRAG_BERT_DEFERRED_LN") == "1"
 
 
 def _diag(**kw):
@@ -42,8 +41,6 @@ def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
     """TMA-store / TMA-reduce-add staged epilogues vs the direct thread-per-row epilogue of the reference kernel.
     Token positions in the self test: even M = sequences of 200 tokens (RoPE slabs fetch cos / sin by TMA, the ones
     straddling a sequence boundary gather), odd M = hashed positions (every slab gathers)."""
-    if epi >= 14 and not BERT_DEFERRED:
-        pytest.skip("BERT deferred-LayerNorm epilogues: opt-in (VRAG_BERT_DEFERRED_LN=1)")
     N, K = 2304, 768
     diff, ref_max = ctx.selftest_gemm(M, N, K, epi)
     _diag(test="gemm_epilogue_selftest", epilogue=name, M=M, max_abs_diff=diff, ref_abs_max=ref_max)
@@ -55,8 +52,6 @@ def test_tcgen05_fused_epilogues_match_simt_reference(ctx, epi, name, M):
 def test_residual_stats_ln_epilogue_bert_shapes(ctx, M, N, K):
     """BERT attention.output / output dense of the deferred-LayerNorm path: the old stream is normalised on the fly
     ((hi + lo - mean) * rstd * gamma + beta + bias) from moments in one buffer while the new moments go to another."""
-    if not BERT_DEFERRED:
-        pytest.skip("BERT deferred-LayerNorm epilogues: opt-in (VRAG_BERT_DEFERRED_LN=1)")
     diff, ref_max = ctx.selftest_gemm(M, N, K, 16)
     _diag(test="gemm_resid_stats_ln", M=M, N=N, K=K, max_abs_diff=diff, ref_abs_max=ref_max)
     assert diff <= 2e-3 * max(ref_max, 1.0), (diff, ref_max)
@@ -217,8 +212,12 @@ def test_span_forward_bench_shape_properties(ctx):
 
 
 # ------------------------------------------------------------------------------------------ SPLADE
-@pytest.mark.parametrize("use_ref_gemm,legacy_attn", [(True, True), (False, False)])
-def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
+@pytest.mark.parametrize("use_ref_gemm,legacy_attn,deferred_ln", [(True, True, True), (False, False, True),
+                                                                  (False, False, False)])
+def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, deferred_ln, monkeypatch):
+    """BERT-MLM + SPLADE head vs the fp32 oracle: the deferred-LayerNorm stack (two-plane pre-norm stream, LayerNorms
+    folded into the GEMMs) with the SIMT reference GEMM and with the tcgen05 GEMM, and the cross-check stack (fp32
+    stream by TMA reduce-add + LayerNorm kernels)."""
     from verbatim_rag_b200 import _native
     from verbatim_rag_b200.synthetic import BertSpec, make_bert_mlm_weights
     from oracle.bert_splade import splade_encode
@@ -232,6 +231,7 @@ def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
         seqs.append(s.astype(np.int64))
     monkeypatch.setenv("VRAG_GEMM_REFERENCE", "1" if use_ref_gemm else "0")
     monkeypatch.setenv("VRAG_ATTENTION_LEGACY", "1" if legacy_attn else "0")
+    monkeypatch.setenv("VRAG_BERT_DEFERRED_LN", "1" if deferred_ln else "0")
     enc = _native.Encoder(ctx, _native.ENC_BERT_MLM, w, spec.layers, spec.vocab_size, max_tokens=2048)
     ids, cu = _native.Encoder._pack(seqs)
     out = enc.splade_forward(ids, cu, min_abs=0.0, want_dense=True)
@@ -240,7 +240,7 @@ def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatch):
     err = np.abs(out["dense"] - ref)
     nnz_ref = (ref != 0).sum(axis=1)
     nnz_got = np.diff(out["indptr"])
-    _diag(test="splade_vs_oracle", use_ref_gemm=use_ref_gemm, max_err=float(err.max()), nnz_ref=nnz_ref.tolist(),
+    _diag(test="splade_vs_oracle", use_ref_gemm=use_ref_gemm, deferred_ln=deferred_ln, max_err=float(err.max()), nnz_ref=nnz_ref.tolist(),
           nnz_got=nnz_got.tolist(), ref_max=float(ref.max()))
     assert err.max() < 5e-3
     # CSR is exactly the non-zeros of the dense output, ascending indices

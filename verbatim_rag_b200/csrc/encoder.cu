@@ -25,7 +25,7 @@ struct vrag_encoder {
   int ffn = 0;  // GeGLU width (1152) or FFN width (3072)
   bool use_reference_gemm = false;
   bool legacy_attention = false;
-  bool deferred_ln = true;  // ModernBERT: LayerNorm folded into the GEMMs (EPI_RESID_STATS / EPI_NORM_*), no LN kernels
+  bool deferred_ln = true;  // LayerNorm folded into the GEMMs (EPI_RESID_STATS* / EPI_NORM_*), no LN kernels in the stack
   void attention(const __half* qkv, __half* out, int nseq, int total_tokens, int max_len, int window) {
     if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
     else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), work.as<int32_t>(), n_pairs, total_tokens, 12,
@@ -500,9 +500,9 @@ extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int 
   e->legacy_attention = leg && leg[0] == '1';
   const char* dl = getenv("VRAG_DEFERRED_LN");   // "0": separate LayerNorm kernels (cross-check path)
   e->deferred_ln = !(dl && dl[0] == '0');
-  if (kind != VRAG_ENC_MODERNBERT_TOKCLS) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=1 opts in until validated on the GPU
-    const char* bd = getenv("VRAG_BERT_DEFERRED_LN");
-    e->deferred_ln = e->deferred_ln && bd && bd[0] == '1';
+  if (kind != VRAG_ENC_MODERNBERT_TOKCLS) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=0 selects the cross-check path
+    const char* bd = getenv("VRAG_BERT_DEFERRED_LN");   // (fp32 stream by TMA reduce-add + LayerNorm kernels)
+    e->deferred_ln = e->deferred_ln && !(bd && bd[0] == '0');
   }
   WeightSet w(tensors, num_tensors);
   if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);

@@ -394,12 +394,13 @@ __device__ __forceinline__ void box_put_float32(uint8_t* box, int r, const float
 
 template <int EPI>
 __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st,
-                                                int m0, int n_tile, const TmemLoader& ld, int lane, int half) {
+                                                int m0, int n_tile, const TmemLoader& ld, int lane, int half,
+                                                float rs /* kNormBias: rstd of this thread's row, fetched by the caller
+                                                            before it waits for the accumulators */) {
   const int col0 = n_tile * BN;
   const int r = lane;  // row of this thread inside the warp's 32-row slab
   float v[32];
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kNormBias<EPI>) {
-    const float rs = kNormBias<EPI> ? row_rstd(p, m0 + lane) : 1.f;
 #pragma unroll 1
     for (int b = 2 * half; b < 2 * half + 2; ++b) {
       uint8_t* box = st.acquire(lane);
@@ -775,16 +776,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t n = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
         const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
-        mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-        float sum = 0.f, sq = 0.f;
         float ra = 1.f, rb = 0.f;   // EPI_RESID_STATS_LN: (x_old - mean) * rstd = x_old * ra + rb for this thread's row
-        if constexpr (EPI == EPI_RESID_STATS_LN) {
+        if constexpr (EPI == EPI_RESID_STATS_LN) {   // fetched before the accumulator wait
           const float2 mr = row_mean_rstd(p, m_idx * BM + quarter * 32 + lane);
           ra = mr.y;
           rb = -mr.x * mr.y;
         }
+        mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int stp = 0; stp < 2; ++stp, ++n) {
           uint8_t* hbox = my_smem + (n & 1) * EPI_BOX_BYTES;
@@ -908,13 +909,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else if constexpr (kRope<EPI>) rope_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, cs, sn, release);
           else geglu_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, release);
         } else {
+          float rs = 1.f;
+          if constexpr (kNormBias<EPI>) rs = row_rstd(p, m0 + lane);   // before the accumulator wait: latency hidden
           mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
           tc_fence_after();
           TmemLoader ld{taddr};
           if (p.debug_mode == 3) {
             // timing experiment: mainloop only
           } else if constexpr (kStaged<EPI>)
-            staged_epilogue<EPI>(p, &tmOut, stager, m0, n_idx, ld, lane, half);
+            staged_epilogue<EPI>(p, &tmOut, stager, m0, n_idx, ld, lane, half, rs);
           else
             epilogue_row<EPI>(p, m0 + lane, n_idx, ld, 4 * half, 4 * half + 4);
           release(lane);
