@@ -153,7 +153,13 @@ class B200SpanExtractor(SpanExtractor):
         q_enc = tk.tok.encode_batch(list(uq.keys()), add_special_tokens=False)
         for q, e in zip(uq.keys(), q_enc):
             uq[q] = np.asarray(e.ids, dtype=np.int32)
-        c_enc = tk.tok.encode_batch([c for _, c in pairs], add_special_tokens=False)
+        # every distinct context is tokenised once (popular chunks are retrieved for many questions of a batch)
+        uc: Dict[str, Any] = {}
+        for _, c in pairs:
+            if c not in uc:
+                uc[c] = None
+        for c, e in zip(uc.keys(), tk.tok.encode_batch(list(uc.keys()), add_special_tokens=False)):
+            uc[c] = (np.asarray(e.ids, dtype=np.int32), np.asarray(e.offsets, dtype=np.int32).reshape(-1, 2))
         cls_a, sep_a = np.asarray([tk.cls_id], np.int32), np.asarray([tk.sep_id], np.int32)
         chunks: List[np.ndarray] = []
         seq_len: List[int] = []
@@ -163,10 +169,9 @@ class B200SpanExtractor(SpanExtractor):
         ctx_ntok = np.zeros(len(pairs) + 1, dtype=np.int64)
         tok_cs: List[np.ndarray] = []
         tok_ce: List[np.ndarray] = []
-        for pi, ((q, _), ce) in enumerate(zip(pairs, c_enc)):
+        for pi, (q, c) in enumerate(pairs):
             qi = uq[q]
-            cids = np.asarray(ce.ids, dtype=np.int32)
-            off = np.asarray(ce.offsets, dtype=np.int32).reshape(-1, 2)
+            cids, off = uc[c]
             ctx_ntok[pi + 1] = ctx_ntok[pi] + len(cids)
             tok_cs.append(off[:, 0])
             tok_ce.append(off[:, 1])
