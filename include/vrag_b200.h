@@ -127,6 +127,11 @@ int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages
 int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, const int32_t* cu_seqlens, int nseq, int window,
                             int legacy, uint16_t* out_f16);
 
+/* Timing hook (development): `iters` back-to-back launches of the attention kernel on synthetic fp16 q|k|v rows
+ * (nseq sequences of seq_len tokens, 12 heads x 64; window as above), CUDA events on the library's stream.
+ * *ms_out = average launch time in milliseconds. */
+int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out);
+
 /* Debug hook (tests): vrag_span_forward with host buffers that also returns the fp32 residual stream after
  * the embedding and after every layer, hidden_out [num_layers + 1, total_tokens, 768]; single pass only. */
 int vrag_debug_span_hidden(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,

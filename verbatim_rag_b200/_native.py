@@ -24,7 +24,7 @@ POOL_MEAN, POOL_CLS = 0, 1
 EXPORTS = [
     "vrag_ctx_create", "vrag_ctx_destroy", "vrag_last_error", "vrag_sync", "vrag_stream", "vrag_launch_count",
     "vrag_version", "vrag_profile", "vrag_profile_read", "vrag_encoder_create", "vrag_encoder_destroy", "vrag_span_forward", "vrag_splade_forward",
-    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_bench_gemm", "vrag_selftest_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
+    "vrag_dense_forward", "vrag_selftest_gemm", "vrag_bench_gemm", "vrag_selftest_attention", "vrag_bench_attention", "vrag_debug_span_hidden", "vrag_spans_from_probs",
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
@@ -78,6 +78,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_selftest_gemm": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
             "vrag_bench_gemm": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, P(f64)]),
             "vrag_selftest_attention": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+            "vrag_bench_attention": (i32, [vp, i32, i32, i32, i32, vp]),
             "vrag_spans_from_probs": (i32, [vp, vp, vp, vp, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
             "vrag_index_create": (i32, [vp, i32, i32, P(vp)]),
             "vrag_index_destroy": (None, [vp]),
@@ -167,6 +168,12 @@ class Context:
         """Average launch time (ms) of one encoder GEMM shape on synthetic operands (CUDA events)."""
         ms = C.c_double()
         self.check(self.lib.vrag_bench_gemm(self.h, M, N, K, epilogue, stages, debug_mode, iters, C.byref(ms)))
+        return ms.value
+
+    def bench_attention(self, nseq: int, seq_len: int, window: int = -1, iters: int = 10) -> float:
+        """Average launch time (ms) of the attention kernel on synthetic rows (CUDA events)."""
+        ms = C.c_double()
+        self.check(self.lib.vrag_bench_attention(self.h, nseq, seq_len, window, iters, C.byref(ms)))
         return ms.value
 
     def selftest_attention(self, qkv_f16, cu_seqlens, window: int = -1, legacy: bool = False):

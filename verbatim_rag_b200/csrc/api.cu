@@ -466,6 +466,64 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Attention timing hook (development, tools/attn_probe.py): `iters` back-to-back launches of the tcgen05 attention
+// kernel on synthetic fp16 q|k|v rows (nseq sequences of seq_len tokens, 12 heads x 64), CUDA events on the
+// library's stream; *ms_out = average launch time.  window < 0: full attention, else keys with |i - j| <= window.
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out) {
+  if (!ctx || !ms_out || nseq < 1 || seq_len < 1 || iters < 1) return VRAG_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  try {
+    VRAG_CUDA(cudaSetDevice(ctx->device));
+    const size_t T = static_cast<size_t>(nseq) * seq_len;
+    VRAG_CHECK(T < (size_t(1) << 30), VRAG_ERR_ARG, "bench_attention: too many tokens");
+    std::vector<int32_t> cu(nseq + 1), work;
+    for (int i = 0; i <= nseq; ++i) cu[i] = i * seq_len;
+    for (int i = 0; i < nseq; ++i)
+      for (int q0 = 0; q0 < seq_len; q0 += 128) {
+        work.push_back(cu[i]);
+        work.push_back(seq_len);
+        work.push_back(q0);
+        work.push_back(0);
+      }
+    DevBuf QKV, OUT, CU, WORK;
+    QKV.reserve(T * 3 * HIDDEN * 2);
+    OUT.reserve(T * HIDDEN * 2);
+    CU.reserve(cu.size() * 4);
+    WORK.reserve(work.size() * 4);
+    cudaStream_t st = ctx->stream;
+    fill_half_kernel<<<blocks_for(T * 3 * HIDDEN), 256, 0, st>>>(QKV.as<__half>(), T * 3 * HIDDEN, 23u, 1.0f);
+    VRAG_CUDA(cudaMemcpyAsync(CU.p, cu.data(), cu.size() * 4, cudaMemcpyHostToDevice, st));
+    VRAG_CUDA(cudaMemcpyAsync(WORK.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, st));
+    auto launch = [&]() {
+      launch_attention_tc(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), WORK.as<int32_t>(),
+                          static_cast<int>(work.size() / 4), static_cast<int>(T), 12, HIDDEN, window);
+    };
+    cudaEvent_t e0, e1;
+    VRAG_CUDA(cudaEventCreate(&e0));
+    VRAG_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) launch();
+    VRAG_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) launch();
+    VRAG_CUDA(cudaEventRecord(e1, st));
+    VRAG_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    VRAG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (DevBuf* b : {&QKV, &OUT, &CU, &WORK}) b->release();
+    return VRAG_OK;
+  } catch (const Error& e) {
+    ctx->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->last_error = e.what();
+    return VRAG_ERR_INTERNAL;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Attention self test: runs one attention launch (tcgen05 kernel, or the mma.sync cross-check with legacy != 0) on
 // caller-supplied fp16 q|k|v rows, so tests can drive score ranges the encoder never produces (online-softmax
 // rescaling, ragged tails, local windows) against a float64 host computation.
