@@ -149,7 +149,7 @@ def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 24   # ~5-10 s of host work per step
+    sample = args.ref_sample   # ~5-10 s of host work per step
     rate, dt, cores = time_cpu(sample, args.steps, min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -453,6 +453,7 @@ def main():
     ap.add_argument("--seqs-per-step", type=int, default=SEQS_PER_STEP)
     ap.add_argument("--max-tokens", type=int, default=131072)  # pass-size sweep: profiles/README.md
     ap.add_argument("--cpu-sample", type=int, default=96)   # ~10-30 s of host work
+    ap.add_argument("--ref-sample", type=int, default=24)    # sequences per step of the --impl reference arm
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     args = ap.parse_args()
