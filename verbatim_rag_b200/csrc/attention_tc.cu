@@ -23,6 +23,8 @@
 // one phase ahead of the waiter.  q/k already carry RoPE (Wqkv GEMM epilogue).  On local layers only key blocks
 // intersecting |i - j| <= window are visited; blocks fully outside a warp's window skip TMEM.
 // Producer / MMA loops are warp-convergent with elect.sync around the TMA / MMA instructions (uniform datapath).
+#include <stdlib.h>
+
 #include "encoder.cuh"
 #include "ptx.cuh"
 
@@ -474,6 +476,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
                          const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden,
                          int window /* <0: full */) {
+  // opt-in experimental kernel (two query tiles per CTA, attention_tc2.cu): not validated yet, off by default
+  static const bool use_v2 = [] { const char* e = getenv("VRAG_ATTENTION_V2"); return e && e[0] == '1'; }();
+  if (use_v2) {
+    launch_attention_tc2(ctx, qkv, out, work_dev, n_pairs, total_tokens, heads, hidden, window);
+    return;
+  }
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   ProfScope prof(ctx, PROF_ATTENTION);
   CUtensorMap tmQ = make_tmap_2d(ctx, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AQ, AD);

@@ -16,6 +16,9 @@ void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32
 void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
                          const int32_t* work_dev /* [n_pairs][2] = (sequence, q0) */, int n_pairs, int total_tokens,
                          int heads, int hidden, int window);
+// Experimental two-tiles-per-CTA variant (attention_tc2.cu), selected by VRAG_ATTENTION_V2=1 inside launch_attention_tc.
+void launch_attention_tc2(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* work_dev, int n_pairs,
+                          int total_tokens, int heads, int hidden, int window);
 
 // rowops.cu  (one warp per token row, H = 768)
 void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, int total, int32_t* pos,
