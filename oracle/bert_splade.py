@@ -31,6 +31,34 @@ def _t(x) -> torch.Tensor:
 def bert_mlm_hidden(weights: Dict[str, np.ndarray], input_ids, attention_mask, spec=None,
                     emulate_fp16: bool = False) -> torch.Tensor:
     """MLM-head transform output [B, L, H] (input of the tied decoder)."""
+    return _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform=True)
+
+
+@torch.no_grad()
+def bert_encoder_hidden(weights: Dict[str, np.ndarray], input_ids, attention_mask, spec=None,
+                        emulate_fp16: bool = False) -> torch.Tensor:
+    """Final hidden states of the encoder stack [B, L, H] (transformers BertModel.last_hidden_state,
+    modeling_bert.py BertEncoder) -- the input of the sentence pooling of a dense embedding model."""
+    return _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform=False)
+
+
+@torch.no_grad()
+def dense_encode(weights, seqs: List[np.ndarray], spec=None, pooling: str = "mean", normalize: bool = True) -> np.ndarray:
+    """Sentence embeddings the way sentence-transformers composes them for BERT-architecture models (the reference's
+    SentenceTransformersProvider, embedding_providers.py:52-80): Transformer -> Pooling (mean over the attended tokens,
+    or the [CLS] token) -> Normalize (L2).  One sequence at a time, so no padding enters the mean.  -> [N, H] fp32."""
+    out = []
+    for s in seqs:
+        ids = np.asarray(s, dtype=np.int64)[None]
+        h = bert_encoder_hidden(weights, ids, np.ones_like(ids), spec)[0]
+        v = h.mean(dim=0) if pooling == "mean" else h[0]
+        if normalize:
+            v = v / v.norm().clamp_min(1e-12)
+        out.append(v.numpy())
+    return np.stack(out).astype(np.float32)
+
+
+def _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform) -> torch.Tensor:
     from verbatim_rag_b200.synthetic import BertSpec
 
     spec = spec or BertSpec()
@@ -69,6 +97,8 @@ def bert_mlm_hidden(weights: Dict[str, np.ndarray], input_ids, attention_mask, s
         f = F.gelu(lin(x, weights[p + "intermediate.dense.weight"], weights[p + "intermediate.dense.bias"]))
         x = ln(x + lin(f, weights[p + "output.dense.weight"], weights[p + "output.dense.bias"]),
                p + "output.LayerNorm")
+    if not mlm_transform:
+        return x
     c = "cls.predictions."
     t = F.gelu(lin(x, weights[c + "transform.dense.weight"], weights[c + "transform.dense.bias"]))
     return ln(t, c + "transform.LayerNorm")

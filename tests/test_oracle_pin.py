@@ -62,3 +62,29 @@ def test_bert_mlm_matches_transformers():
     hid = bert_mlm_hidden(w, ids, am, spec)
     got = splade_pool(w, hid, am)
     assert np.abs(got - ref).max() < 2e-4
+
+
+def test_bert_dense_encode_matches_transformers():
+    """oracle.bert_splade.dense_encode (encoder -> mean / CLS pooling -> L2 normalise) against transformers' BertModel
+    last_hidden_state pooled the way sentence-transformers' Pooling + Normalize modules do."""
+    from transformers import BertConfig, BertModel
+    from oracle.bert_splade import dense_encode
+
+    spec = BertSpec(layers=2, vocab_size=3000)
+    w = make_bert_mlm_weights(12, spec)
+    cfg = BertConfig(vocab_size=spec.vocab_size, num_hidden_layers=spec.layers, attn_implementation="eager")
+    m = BertModel(cfg, add_pooling_layer=False).eval()
+    sd = {k[len("bert."):]: torch.from_numpy(v) for k, v in w.items() if k.startswith("bert.")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in k for k in missing), missing
+    rng = np.random.default_rng(2)
+    seqs = [rng.integers(1000, 3000, size=n) for n in (48, 7, 1, 130)]
+    for pooling in ("mean", "cls"):
+        got = dense_encode(w, seqs, spec, pooling=pooling, normalize=True)
+        for s, g in zip(seqs, got):
+            with torch.no_grad():
+                h = m(input_ids=torch.from_numpy(np.asarray(s, dtype=np.int64))[None]).last_hidden_state[0]
+            v = h.mean(dim=0) if pooling == "mean" else h[0]
+            v = torch.nn.functional.normalize(v, dim=0)
+            assert np.abs(g - v.numpy()).max() < 2e-5, pooling
