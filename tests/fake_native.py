@@ -47,6 +47,10 @@ class FakeEncoder:
             out["dense"] = dense
         return out
 
+    def dense_forward(self, ids, cu, pooling=0, normalize=True):
+        return bert_splade.dense_encode(self.weights, self._split(ids, cu), self.spec,
+                                        pooling="mean" if pooling == 0 else "cls", normalize=bool(normalize))
+
     def close(self):
         pass
 
