@@ -322,11 +322,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint64_t l2 = 0ull;
       const int k_lo = LOCAL ? max(q - window, 0) : 0;
       const int k_hi = LOCAL ? min(q + window, it.L - 1) : it.L - 1;
-      const int nbt = it.t_hi[tile] - it.t_lo[tile];   // key blocks of this tile
+      const int my_lo = tile == 0 ? it.t_lo[0] : it.t_lo[1];   // (selects, not a runtime index: keeps Item2 in registers)
+      const int my_hi = tile == 0 ? it.t_hi[0] : it.t_hi[1];
+      const int nbt = my_hi - my_lo;                            // key blocks of this tile
 
       for (int i = 0; i < nbt; ++i) {
         const uint32_t G = kt + i;
-        const int key0 = (it.t_lo[tile] + i) * AK;
+        const int key0 = (my_lo + i) * AK;
         const int e_lo = k_lo - key0, e_hi = k_hi - key0;  // valid local columns
         const bool dead = __all_sync(0xffffffffu, e_hi < 0 || e_lo > AK - 1);
         mbar_wait_tagged(my_s_full, G & 1, 4);
