@@ -87,6 +87,18 @@ int vrag_profile_read(vrag_ctx* ctx, double* ms_per_class, int64_t* launches_per
  * max_tokens bounds the tokens processed per internal pass (workspace size). */
 int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
                         const vrag_tensor* tensors, int num_tensors, vrag_encoder** out);
+/* Same with an arithmetic mode.  The reference runs these models in fp32 (extractors.py:151-157 loads with
+ * AutoModel.from_pretrained and only moves to the device: no autocast).
+ *   VRAG_PRECISION_FAST    fp16 tensor-core operands (11-bit significands), fp32 accumulation: span logits within
+ *                          ~3.5e-3 of the fp32 reference, identical spans except at tokens within that distance of
+ *                          the threshold.
+ *   VRAG_PRECISION_PRECISE every weight / activation as two fp16 planes x = hi + lo (>= 21 significant bits), each
+ *                          product as three tcgen05.mma (a_hi w_hi + a_lo w_hi + a_hi w_lo), fp32 residual stream:
+ *                          span logits within 1e-3 (measured ~1e-4) at roughly a third of the throughput. */
+#define VRAG_PRECISION_FAST 0
+#define VRAG_PRECISION_PRECISE 1
+int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
+                           const vrag_tensor* tensors, int num_tensors, int precision, vrag_encoder** out);
 void vrag_encoder_destroy(vrag_encoder* enc);
 
 /* Token-classification forward over `nseq` unpadded sequences packed back to back:
@@ -113,12 +125,20 @@ int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_
  * an in-library SIMT reference GEMM on random data and return the max |diff| (device-side self check). */
 int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff, double* ref_abs_max);
 
+/* Same self check in split-precision mode (VRAG_PRECISION_PRECISE): random hi / lo planes of both operands, three MMAs
+ * per product; fp16 outputs are compared as hi + lo sums.  Epilogues 10, 0, 1, 2, 3. */
+int vrag_selftest_gemm_split(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff,
+                             double* ref_abs_max);
+
 /* Timing hook (bench.py's per-kernel table, development): `iters` back-to-back launches of one encoder GEMM shape
  * (epilogue numbering of csrc/gemm.cuh) on synthetic device operands, CUDA events on the library's stream.
  * stages: operand ring depth 3..5 (0 = the context's default); debug_mode 3 skips the epilogue (mainloop only).
  * *ms_out = average launch time in milliseconds. */
 int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
                     double* ms_out);
+
+/* Split-precision variant of the timing hook (epilogues 0, 1, 2, 3). */
+int vrag_bench_gemm_split(vrag_ctx* ctx, int M, int N, int K, int epilogue, int iters, double* ms_out);
 
 /* Debug / test hook: one self-attention launch (12 heads x 64, as in both encoders; reference semantics:
  * transformers ModernBertAttention sdpa path -- softmax(q k^T / 8 + window mask) v per sequence) on caller-supplied
@@ -127,10 +147,16 @@ int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages
 int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, const int32_t* cu_seqlens, int nseq, int window,
                             int legacy, uint16_t* out_f16);
 
+/* Split-precision attention (VRAG_PRECISION_PRECISE): q|k|v rows and the output as hi / lo fp16 planes. */
+int vrag_selftest_attention_split(vrag_ctx* ctx, const uint16_t* qkv_hi_f16, const uint16_t* qkv_lo_f16,
+                                  const int32_t* cu_seqlens, int nseq, int window, uint16_t* out_hi_f16,
+                                  uint16_t* out_lo_f16);
+
 /* Timing hook (development): `iters` back-to-back launches of the attention kernel on synthetic fp16 q|k|v rows
  * (nseq sequences of seq_len tokens, 12 heads x 64; window as above), CUDA events on the library's stream.
  * *ms_out = average launch time in milliseconds. */
 int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out);
+int vrag_bench_attention_split(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out);
 
 /* Debug hook (tests): vrag_span_forward with host buffers that also returns the fp32 residual stream after
  * the embedding and after every layer, hidden_out [num_layers + 1, total_tokens, 768]; single pass only. */

@@ -19,6 +19,8 @@ VRAG_OK, VRAG_ERR_CUDA, VRAG_ERR_ARG, VRAG_ERR_CAPACITY, VRAG_ERR_WEIGHTS, VRAG_
 ENC_MODERNBERT_TOKCLS, ENC_BERT_MLM, ENC_BERT_DENSE = 0, 1, 2
 INDEX_DENSE_COSINE, INDEX_SPARSE_IP = 0, 1
 POOL_MEAN, POOL_CLS = 0, 1
+PRECISION_FAST, PRECISION_PRECISE = 0, 1
+PRECISIONS = {"fast": PRECISION_FAST, "precise": PRECISION_PRECISE}
 
 # every symbol include/vrag_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
@@ -28,6 +30,8 @@ EXPORTS = [
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
+    "vrag_encoder_create_ex", "vrag_selftest_gemm_split", "vrag_bench_gemm_split", "vrag_selftest_attention_split",
+    "vrag_bench_attention_split",
 ]
 
 
@@ -70,7 +74,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_profile": (i32, [vp, i32]),
             "vrag_profile_read": (i32, [vp, P(f64), P(i64)]),
             "vrag_encoder_create": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, P(vp)]),
+            "vrag_encoder_create_ex": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, i32, P(vp)]),
             "vrag_encoder_destroy": (None, [vp]),
+            "vrag_selftest_gemm_split": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
+            "vrag_bench_gemm_split": (i32, [vp, i32, i32, i32, i32, i32, P(f64)]),
+            "vrag_selftest_attention_split": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
+            "vrag_bench_attention_split": (i32, [vp, i32, i32, i32, i32, vp]),
             "vrag_span_forward": (i32, [vp, vp, vp, i32, vp, vp, i32]),
             "vrag_debug_span_hidden": (i32, [vp, vp, vp, i32, vp, vp, vp]),
             "vrag_splade_forward": (i32, [vp, vp, vp, i32, f32, vp, vp, vp, i64, P(i64), vp, i32]),
@@ -163,6 +172,37 @@ class Context:
         self.check(self.lib.vrag_selftest_gemm(self.h, M, N, K, epilogue, C.byref(d), C.byref(m)))
         return d.value, m.value
 
+    def selftest_gemm_split(self, M: int, N: int, K: int, epilogue: int = 10) -> Tuple[float, float]:
+        """Split-precision GEMM (hi / lo planes, three MMAs per product) vs the SIMT reference; fp16 outputs are
+        compared as hi + lo sums.  Epilogues 10, 0, 1, 2, 3."""
+        d, m = C.c_double(), C.c_double()
+        self.check(self.lib.vrag_selftest_gemm_split(self.h, M, N, K, epilogue, C.byref(d), C.byref(m)))
+        return d.value, m.value
+
+    def bench_gemm_split(self, M: int, N: int, K: int, epilogue: int, iters: int = 10) -> float:
+        ms = C.c_double()
+        self.check(self.lib.vrag_bench_gemm_split(self.h, M, N, K, epilogue, iters, C.byref(ms)))
+        return ms.value
+
+    def bench_attention_split(self, nseq: int, seq_len: int, window: int = -1, iters: int = 10) -> float:
+        ms = C.c_double()
+        self.check(self.lib.vrag_bench_attention_split(self.h, nseq, seq_len, window, iters, C.byref(ms)))
+        return ms.value
+
+    def selftest_attention_split(self, qkv_f32, cu_seqlens, window: int = -1):
+        """One split-precision attention launch on fp32 rows qkv [T, 2304] (split into hi / lo fp16 planes here);
+        returns the fp32 sum of the output planes [T, 768]."""
+        x = np.ascontiguousarray(qkv_f32, dtype=np.float32)
+        hi = x.astype(np.float16)
+        lo = (x - hi.astype(np.float32)).astype(np.float16)
+        cu = np.ascontiguousarray(cu_seqlens, dtype=np.int32)
+        assert x.ndim == 2 and x.shape[1] == 2304 and x.shape[0] == int(cu[-1])
+        oh = np.empty((x.shape[0], 768), dtype=np.float16)
+        ol = np.empty((x.shape[0], 768), dtype=np.float16)
+        self.check(self.lib.vrag_selftest_attention_split(self.h, hi.ctypes.data, lo.ctypes.data, cu.ctypes.data,
+                                                          len(cu) - 1, int(window), oh.ctypes.data, ol.ctypes.data))
+        return oh.astype(np.float32) + ol.astype(np.float32)
+
     def bench_gemm(self, M: int, N: int, K: int, epilogue: int, stages: int = 0, debug_mode: int = 0,
                    iters: int = 10) -> float:
         """Average launch time (ms) of one encoder GEMM shape on synthetic operands (CUDA events)."""
@@ -217,9 +257,14 @@ def default_context(device: int = 0) -> Context:
 
 class Encoder:
     def __init__(self, ctx: Context, kind: int, weights: Dict[str, np.ndarray], num_layers: int, vocab_size: int,
-                 max_tokens: int = 65536):
+                 max_tokens: int = 65536, precision: str = "fast"):
+        """precision: "fast" = fp16 tensor-core operands (logits within ~3.5e-3 of the fp32 reference);
+        "precise" = split-precision operands, three MMAs per product (logits within 1e-3, ~3x the time)."""
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
         self.ctx = ctx
         self.kind = kind
+        self.precision = precision
         keep = []
         arr = (_Tensor * len(weights))()
         for i, (name, w) in enumerate(weights.items()):
@@ -229,8 +274,8 @@ class Encoder:
             arr[i].data = a.ctypes.data
             arr[i].numel = a.size
         h = C.c_void_p()
-        ctx.check(ctx.lib.vrag_encoder_create(ctx.h, kind, num_layers, vocab_size, max_tokens, arr, len(weights),
-                                              C.byref(h)))
+        ctx.check(ctx.lib.vrag_encoder_create_ex(ctx.h, kind, num_layers, vocab_size, max_tokens, arr, len(weights),
+                                                 PRECISIONS[precision], C.byref(h)))
         self.h = h
         self.num_layers = num_layers
         self.vocab_size = vocab_size

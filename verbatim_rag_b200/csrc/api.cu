@@ -256,6 +256,21 @@ __global__ void diff_hilo_kernel(const __half* h0, const uint8_t* l0, const __ha
   }
   atomicMax(reinterpret_cast<int*>(out), __float_as_int(d));
 }
+// max |(h0 + l0) - (h1 + l1)| and max |h1 + l1| over two fp16 plane pairs (split-precision outputs)
+__global__ void diff_split_kernel(const __half* h0, const __half* l0, const __half* h1, const __half* l1, size_t n,
+                                  float* out /*[2]*/) {
+  float d = 0.f, m = 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float a = __half2float(h0[i]) + __half2float(l0[i]), b = __half2float(h1[i]) + __half2float(l1[i]);
+    float x = fabsf(a - b);
+    if (!(x == x)) x = INFINITY;
+    d = fmaxf(d, x);
+    m = fmaxf(m, fabsf(b));
+  }
+  atomicMax(reinterpret_cast<int*>(out), __float_as_int(d));
+  atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(m));
+}
 template <typename T>
 __global__ void diff_kernel(const T* a, const T* b, size_t n, float* out /*[2]: max diff, max |b|*/) {
   float d = 0.f, m = 0.f;
@@ -273,8 +288,20 @@ __global__ void diff_kernel(const T* a, const T* b, size_t n, float* out /*[2]: 
 inline unsigned blocks_for(size_t n) { return static_cast<unsigned>((n + 255) / 256); }
 }  // namespace
 
+static int selftest_gemm_impl(vrag_ctx* ctx, int M, int N, int K, int epilogue, bool split, double* max_abs_diff,
+                              double* ref_abs_max);
+
 extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff,
                                   double* ref_abs_max) {
+  return selftest_gemm_impl(ctx, M, N, K, epilogue, false, max_abs_diff, ref_abs_max);
+}
+extern "C" int vrag_selftest_gemm_split(vrag_ctx* ctx, int M, int N, int K, int epilogue, double* max_abs_diff,
+                                        double* ref_abs_max) {
+  return selftest_gemm_impl(ctx, M, N, K, epilogue, true, max_abs_diff, ref_abs_max);
+}
+
+static int selftest_gemm_impl(vrag_ctx* ctx, int M, int N, int K, int epilogue, bool split, double* max_abs_diff,
+                              double* ref_abs_max) {
   if (!ctx || !max_abs_diff) return VRAG_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
@@ -288,13 +315,15 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
                    norm_bias,
                VRAG_ERR_ARG, "selftest_gemm: epilogue must be one of 10, 0, 1, 2, 3, 11, 12, 13, 14, 15, 16");
     VRAG_CHECK(!rope || N % 192 == 0, VRAG_ERR_ARG, "selftest_gemm: ROPE needs N = 3 * hidden");
+    VRAG_CHECK(!split || !(stats || norm_bias || epilogue == EPI_NORM_ROPE_QKV || epilogue == EPI_NORM_GEGLU),
+               VRAG_ERR_ARG, "selftest_gemm_split: epilogue must be one of 10, 0, 1, 2, 3");
     const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
     const size_t out_bytes = out_n * (f32_out ? 4 : 2);
     const int max_pos = 512;
     const int slots = N / 128;   // EPI_RESID_STATS writes one (sum, sumsq) pair per row and 128 columns
     const size_t st_pairs = static_cast<size_t>(M) * (stats ? slots : 6);
-    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS, SIN, BIAS, GAMMA;
+    DevBuf A, W, C0, C1, H0, H1, S0, S1, R, POS, CS, SIN, BIAS, GAMMA, AL, WL;
     SIN.reserve(static_cast<size_t>(M) * 6 * 8);
     BIAS.reserve(static_cast<size_t>(N) * 4);
     GAMMA.reserve(static_cast<size_t>(N) * 4);
@@ -312,6 +341,12 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     cudaStream_t st = ctx->stream;
     fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(A.as<__half>(), static_cast<size_t>(M) * K, 17u, 1.0f);
     fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(W.as<__half>(), static_cast<size_t>(N) * K, 91u, 0.05f);
+    if (split) {   // low planes: remainders of the size a real hi / lo split produces (|lo| <= ulp(hi) / 2)
+      AL.reserve(static_cast<size_t>(M) * K * 2);
+      WL.reserve(static_cast<size_t>(N) * K * 2);
+      fill_half_kernel<<<blocks_for(static_cast<size_t>(M) * K), 256, 0, st>>>(AL.as<__half>(), static_cast<size_t>(M) * K, 29u, 1.0f / 2048.0f);
+      fill_half_kernel<<<blocks_for(static_cast<size_t>(N) * K), 256, 0, st>>>(WL.as<__half>(), static_cast<size_t>(N) * K, 57u, 0.05f / 2048.0f);
+    }
     // positions: runs of consecutive positions (sequences of 200 tokens: slabs of 32 rows that straddle a boundary take
     // the gather path, the others the TMA path), or hashed positions (pos_mode 1: every slab gathers)
     fill_pos_kernel<<<blocks_for(M), 256, 0, st>>>(POS.as<int32_t>(), M, max_pos, (M % 2) ? 1 : 0);
@@ -326,6 +361,10 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     } else {
       VRAG_CUDA(cudaMemsetAsync(C0.p, 0xff, out_bytes, st));  // NaN pattern: unwritten outputs are detected
       VRAG_CUDA(cudaMemsetAsync(C1.p, 0, out_bytes, st));
+      if (split) {
+        VRAG_CUDA(cudaMemsetAsync(H0.p, 0xff, out_n * 2, st));
+        VRAG_CUDA(cudaMemsetAsync(H1.p, 0, out_n * 2, st));
+      }
     }
     fill_float_kernel<<<blocks_for(N), 256, 0, st>>>(BIAS.as<float>(), N, 71u, 0.5f);
     fill_float_kernel<<<blocks_for(N), 256, 0, st>>>(GAMMA.as<float>(), N, 72u, 1.0f);
@@ -344,6 +383,11 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       p.out32 = (ref ? C1 : C0).as<float>();
       p.out16 = (ref ? C1 : C0).as<__half>();
       p.out8_lo = (ref ? H1 : H0).as<uint8_t>();
+      if (split) {
+        p.a_lo = AL.as<__half>();
+        p.w_lo = WL.as<__half>();
+        p.out16_lo = (ref ? H1 : H0).as<__half>();
+      }
       p.pos = POS.as<int32_t>(); p.rope_tab = CS.as<float>(); p.rope_rows = max_pos;
       p.hidden = N / 3;
       p.stats_in = stats ? SIN.as<float>() : S0.as<float>();   // EPI_RESID_STATS_LN reads the old moments, writes new ones
@@ -354,6 +398,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
       launch_gemm(ctx, epilogue, A.as<__half>(), W.as<__half>(), M, N, K, p, ref);
     }
     if (f32_out) diff_kernel<float><<<256, 256, 0, st>>>(C0.as<float>(), C1.as<float>(), out_n, R.as<float>());
+    else if (split) diff_split_kernel<<<256, 256, 0, st>>>(C0.as<__half>(), H0.as<__half>(), C1.as<__half>(), H1.as<__half>(), out_n, R.as<float>());
     else diff_kernel<__half><<<256, 256, 0, st>>>(C0.as<__half>(), C1.as<__half>(), out_n, R.as<float>());
     float h[2], hs[2] = {0.f, 0.f};
     VRAG_CUDA(cudaMemcpyAsync(h, R.p, 8, cudaMemcpyDeviceToHost, st));
@@ -378,7 +423,7 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
     }
     *max_abs_diff = std::isnan(h[0]) ? INFINITY : h[0];
     if (ref_abs_max) *ref_abs_max = h[1];
-    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS, &SIN, &BIAS, &GAMMA}) b->release();
+    for (DevBuf* b : {&A, &W, &C0, &C1, &H0, &H1, &S0, &S1, &R, &POS, &CS, &SIN, &BIAS, &GAMMA, &AL, &WL}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();
@@ -391,8 +436,17 @@ extern "C" int vrag_selftest_gemm(vrag_ctx* ctx, int M, int N, int K, int epilog
 
 // GEMM timing hook (development / bench.py's per-kernel table): `iters` back-to-back launches of one encoder GEMM
 // shape on synthetic operands, CUDA events on the library's stream; *ms_out = average launch time.
+static int bench_gemm_impl(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
+                           bool split, double* ms_out);
 extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
                                double* ms_out) {
+  return bench_gemm_impl(ctx, M, N, K, epilogue, stages, debug_mode, iters, false, ms_out);
+}
+extern "C" int vrag_bench_gemm_split(vrag_ctx* ctx, int M, int N, int K, int epilogue, int iters, double* ms_out) {
+  return bench_gemm_impl(ctx, M, N, K, epilogue, 0, 0, iters, true, ms_out);
+}
+static int bench_gemm_impl(vrag_ctx* ctx, int M, int N, int K, int epilogue, int stages, int debug_mode, int iters,
+                           bool split, double* ms_out) {
   if (!ctx || !ms_out || iters < 1) return VRAG_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   const int saved_stages = ctx->gemm_stages;
@@ -407,9 +461,11 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     const int out_cols = geglu ? N / 2 : N;
     const size_t out_n = static_cast<size_t>(M) * out_cols;
     const int max_pos = 512;
+    VRAG_CHECK(!split || epilogue == EPI_F16 || epilogue == EPI_ROPE_QKV || epilogue == EPI_RESID_F32 ||
+                   epilogue == EPI_GEGLU, VRAG_ERR_ARG, "bench_gemm_split: unsupported epilogue");
     DevBuf A, W, C, C16, POS, CS, ST;
-    A.reserve(static_cast<size_t>(M) * K * 2);
-    W.reserve(static_cast<size_t>(N) * K * 2);
+    A.reserve(static_cast<size_t>(M) * K * 2 * (split ? 2 : 1));   // split: the lo plane follows the hi plane
+    W.reserve(static_cast<size_t>(N) * K * 2 * (split ? 2 : 1));
     C.reserve(out_n * (f32_out ? 4 : 2));
     C16.reserve(out_n * 2);
     POS.reserve(static_cast<size_t>(M) * 4);
@@ -437,6 +493,13 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
     if (epilogue == EPI_RESID_STATS_LN) p.stats_out = ST.as<float>() + static_cast<size_t>(M) * 12;
     p.bias = CS.as<float>(); p.gamma = CS.as<float>() + 4096;   // any finite per-column vectors (N <= 4096)
     p.debug_mode = debug_mode;
+    if (split) {
+      VRAG_CUDA(cudaMemsetAsync(A.as<__half>() + static_cast<size_t>(M) * K, 0, static_cast<size_t>(M) * K * 2, st));
+      VRAG_CUDA(cudaMemsetAsync(W.as<__half>() + static_cast<size_t>(N) * K, 0, static_cast<size_t>(N) * K * 2, st));
+      p.a_lo = A.as<__half>() + static_cast<size_t>(M) * K;
+      p.w_lo = W.as<__half>() + static_cast<size_t>(N) * K;
+      p.out16_lo = C16.as<__half>();
+    }
     if (stages >= 3 && stages <= 5) ctx->gemm_stages = stages;
     cudaEvent_t e0, e1;
     VRAG_CUDA(cudaEventCreate(&e0));
@@ -470,7 +533,14 @@ extern "C" int vrag_bench_gemm(vrag_ctx* ctx, int M, int N, int K, int epilogue,
 // kernel on synthetic fp16 q|k|v rows (nseq sequences of seq_len tokens, 12 heads x 64), CUDA events on the
 // library's stream; *ms_out = average launch time.  window < 0: full attention, else keys with |i - j| <= window.
 // ------------------------------------------------------------------------------------------------
+static int bench_attention_impl(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, bool split, double* ms_out);
 extern "C" int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out) {
+  return bench_attention_impl(ctx, nseq, seq_len, window, iters, false, ms_out);
+}
+extern "C" int vrag_bench_attention_split(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, double* ms_out) {
+  return bench_attention_impl(ctx, nseq, seq_len, window, iters, true, ms_out);
+}
+static int bench_attention_impl(vrag_ctx* ctx, int nseq, int seq_len, int window, int iters, bool split, double* ms_out) {
   if (!ctx || !ms_out || nseq < 1 || seq_len < 1 || iters < 1) return VRAG_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
@@ -487,17 +557,25 @@ extern "C" int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int wi
         work.push_back(0);
       }
     DevBuf QKV, OUT, CU, WORK;
-    QKV.reserve(T * 3 * HIDDEN * 2);
-    OUT.reserve(T * HIDDEN * 2);
+    QKV.reserve(T * 3 * HIDDEN * 2 * (split ? 2 : 1));   // split: the lo plane follows the hi plane
+    OUT.reserve(T * HIDDEN * 2 * (split ? 2 : 1));
     CU.reserve(cu.size() * 4);
     WORK.reserve(work.size() * 4);
     cudaStream_t st = ctx->stream;
     fill_half_kernel<<<blocks_for(T * 3 * HIDDEN), 256, 0, st>>>(QKV.as<__half>(), T * 3 * HIDDEN, 23u, 1.0f);
+    if (split)
+      fill_half_kernel<<<blocks_for(T * 3 * HIDDEN), 256, 0, st>>>(QKV.as<__half>() + T * 3 * HIDDEN, T * 3 * HIDDEN, 41u,
+                                                                    1.0f / 2048.0f);
     VRAG_CUDA(cudaMemcpyAsync(CU.p, cu.data(), cu.size() * 4, cudaMemcpyHostToDevice, st));
     VRAG_CUDA(cudaMemcpyAsync(WORK.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, st));
     auto launch = [&]() {
-      launch_attention_tc(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), WORK.as<int32_t>(),
-                          static_cast<int>(work.size() / 4), static_cast<int>(T), 12, HIDDEN, window);
+      if (split)
+        launch_attention_tc_split(ctx, QKV.as<__half>(), QKV.as<__half>() + T * 3 * HIDDEN, OUT.as<__half>(),
+                                  OUT.as<__half>() + T * HIDDEN, WORK.as<int32_t>(), static_cast<int>(work.size() / 4),
+                                  static_cast<int>(T), 12, HIDDEN, window);
+      else
+        launch_attention_tc(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), WORK.as<int32_t>(),
+                            static_cast<int>(work.size() / 4), static_cast<int>(T), 12, HIDDEN, window);
     };
     cudaEvent_t e0, e1;
     VRAG_CUDA(cudaEventCreate(&e0));
@@ -528,9 +606,24 @@ extern "C" int vrag_bench_attention(vrag_ctx* ctx, int nseq, int seq_len, int wi
 // caller-supplied fp16 q|k|v rows, so tests can drive score ranges the encoder never produces (online-softmax
 // rescaling, ragged tails, local windows) against a float64 host computation.
 // ------------------------------------------------------------------------------------------------
+static int selftest_attention_impl(vrag_ctx* ctx, const uint16_t* qkv_f16, const uint16_t* qkv_lo_f16,
+                                   const int32_t* cu_seqlens, int nseq, int window, int legacy, uint16_t* out_f16,
+                                   uint16_t* out_lo_f16);
 extern "C" int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, const int32_t* cu_seqlens, int nseq,
                                        int window, int legacy, uint16_t* out_f16) {
+  return selftest_attention_impl(ctx, qkv_f16, nullptr, cu_seqlens, nseq, window, legacy, out_f16, nullptr);
+}
+extern "C" int vrag_selftest_attention_split(vrag_ctx* ctx, const uint16_t* qkv_hi_f16, const uint16_t* qkv_lo_f16,
+                                             const int32_t* cu_seqlens, int nseq, int window, uint16_t* out_hi_f16,
+                                             uint16_t* out_lo_f16) {
+  if (!qkv_lo_f16 || !out_lo_f16) return VRAG_ERR_ARG;
+  return selftest_attention_impl(ctx, qkv_hi_f16, qkv_lo_f16, cu_seqlens, nseq, window, 0, out_hi_f16, out_lo_f16);
+}
+static int selftest_attention_impl(vrag_ctx* ctx, const uint16_t* qkv_f16, const uint16_t* qkv_lo_f16,
+                                   const int32_t* cu_seqlens, int nseq, int window, int legacy, uint16_t* out_f16,
+                                   uint16_t* out_lo_f16) {
   if (!ctx || !qkv_f16 || !cu_seqlens || !out_f16 || nseq < 1) return VRAG_ERR_ARG;
+  const bool split = qkv_lo_f16 != nullptr;
   std::lock_guard<std::mutex> lk(ctx->mu);
   try {
     VRAG_CUDA(cudaSetDevice(ctx->device));
@@ -549,9 +642,13 @@ extern "C" int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, c
         work.push_back(0);
       }
     }
-    DevBuf QKV, OUT, CU, WORK;
+    DevBuf QKV, OUT, CU, WORK, QKVL, OUTL;
     QKV.reserve(static_cast<size_t>(T) * 3 * HIDDEN * 2);
     OUT.reserve(static_cast<size_t>(T) * HIDDEN * 2);
+    if (split) {
+      QKVL.reserve(static_cast<size_t>(T) * 3 * HIDDEN * 2);
+      OUTL.reserve(static_cast<size_t>(T) * HIDDEN * 2);
+    }
     CU.reserve(static_cast<size_t>(nseq + 1) * 4);
     WORK.reserve(work.size() * 4);
     cudaStream_t st = ctx->stream;
@@ -559,14 +656,20 @@ extern "C" int vrag_selftest_attention(vrag_ctx* ctx, const uint16_t* qkv_f16, c
     VRAG_CUDA(cudaMemcpyAsync(CU.p, cu_seqlens, static_cast<size_t>(nseq + 1) * 4, cudaMemcpyHostToDevice, st));
     VRAG_CUDA(cudaMemcpyAsync(WORK.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, st));
     VRAG_CUDA(cudaMemsetAsync(OUT.p, 0xff, static_cast<size_t>(T) * HIDDEN * 2, st));  // NaN pattern
-    if (legacy)
+    if (split) {
+      VRAG_CUDA(cudaMemcpyAsync(QKVL.p, qkv_lo_f16, static_cast<size_t>(T) * 3 * HIDDEN * 2, cudaMemcpyHostToDevice, st));
+      VRAG_CUDA(cudaMemsetAsync(OUTL.p, 0xff, static_cast<size_t>(T) * HIDDEN * 2, st));
+      launch_attention_tc_split(ctx, QKV.as<__half>(), QKVL.as<__half>(), OUT.as<__half>(), OUTL.as<__half>(),
+                                WORK.as<int32_t>(), static_cast<int>(work.size() / 4), T, 12, HIDDEN, window);
+      VRAG_CUDA(cudaMemcpyAsync(out_lo_f16, OUTL.p, static_cast<size_t>(T) * HIDDEN * 2, cudaMemcpyDeviceToHost, st));
+    } else if (legacy)
       launch_attention(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), nseq, max_len, 12, HIDDEN, window);
     else
       launch_attention_tc(ctx, QKV.as<__half>(), OUT.as<__half>(), CU.as<int32_t>(), WORK.as<int32_t>(),
                           static_cast<int>(work.size() / 4), T, 12, HIDDEN, window);
     VRAG_CUDA(cudaMemcpyAsync(out_f16, OUT.p, static_cast<size_t>(T) * HIDDEN * 2, cudaMemcpyDeviceToHost, st));
     VRAG_CUDA(cudaStreamSynchronize(st));
-    for (DevBuf* b : {&QKV, &OUT, &CU, &WORK}) b->release();
+    for (DevBuf* b : {&QKV, &OUT, &CU, &WORK, &QKVL, &OUTL}) b->release();
     return VRAG_OK;
   } catch (const Error& e) {
     ctx->last_error = e.what();

@@ -25,6 +25,8 @@
 // Producer / MMA loops are warp-convergent with elect.sync around the TMA / MMA instructions (uniform datapath).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "encoder.cuh"
 #include "ptx.cuh"
 
@@ -43,8 +45,19 @@ constexpr uint32_t ATT_TMEM_COLS = 128;  // S [0,64)  O [64,128)
 constexpr int SQ_BYTES = AQ * AD * 2;    // 16384
 constexpr int SKV_BYTES = AK * AD * 2;   // 8192
 constexpr int SP_BYTES = AQ * AK * 2;    // 16384
-constexpr int ATT_SMEM = SQ_BYTES + (KS + VS) * SKV_BYTES + SP_BYTES + 1024 + 256;
+// SPLIT (split-precision / "precise" mode, gemm.cuh): every tile exists twice, hi plane then lo plane
+template <bool SPLIT>
+constexpr int att_smem() { return (SPLIT ? 2 : 1) * (SQ_BYTES + (KS + VS) * SKV_BYTES + SP_BYTES) + 1024 + 256; }
 constexpr float RESCALE_THRESHOLD = 8.f; // log2 units
+
+// split-precision planes of two values: hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -102,19 +115,24 @@ __device__ __forceinline__ Item read_item(const int4* info, uint32_t it_n, int w
   return make_item<LOCAL>(e, window);
 }
 
-template <bool LOCAL>
-__global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
+// SPLIT: q | k | v, P and the output are pairs of fp16 planes (x = hi + lo); S = Q_hi K_hi + Q_lo K_hi + Q_hi K_lo and
+// O += P_hi V_hi + P_lo V_hi + P_hi V_lo (three MMAs per k-step); 144 KB of shared memory -> one CTA per SM.
+template <bool LOCAL, bool SPLIT>
+__global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : ATT_CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    __half* __restrict__ out,
+                    const __grid_constant__ CUtensorMap tmQlo, const __grid_constant__ CUtensorMap tmKVlo,
+                    __half* __restrict__ out, __half* __restrict__ out_lo,
                     const int4* __restrict__ work, int n_pairs, int heads, int hidden, float scale_log2e,
                     int window) {
+  constexpr int PL = SPLIT ? 2 : 1;            // planes per tile
+  constexpr int SQ_SLOT = PL * SQ_BYTES, SKV_SLOT = PL * SKV_BYTES, SP_SLOT = PL * SP_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // 16 KB
-  uint8_t* sK = sQ + SQ_BYTES;                 // K ring: slot s at sK + s*8192
-  uint8_t* sV = sK + KS * SKV_BYTES;           // V ring: slot s at sV + s*8192
-  uint8_t* sP = sV + VS * SKV_BYTES;           // 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + SP_BYTES);
+  uint8_t* sQ = smem;                          // 16 KB (per plane)
+  uint8_t* sK = sQ + SQ_SLOT;                  // K ring: slot s at sK + s * SKV_SLOT (hi plane, then lo plane)
+  uint8_t* sV = sK + KS * SKV_SLOT;            // V ring: slot s at sV + s * SKV_SLOT
+  uint8_t* sP = sV + VS * SKV_SLOT;            // 16 KB (per plane)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + SP_SLOT);
   uint64_t* q_full = bars;                   // 1
   uint64_t* q_empty = q_full + 1;            // 1
   uint64_t* k_full = q_empty + 1;            // [KS]
@@ -154,6 +172,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    if constexpr (SPLIT) {
+      tma_prefetch_desc(&tmQlo);
+      tma_prefetch_desc(&tmKVlo);
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_holder, ATT_TMEM_COLS);
@@ -186,8 +208,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(info + (it_n & 1))), "r"(entry.x),
                      "r"(entry.y), "r"(entry.z), "r"(entry.w)
                      : "memory");  // released by the arrive below
-        mbar_arrive_expect_tx(q_full, SQ_BYTES);
+        mbar_arrive_expect_tx(q_full, SQ_SLOT);
         tma_load_2d(sQ, &tmQ, q_full, it.head * AD, it.s0 + it.q0);
+        if constexpr (SPLIT) tma_load_2d(sQ + SQ_BYTES, &tmQlo, q_full, it.head * AD, it.s0 + it.q0);
       }
       __syncwarp();
       // K runs one block ahead of V in issue order (K_g, V_{g-1}, K_{g+1}, V_g, ...): a full V ring never holds back
@@ -197,8 +220,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait_tagged(k_empty + ks, ((g / KS) & 1) ^ 1, 3);
         const int row = it.s0 + (it.j_lo + i) * AK;
         if (elect_one()) {
-          mbar_arrive_expect_tx(k_full + ks, SKV_BYTES);
-          tma_load_2d(sK + ks * SKV_BYTES, &tmKV, k_full + ks, hidden + it.head * AD, row);
+          mbar_arrive_expect_tx(k_full + ks, SKV_SLOT);
+          tma_load_2d(sK + ks * SKV_SLOT, &tmKV, k_full + ks, hidden + it.head * AD, row);
+          if constexpr (SPLIT) tma_load_2d(sK + ks * SKV_SLOT + SKV_BYTES, &tmKVlo, k_full + ks, hidden + it.head * AD, row);
         }
         __syncwarp();
         if (g > 0) {   // V of the previous block of the flat stream
@@ -206,8 +230,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int vs = gv % VS;
           mbar_wait_tagged(v_empty + vs, ((gv / VS) & 1) ^ 1, 10);
           if (elect_one()) {
-            mbar_arrive_expect_tx(v_full + vs, SKV_BYTES);
-            tma_load_2d(sV + vs * SKV_BYTES, &tmKV, v_full + vs, v_col, v_row);
+            mbar_arrive_expect_tx(v_full + vs, SKV_SLOT);
+            tma_load_2d(sV + vs * SKV_SLOT, &tmKV, v_full + vs, v_col, v_row);
+            if constexpr (SPLIT) tma_load_2d(sV + vs * SKV_SLOT + SKV_BYTES, &tmKVlo, v_full + vs, v_col, v_row);
           }
           __syncwarp();
         }
@@ -223,8 +248,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int vs = gv % VS;
       mbar_wait_tagged(v_empty + vs, ((gv / VS) & 1) ^ 1, 10);
       if (elect_one()) {
-        mbar_arrive_expect_tx(v_full + vs, SKV_BYTES);
-        tma_load_2d(sV + vs * SKV_BYTES, &tmKV, v_full + vs, v_col, v_row);
+        mbar_arrive_expect_tx(v_full + vs, SKV_SLOT);
+        tma_load_2d(sV + vs * SKV_SLOT, &tmKV, v_full + vs, v_col, v_row);
+        if constexpr (SPLIT) tma_load_2d(sV + vs * SKV_SLOT + SKV_BYTES, &tmKVlo, v_full + vs, v_col, v_row);
       }
       __syncwarp();
     }
@@ -240,12 +266,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait_tagged(k_full + ks, (G / KS) & 1, 2);
       mbar_wait_tagged(s_empty, (G & 1) ^ 1, 5);  // the softmax warps hold S_{G-1} in registers
       tc_fence_after();
-      const uint32_t k_addr = k_base + ks * SKV_BYTES;
+      const uint32_t k_addr = k_base + ks * SKV_SLOT;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AD / 16; ++k)
+        for (int k = 0; k < AD / 16; ++k) {
           umma_f16(tmem_base, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s,
                    k > 0 ? 1u : 0u);
+          if constexpr (SPLIT) {
+            umma_f16(tmem_base, umma_desc_sw128(q_addr + SQ_BYTES + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s, 1u);
+            umma_f16(tmem_base, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + SKV_BYTES + k * 32), idesc_s, 1u);
+          }
+        }
         umma_commit(s_full);
         umma_commit(k_empty + ks);                // the K slot is free once this S has completed
         if (last) umma_commit(q_empty);  // the Q tile is free once this item's last S has completed
@@ -274,12 +305,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait_tagged(v_full + vs, (G / VS) & 1, 11);
         mbar_wait_tagged(p_full, G & 1, 6);
         tc_fence_after();
-        const uint32_t v_addr = v_base + vs * SKV_BYTES;
+        const uint32_t v_addr = v_base + vs * SKV_SLOT;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AK / 16; ++k)  // 16 keys per step = two 8-row groups of the V tile = 2048 bytes
+          for (int k = 0; k < AK / 16; ++k) {  // 16 keys per step = two 8-row groups of the V tile = 2048 bytes
             umma_f16(tmem_o, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128(v_addr + k * 2048), idesc_pv,
                      (i > 0 || k > 0) ? 1u : 0u);  // first block of the item overwrites O
+            if constexpr (SPLIT) {
+              umma_f16(tmem_o, umma_desc_sw128(p_addr + SP_BYTES + k * 32), umma_desc_sw128(v_addr + k * 2048), idesc_pv, 1u);
+              umma_f16(tmem_o, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128(v_addr + SKV_BYTES + k * 2048), idesc_pv, 1u);
+            }
+          }
           umma_commit(pv_done);
           umma_commit(v_empty + vs);
         }
@@ -332,6 +368,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           st_p_chunk<5>(p_row_sw, 0u, 0u, 0u, 0u);
           st_p_chunk<6>(p_row_sw, 0u, 0u, 0u, 0u);
           st_p_chunk<7>(p_row_sw, 0u, 0u, 0u, 0u);
+          if constexpr (SPLIT) {
+            st_p_chunk<0>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<1>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<2>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<3>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<4>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<5>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<6>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+            st_p_chunk<7>(p_row_sw + SP_BYTES, 0u, 0u, 0u, 0u);
+          }
         } else {
           float s[AK];
           {
@@ -415,8 +461,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               if (e & 1) sum2b = f2_add(sum2b, f2_pack(pe[2 * e], pe[2 * e + 1]));
               else sum2 = f2_add(sum2, f2_pack(pe[2 * e], pe[2 * e + 1]));
             }
-            st_p_chunk<c>(p_row_sw, pack_half2(pe[0], pe[1]), pack_half2(pe[2], pe[3]), pack_half2(pe[4], pe[5]),
-                          pack_half2(pe[6], pe[7]));
+            if constexpr (SPLIT) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_half2(pe[2 * e], pe[2 * e + 1], h[e], l[e]);
+              st_p_chunk<c>(p_row_sw, h[0], h[1], h[2], h[3]);
+              st_p_chunk<c>(p_row_sw + SP_BYTES, l[0], l[1], l[2], l[3]);
+            } else {
+              st_p_chunk<c>(p_row_sw, pack_half2(pe[0], pe[1]), pack_half2(pe[2], pe[3]), pack_half2(pe[4], pe[5]),
+                            pack_half2(pe[6], pe[7]));
+            }
           };
           chunk(IntC<0>{}); chunk(IntC<1>{}); chunk(IntC<2>{}); chunk(IntC<3>{});
           chunk(IntC<4>{}); chunk(IntC<5>{}); chunk(IntC<6>{}); chunk(IntC<7>{});
@@ -442,7 +496,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_wait();
         tc_fence_before();  // the next item's first PV overwrites O only after this warp's next p_full arrival
         if (q < it.L) {
-          uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(it.s0 + q) * hidden + it.head * AD);
+          const size_t o_off = static_cast<size_t>(it.s0 + q) * hidden + it.head * AD;
+          uint4* dst = reinterpret_cast<uint4*>(out + o_off);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t* t = c < 4 ? ta + 8 * c : tb + 8 * (c - 4);
@@ -450,10 +505,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 4; ++e) f2_unpack(f2_mul(f2_pack_bits(t[2 * e], t[2 * e + 1]), inv2), v[2 * e], v[2 * e + 1]);
             uint4 u;
-            u.x = pack_half2(v[0], v[1]);
-            u.y = pack_half2(v[2], v[3]);
-            u.z = pack_half2(v[4], v[5]);
-            u.w = pack_half2(v[6], v[7]);
+            if constexpr (SPLIT) {
+              uint4 l;
+              split_half2(v[0], v[1], u.x, l.x);
+              split_half2(v[2], v[3], u.y, l.y);
+              split_half2(v[4], v[5], u.z, l.z);
+              split_half2(v[6], v[7], u.w, l.w);
+              reinterpret_cast<uint4*>(out_lo + o_off)[c] = l;
+            } else {
+              u.x = pack_half2(v[0], v[1]);
+              u.y = pack_half2(v[2], v[3]);
+              u.z = pack_half2(v[4], v[5]);
+              u.w = pack_half2(v[6], v[7]);
+            }
             dst[c] = u;
           }
         }
@@ -473,38 +537,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 }  // namespace
 
-void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
-                         const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden,
-                         int window /* <0: full */) {
-  // opt-in experimental kernel (two query tiles per CTA, attention_tc2.cu): not validated yet, off by default
-  static const bool use_v2 = [] { const char* e = getenv("VRAG_ATTENTION_V2"); return e && e[0] == '1'; }();
-  if (use_v2) {
-    launch_attention_tc2(ctx, qkv, out, work_dev, n_pairs, total_tokens, heads, hidden, window);
-    return;
-  }
+namespace {
+template <bool SPLIT>
+void launch_attention_impl(vrag_ctx* ctx, const __half* qkv, const __half* qkv_lo, __half* out, __half* out_lo,
+                           const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden, int window) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   ProfScope prof(ctx, PROF_ATTENTION);
   CUtensorMap tmQ = make_tmap_2d(ctx, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AQ, AD);
   CUtensorMap tmKV = make_tmap_2d(ctx, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AK, AD);
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr_set = true;
+  CUtensorMap tmQlo = tmQ, tmKVlo = tmKV;
+  if (SPLIT) {
+    tmQlo = make_tmap_2d(ctx, qkv_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AQ, AD);
+    tmKVlo = make_tmap_2d(ctx, qkv_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, total_tokens, 3 * hidden, 3 * hidden, AK, AD);
+  }
+  constexpr int SMEM = att_smem<SPLIT>();
+  static std::atomic<uint64_t> attr_mask{0};   // cudaFuncSetAttribute is per device
+  const uint64_t bit = 1ull << (ctx->device & 63);
+  if ((attr_mask.fetch_or(bit) & bit) == 0) {
+    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VRAG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   }
   const int n_work = n_pairs * heads;
   if (n_work == 0) return;
   const int4* work4 = reinterpret_cast<const int4*>(work_dev);  // {s0, L, q0, -} per (sequence, query tile)
-  (void)cu_seqlens_dev;
-  const int grid = n_work < ATT_CTAS_PER_SM * ctx->num_sms ? n_work : ATT_CTAS_PER_SM * ctx->num_sms;
+  const int per_sm = SPLIT ? 1 : ATT_CTAS_PER_SM;
+  const int grid = n_work < per_sm * ctx->num_sms ? n_work : per_sm * ctx->num_sms;
   if (window >= 0)
-    attention_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tmQ, tmKV, out, work4, n_pairs, heads, hidden,
-                                                                            scale_log2e, window);
+    attention_tc_kernel<true, SPLIT><<<grid, ATT_THREADS, SMEM, ctx->stream>>>(tmQ, tmKV, tmQlo, tmKVlo, out, out_lo, work4,
+                                                                               n_pairs, heads, hidden, scale_log2e, window);
   else
-    attention_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tmQ, tmKV, out, work4, n_pairs, heads, hidden,
-                                                                             scale_log2e, 0);
+    attention_tc_kernel<false, SPLIT><<<grid, ATT_THREADS, SMEM, ctx->stream>>>(tmQ, tmKV, tmQlo, tmKVlo, out, out_lo, work4,
+                                                                                n_pairs, heads, hidden, scale_log2e, 0);
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
+}
+}  // namespace
+
+void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
+                         const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden,
+                         int window /* <0: full */) {
+  (void)cu_seqlens_dev;
+  launch_attention_impl<false>(ctx, qkv, nullptr, out, nullptr, work_dev, n_pairs, total_tokens, heads, hidden, window);
+}
+
+void launch_attention_tc_split(vrag_ctx* ctx, const __half* qkv, const __half* qkv_lo, __half* out, __half* out_lo,
+                               const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden,
+                               int window) {
+  VRAG_CHECK(qkv_lo && out_lo, VRAG_ERR_ARG, "attention: split precision needs the low planes");
+  launch_attention_impl<true>(ctx, qkv, qkv_lo, out, out_lo, work_dev, n_pairs, total_tokens, heads, hidden, window);
 }
 
 }  // namespace vrag

@@ -26,8 +26,14 @@ struct vrag_encoder {
   bool use_reference_gemm = false;
   bool legacy_attention = false;
   bool deferred_ln = true;  // LayerNorm folded into the GEMMs (EPI_RESID_STATS* / EPI_NORM_*), no LN kernels in the stack
+  // VRAG_PRECISION_PRECISE: split-precision operands (gemm.cuh): every fp16 weight / activation is a hi + lo pair of
+  // planes (>= 21 significant bits), three tcgen05.mma per product, fp32 residual stream and LayerNorm kernels.
+  bool precise = false;
   void attention(const __half* qkv, __half* out, int nseq, int total_tokens, int max_len, int window) {
-    if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
+    if (precise)
+      vrag::launch_attention_tc_split(ctx, qkv, qkv16_lo.as<__half>(), out, o16_lo.as<__half>(), work.as<int32_t>(),
+                                      n_pairs, total_tokens, 12, vrag::HIDDEN, window);
+    else if (legacy_attention) vrag::launch_attention(ctx, qkv, out, cu.as<int32_t>(), nseq, max_len, 12, vrag::HIDDEN, window);
     else vrag::launch_attention_tc(ctx, qkv, out, cu.as<int32_t>(), work.as<int32_t>(), n_pairs, total_tokens, 12,
                                    vrag::HIDDEN, window);
   }
@@ -35,10 +41,13 @@ struct vrag_encoder {
   // shared
   float *emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
   // ModernBERT
-  struct MLayer { float* attn_g; __half* wqkv; __half* wo; float* mlp_g; __half* wi; __half* wo2; };
+  struct MLayer {
+    float* attn_g; __half* wqkv; __half* wo; float* mlp_g; __half* wi; __half* wo2;
+    __half *wqkv_lo = nullptr, *wo_lo = nullptr, *wi_lo = nullptr, *wo2_lo = nullptr;   // precise mode: low planes
+  };
   std::vector<MLayer> ml;
   float *final_g = nullptr, *head_g = nullptr, *cls_w = nullptr, *cls_b = nullptr;
-  __half* head_w = nullptr;
+  __half *head_w = nullptr, *head_w_lo = nullptr;
   float *rope_g = nullptr, *rope_l = nullptr;  // [max_pos, 64] cos | sin tables (global / local theta)
   // BERT
   struct BLayer {
@@ -47,20 +56,22 @@ struct vrag_encoder {
     // deferred-LayerNorm path: folded biases of the consumer GEMMs (beta . W + b) and, for the two residual GEMMs, the
     // LayerNorm weight / (beta + dense bias) that normalise the OLD stream (the LayerNorm that precedes the sublayer)
     float *cqkv = nullptr, *ci = nullptr, *ra_g = nullptr, *ra_b = nullptr, *rb_g = nullptr, *rb_b = nullptr;
+    __half *wqkv_lo = nullptr, *wo_lo = nullptr, *wi_lo = nullptr, *wo2_lo = nullptr;   // precise mode: low planes
   };
   std::vector<BLayer> bl;
   float *pos_emb = nullptr, *type_emb = nullptr;
-  __half *mlm_w = nullptr, *dec_w = nullptr;
+  __half *mlm_w = nullptr, *dec_w = nullptr, *mlm_w_lo = nullptr, *dec_w_lo = nullptr;
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work, stats, stats2, xl8;
+      pooled, work, stats, stats2, xl8, h16_lo, qkv16_lo, o16_lo, w16_lo;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
-                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &stats2, &xl8})
+                      &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &stats2, &xl8, &h16_lo, &qkv16_lo,
+                      &o16_lo, &w16_lo})
       b->release();
   }
   template <typename T>
@@ -97,15 +108,23 @@ float* upload_f32(vrag_encoder* e, const float* host, size_t n, size_t n_alloc =
 }
 
 // fp32 host [rows, cols] -> fp16 device [rows_alloc, cols] (extra rows zero)
+// lo_out (precise mode): also allocate and fill the low plane fp16(w - fp16(w)).
 __half* upload_f16(vrag_encoder* e, DevBuf& staging, const float* host, size_t rows, size_t cols,
-                   size_t rows_alloc = 0) {
+                   size_t rows_alloc = 0, __half** lo_out = nullptr) {
   if (!rows_alloc) rows_alloc = rows;
+  const bool want_lo = lo_out && e->precise;
   __half* d = e->alloc<__half>(rows_alloc * cols);
-  if (rows_alloc > rows) VRAG_CUDA(cudaMemsetAsync(d, 0, rows_alloc * cols * sizeof(__half), e->ctx->stream));
+  __half* dl = want_lo ? e->alloc<__half>(rows_alloc * cols) : nullptr;
+  if (rows_alloc > rows) {
+    VRAG_CUDA(cudaMemsetAsync(d, 0, rows_alloc * cols * sizeof(__half), e->ctx->stream));
+    if (dl) VRAG_CUDA(cudaMemsetAsync(dl, 0, rows_alloc * cols * sizeof(__half), e->ctx->stream));
+  }
   staging.reserve(rows * cols * sizeof(float));
   VRAG_CUDA(cudaMemcpyAsync(staging.p, host, rows * cols * sizeof(float), cudaMemcpyHostToDevice, e->ctx->stream));
-  launch_f32_to_f16(e->ctx, staging.as<float>(), d, rows * cols);
+  if (dl) launch_f32_to_f16_split(e->ctx, staging.as<float>(), d, dl, rows * cols);
+  else launch_f32_to_f16(e->ctx, staging.as<float>(), d, rows * cols);
   VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // staging is reused by the next tensor
+  if (lo_out) *lo_out = dl;
   return d;
 }
 
@@ -166,8 +185,8 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
       fold_layernorm(wqkv, attn_g, 3 * H, H, folded.data());
       wqkv = folded.data();
     }
-    L.wqkv = upload_f16(e, staging, wqkv, 3 * H, H);
-    L.wo = upload_f16(e, staging, w.get(p + "attn.Wo.weight", (int64_t)H * H), H, H);
+    L.wqkv = upload_f16(e, staging, wqkv, 3 * H, H, 0, &L.wqkv_lo);
+    L.wo = upload_f16(e, staging, w.get(p + "attn.Wo.weight", (int64_t)H * H), H, H, 0, &L.wo_lo);
     L.mlp_g = upload_f32(e, mlp_g, H);
     // GeGLU: Wi = [input rows 0..I) | gate rows I..2I).  Interleave per 128 so one 256-wide GEMM tile holds
     // input[128t..128t+128) and gate[128t..128t+128) -> act(input)*gate is tile-local (EPI_GEGLU).
@@ -181,12 +200,12 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
       memcpy(&wi_perm[static_cast<size_t>(t * 256 + 128) * H], wi + static_cast<size_t>(I + t * 128) * H,
              sizeof(float) * 128 * H);
     }
-    L.wi = upload_f16(e, staging, wi_perm.data(), 2 * I, H);
-    L.wo2 = upload_f16(e, staging, w.get(p + "mlp.Wo.weight", (int64_t)H * I), H, I);
+    L.wi = upload_f16(e, staging, wi_perm.data(), 2 * I, H, 0, &L.wi_lo);
+    L.wo2 = upload_f16(e, staging, w.get(p + "mlp.Wo.weight", (int64_t)H * I), H, I, 0, &L.wo2_lo);
     e->ml.push_back(L);
   }
   e->final_g = upload_f32(e, w.get("model.final_norm.weight", H), H);
-  e->head_w = upload_f16(e, staging, w.get("head.dense.weight", (int64_t)H * H), H, H);
+  e->head_w = upload_f16(e, staging, w.get("head.dense.weight", (int64_t)H * H), H, H, 0, &e->head_w_lo);
   e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
   e->cls_w = upload_f32(e, w.get("classifier.weight", 2LL * H), 2 * H);
   e->cls_b = upload_f32(e, w.get("classifier.bias", 2), 2);
@@ -228,11 +247,11 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
       fold_layernorm(cat.data(), ga, 3 * H, H, folded.data());
       L.wqkv = upload_f16(e, staging, folded.data(), 3 * H, H);
     } else {
-      L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H);
+      L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H, 0, &L.wqkv_lo);
     }
     L.bqkv = upload_f32(e, bcat.data(), 3 * H);
     VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // bcat / cbias / folded reused next layer
-    L.wo = upload_f16(e, staging, w.get(p + "attention.output.dense.weight", (int64_t)H * H), H, H);
+    L.wo = upload_f16(e, staging, w.get(p + "attention.output.dense.weight", (int64_t)H * H), H, H, 0, &L.wo_lo);
     L.bo = upload_f32(e, w.get(p + "attention.output.dense.bias", H), H);
     L.g1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.weight", H), H);
     L.b1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.bias", H), H);
@@ -258,10 +277,10 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
       L.rb_b = upload_f32(e, t.data(), H);
       VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
     } else {
-      L.wi = upload_f16(e, staging, wi, I, H);
+      L.wi = upload_f16(e, staging, wi, I, H, 0, &L.wi_lo);
     }
     L.bi = upload_f32(e, bi, I);
-    L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I);
+    L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I, 0, &L.wo2_lo);
     L.bo2 = upload_f32(e, w.get(p + "output.dense.bias", H), H);
     L.g2 = upload_f32(e, w.get(p + "output.LayerNorm.weight", H), H);
     L.b2 = upload_f32(e, w.get(p + "output.LayerNorm.bias", H), H);
@@ -269,12 +288,12 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
   }
   if (e->kind == VRAG_ENC_BERT_MLM) {
     const std::string c = "cls.predictions.";
-    e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H);
+    e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H, 0, &e->mlm_w_lo);
     e->mlm_b = upload_f32(e, w.get(c + "transform.dense.bias", H), H);
     e->mlm_g = upload_f32(e, w.get(c + "transform.LayerNorm.weight", H), H);
     e->mlm_beta = upload_f32(e, w.get(c + "transform.LayerNorm.bias", H), H);
     // decoder is tied to the word embeddings (modeling_bert.py:471-511); pad the vocabulary to a tile multiple
-    e->dec_w = upload_f16(e, staging, wemb, e->vocab, H, e->vocab_pad);
+    e->dec_w = upload_f16(e, staging, wemb, e->vocab, H, e->vocab_pad, &e->dec_w_lo);
     e->dec_b = upload_f32(e, w.get(c + "bias", e->vocab), e->vocab, e->vocab_pad);
   }
   VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
@@ -295,6 +314,12 @@ void reserve_workspace(vrag_encoder* e) {
   e->buf32.reserve(T * H * 4);
   e->probs.reserve(T * 4);
   e->logits.reserve(T * 8);
+  if (e->precise) {
+    e->h16_lo.reserve(T * H * 2);
+    e->qkv16_lo.reserve(T * 3 * H * 2);
+    e->o16_lo.reserve(T * H * 2);
+    e->w16_lo.reserve(T * e->ffn * 2);
+  }
   if (e->deferred_ln) {
     e->stats.reserve(T * 6 * 8);
     e->xl8.reserve(T * H);
@@ -366,34 +391,45 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
   // h16 always holds the A operand of the next Wqkv / Wi GEMM: LN(x) (plain path), or the hi plane of the raw
   // residual stream (deferred LayerNorm: row moments in `stats`, gamma and the mean folded into the weights).
   float* stats = e->stats.as<float>();
+  // precise mode (dln is off): low planes of every fp16 activation; nullptr selects the plain fp16 kernels
+  const bool pr = e->precise;
+  __half* h16_lo = pr ? e->h16_lo.as<__half>() : nullptr;
+  __half* qkv_lo = pr ? e->qkv16_lo.as<__half>() : nullptr;
+  __half* o16_lo = pr ? e->o16_lo.as<__half>() : nullptr;
+  __half* g16_lo = pr ? e->w16_lo.as<__half>() : nullptr;
   launch_embed_ln(ctx, e->ids.as<int32_t>(), T, e->vocab, e->emb, e->emb_g, 1e-5f, dln ? nullptr : x32, h16,
-                  dln ? xl8 : nullptr);
+                  dln ? xl8 : nullptr, h16_lo);
   dump(0);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->ml[i];
     const bool global = (i % 3) == 0;
-    if (i > 0 && !dln) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false);
+    if (i > 0 && !dln) launch_layernorm(ctx, x32, T, L.attn_g, nullptr, 1e-5f, h16, false, h16_lo);
     GemmEpiParams p;
     p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.hidden = H; p.pos = e->pos.as<int32_t>();
     p.rope_tab = global ? e->rope_g : e->rope_l;
     p.rope_rows = e->max_pos;
     p.stats_in = stats;
+    p.a_lo = h16_lo; p.w_lo = pr ? L.wqkv_lo : nullptr; p.out16_lo = qkv_lo;
     launch_gemm(ctx, (dln && i > 0) ? EPI_NORM_ROPE_QKV : EPI_ROPE_QKV, h16, L.wqkv, T, 3 * H, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, global ? -1 : 64);
     GemmEpiParams r;
     r.M = T; r.out32 = x32; r.ld32 = H; r.out16 = h16; r.out8_lo = xl8; r.ld16 = H; r.stats_out = stats;
+    r.a_lo = o16_lo; r.w_lo = pr ? L.wo_lo : nullptr;
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, o16, L.wo, T, H, H, r, ref);
-    if (!dln) launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false);
+    if (!dln) launch_layernorm(ctx, x32, T, L.mlp_g, nullptr, 1e-5f, h16, false, h16_lo);
     GemmEpiParams g;
     g.M = T; g.out16 = g16; g.ld16 = I; g.stats_in = stats;
+    g.a_lo = h16_lo; g.w_lo = pr ? L.wi_lo : nullptr; g.out16_lo = g16_lo;
     launch_gemm(ctx, dln ? EPI_NORM_GEGLU : EPI_GEGLU, h16, L.wi, T, 2 * I, H, g, ref);
+    r.a_lo = g16_lo; r.w_lo = pr ? L.wo2_lo : nullptr;
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
     dump(i + 1);
   }
   if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, nullptr, 1e-5f, nullptr, h16);
-  else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false);
+  else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false, h16_lo);
   GemmEpiParams hd;
   hd.M = T; hd.out32 = e->buf32.as<float>(); hd.ld32 = H;
+  hd.a_lo = h16_lo; hd.w_lo = pr ? e->head_w_lo : nullptr;
   launch_gemm(ctx, EPI_GELU_F32, h16, e->head_w, T, H, H, hd, ref);
   launch_head_final(ctx, e->buf32.as<float>(), T, e->head_g, 1e-5f, e->cls_w, e->cls_b, e->logits.as<float>(),
                     e->probs.as<float>());
@@ -438,25 +474,35 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
     launch_layernorm_hilo(ctx, h16, xl8, T, last.g2, last.b2, 1e-12f, x32, h16);
     return;
   }
+  // precise mode: low planes of every fp16 activation (nullptr selects the plain fp16 kernels)
+  const bool pr = e->precise;
+  __half* h16_lo = pr ? e->h16_lo.as<__half>() : nullptr;
+  __half* qkv_lo = pr ? e->qkv16_lo.as<__half>() : nullptr;
+  __half* o16_lo = pr ? e->o16_lo.as<__half>() : nullptr;
+  __half* f16_lo = pr ? e->w16_lo.as<__half>() : nullptr;
   launch_bert_embed_ln(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
-                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16);
+                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16, h16_lo);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->bl[i];
     GemmEpiParams p;
     p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.bias = L.bqkv;
+    p.a_lo = h16_lo; p.w_lo = pr ? L.wqkv_lo : nullptr; p.out16_lo = qkv_lo;
     launch_gemm(ctx, EPI_BIAS_F16, h16, L.wqkv, T, 3 * H, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, -1);
     GemmEpiParams r;
     r.M = T; r.out32 = x32; r.ld32 = H; r.bias = L.bo;
+    r.a_lo = o16_lo; r.w_lo = pr ? L.wo_lo : nullptr;
     launch_gemm(ctx, EPI_BIAS_RESID_F32, o16, L.wo, T, H, H, r, ref);
-    launch_layernorm(ctx, x32, T, L.g1, L.b1, 1e-12f, h16, true);
+    launch_layernorm(ctx, x32, T, L.g1, L.b1, 1e-12f, h16, true, h16_lo);
     GemmEpiParams f;
     f.M = T; f.out16 = f16; f.ld16 = I; f.bias = L.bi;
+    f.a_lo = h16_lo; f.w_lo = pr ? L.wi_lo : nullptr; f.out16_lo = f16_lo;
     launch_gemm(ctx, EPI_BIAS_GELU_F16, h16, L.wi, T, I, H, f, ref);
     GemmEpiParams r2;
     r2.M = T; r2.out32 = x32; r2.ld32 = H; r2.bias = L.bo2;
+    r2.a_lo = f16_lo; r2.w_lo = pr ? L.wo2_lo : nullptr;
     launch_gemm(ctx, EPI_BIAS_RESID_F32, f16, L.wo2, T, H, I, r2, ref);
-    launch_layernorm(ctx, x32, T, L.g2, L.b2, 1e-12f, h16, true);
+    launch_layernorm(ctx, x32, T, L.g2, L.b2, 1e-12f, h16, true, h16_lo);
   }
 }
 
@@ -482,13 +528,22 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
 
 extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
                                    const vrag_tensor* tensors, int num_tensors, vrag_encoder** out) {
+  return vrag_encoder_create_ex(ctx, kind, num_layers, vocab_size, max_tokens, tensors, num_tensors, VRAG_PRECISION_FAST,
+                                out);
+}
+
+extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
+                                      const vrag_tensor* tensors, int num_tensors, int precision, vrag_encoder** out) {
   if (!ctx || !out) return VRAG_ERR_ARG;
   VRAG_API_BEGIN(ctx)
   VRAG_CHECK(kind >= 0 && kind <= 2 && num_layers > 0 && vocab_size > 0 && max_tokens >= 128, VRAG_ERR_ARG,
              "encoder_create: bad kind / num_layers / vocab_size / max_tokens");
+  VRAG_CHECK(precision == VRAG_PRECISION_FAST || precision == VRAG_PRECISION_PRECISE, VRAG_ERR_ARG,
+             "encoder_create: precision must be VRAG_PRECISION_FAST or VRAG_PRECISION_PRECISE");
   std::unique_ptr<vrag_encoder> e(new vrag_encoder());
   e->ctx = ctx;
   e->kind = kind;
+  e->precise = precision == VRAG_PRECISION_PRECISE;
   e->layers = num_layers;
   e->vocab = vocab_size;
   e->vocab_pad = (vocab_size + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
@@ -503,6 +558,10 @@ extern "C" int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int 
   if (kind != VRAG_ENC_MODERNBERT_TOKCLS) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=0 selects the cross-check path
     const char* bd = getenv("VRAG_BERT_DEFERRED_LN");   // (fp32 stream by TMA reduce-add + LayerNorm kernels)
     e->deferred_ln = e->deferred_ln && !(bd && bd[0] == '0');
+  }
+  if (e->precise) {   // fp32 residual stream + LayerNorm kernels; the split GEMMs have no deferred-LayerNorm epilogues
+    e->deferred_ln = false;
+    e->legacy_attention = false;
   }
   WeightSet w(tensors, num_tensors);
   if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
@@ -584,14 +643,18 @@ extern "C" int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const 
     stage_pass(enc, ps, ids, cu, on_device);
     bert_stack(enc, ps);
     GemmEpiParams t;
+    __half* h16_lo = enc->precise ? enc->h16_lo.as<__half>() : nullptr;
     t.M = T; t.out32 = enc->buf32.as<float>(); t.ld32 = H; t.bias = enc->mlm_b;
+    t.a_lo = h16_lo; t.w_lo = enc->precise ? enc->mlm_w_lo : nullptr;
     launch_gemm(_ctx, EPI_BIAS_GELU_F32, enc->h16.as<__half>(), enc->mlm_w, T, H, H, t, ref);
-    launch_layernorm(_ctx, enc->buf32.as<float>(), T, enc->mlm_g, enc->mlm_beta, 1e-12f, enc->h16.as<__half>(), false);
+    launch_layernorm(_ctx, enc->buf32.as<float>(), T, enc->mlm_g, enc->mlm_beta, 1e-12f, enc->h16.as<__half>(), false,
+                     h16_lo);
     enc->splade.reserve(static_cast<size_t>(ns) * VP * 4);
     VRAG_CUDA(cudaMemsetAsync(enc->splade.p, 0, static_cast<size_t>(ns) * VP * 4, _ctx->stream));
     GemmEpiParams sp;
     sp.M = T; sp.bias = enc->dec_b; sp.seq_of_row = enc->seqrow.as<int32_t>(); sp.splade_out = enc->splade.as<float>();
     sp.splade_ld = VP; sp.n_valid = V;
+    sp.a_lo = h16_lo; sp.w_lo = enc->precise ? enc->dec_w_lo : nullptr;
     launch_gemm(_ctx, EPI_SPLADE, enc->h16.as<__half>(), enc->dec_w, T, VP, H, sp, ref);
     if (dense_out)
       VRAG_CUDA(cudaMemcpy2DAsync(dense_out + static_cast<size_t>(ps.s0) * V, static_cast<size_t>(V) * 4, enc->splade.p,

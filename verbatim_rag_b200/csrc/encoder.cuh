@@ -16,16 +16,19 @@ void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32
 void launch_attention_tc(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev,
                          const int32_t* work_dev /* [n_pairs][2] = (sequence, q0) */, int n_pairs, int total_tokens,
                          int heads, int hidden, int window);
-// Experimental two-tiles-per-CTA variant (attention_tc2.cu), selected by VRAG_ATTENTION_V2=1 inside launch_attention_tc.
-void launch_attention_tc2(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* work_dev, int n_pairs,
-                          int total_tokens, int heads, int hidden, int window);
+// Split-precision ("precise") variant: q|k|v and the output as hi / lo fp16 planes (gemm.cuh), three tcgen05.mma per
+// product (S = Q_hi K_hi + Q_lo K_hi + Q_hi K_lo, O += P_hi V_hi + P_lo V_hi + P_hi V_lo).
+void launch_attention_tc_split(vrag_ctx* ctx, const __half* qkv, const __half* qkv_lo, __half* out, __half* out_lo,
+                               const int32_t* work_dev, int n_pairs, int total_tokens, int heads, int hidden, int window);
+void launch_f32_to_f16_split(vrag_ctx* ctx, const float* src, __half* hi, __half* lo, size_t n);
 
 // rowops.cu  (one warp per token row, H = 768)
 void launch_token_meta(vrag_ctx* ctx, const int32_t* cu_seqlens_dev, int nseq, int total, int32_t* pos,
                        int32_t* seq_of_row);
 // x32 (nullable) = LN(emb[ids]) * gamma, h16 = fp16 of it, lo8 (nullable) = e5m2 of the rounding remainder.
+// h16_lo (nullable): fp16 of the same remainder = low plane of the split-precision ("precise") mode.
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
-                     float eps, float* x32, __half* h16, uint8_t* lo8);
+                     float eps, float* x32, __half* h16, uint8_t* lo8, __half* h16_lo = nullptr);
 // Two-plane residual stream (x = fp16 hi + e5m2 lo, deferred-LayerNorm path): final LayerNorm, fp32 reconstruction.
 void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma,
                            const float* beta /*nullable*/, float eps, float* x32 /*nullable*/, __half* h16);
@@ -36,10 +39,11 @@ void launch_bert_embed_raw(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos
 void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32);
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
-                          const float* beta, float eps, float* x32, __half* h16);
+                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo = nullptr);
 // h16 = LN(x32) * gamma (+ beta); if write_back, x32 is overwritten with the normalised row too (post-LN residual).
+// h16_lo (nullable): low plane of h16 (split-precision mode).
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps,
-                      __half* h16, bool write_back);
+                      __half* h16, bool write_back, __half* h16_lo = nullptr);
 // ModernBERT head tail: LN(buf32) * gamma -> classifier (2 x 768) + bias -> logits, P(class 1).
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
                        const float* cls_b, float* logits /*nullable*/, float* probs);

@@ -6,6 +6,8 @@
 //                                 the memory system, the SM never reads x)
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Tiles are walked n-fastest so concurrently running CTAs share the same A rows (L2 reuse); W is L2 resident.
+#include <atomic>
+
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -122,6 +124,33 @@ __device__ __forceinline__ void store_half32(__half* dst, const float (&v)[32]) 
     d[i] = u;
   }
 }
+// Split-precision planes of two values: hi = fp16(x), lo = fp16(x - hi)  (gemm.cuh: "precise" mode)
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// hi plane -> dst, lo plane -> dst_lo (nullable: plain fp16 store)
+__device__ __forceinline__ void store_half32_split(__half* dst, __half* dst_lo, const float (&v)[32]) {
+  if (!dst_lo) {
+    store_half32(dst, v);
+    return;
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  uint4* dl = reinterpret_cast<uint4*>(dst_lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u, l;
+    split_half2(v[8 * i + 0], v[8 * i + 1], u.x, l.x);
+    split_half2(v[8 * i + 2], v[8 * i + 3], u.y, l.y);
+    split_half2(v[8 * i + 4], v[8 * i + 5], u.z, l.z);
+    split_half2(v[8 * i + 6], v[8 * i + 7], u.w, l.w);
+    d[i] = u;
+    dl[i] = l;
+  }
+}
 __device__ __forceinline__ void store_float32(float* dst, const float (&v)[32]) {
   float4* d = reinterpret_cast<float4*>(dst);
 #pragma unroll
@@ -143,13 +172,26 @@ struct ReferenceLoader {  // SIMT dot products (debug / self test)
   const __half* a_row;    // nullptr for rows >= M
   const __half* w_tile;   // W + n_tile*256*K
   int K;
+  const __half* a_lo_row = nullptr;   // split-precision mode: low planes (nullptr otherwise)
+  const __half* w_lo_tile = nullptr;
   __device__ __forceinline__ void load(int chunk, float (&v)[32]) const {
 #pragma unroll 1
     for (int j = 0; j < 32; ++j) {
       float acc = 0.f;
       if (a_row) {
         const __half* w = w_tile + static_cast<size_t>(chunk * 32 + j) * K;
-        for (int k = 0; k < K; ++k) acc = fmaf(__half2float(a_row[k]), __half2float(w[k]), acc);
+        if (a_lo_row && w_lo_tile) {   // same three products as the tensor-core path, k by k
+          const __half* wl = w_lo_tile + static_cast<size_t>(chunk * 32 + j) * K;
+          for (int k = 0; k < K; ++k) {
+            const float ah = __half2float(a_row[k]), al = __half2float(a_lo_row[k]);
+            const float wh = __half2float(w[k]), wlo = __half2float(wl[k]);
+            acc = fmaf(ah, wh, acc);
+            acc = fmaf(al, wh, acc);
+            acc = fmaf(ah, wlo, acc);
+          }
+        } else {
+          for (int k = 0; k < K; ++k) acc = fmaf(__half2float(a_row[k]), __half2float(w[k]), acc);
+        }
       }
       v[j] = acc;
     }
@@ -184,7 +226,10 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (valid) store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + col0 + c * 32, v);
+      if (valid) {
+        const size_t o = static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
+        store_half32_split(p.out16 + o, p.out16_lo ? p.out16_lo + o : nullptr, v);
+      }
     }
   } else if constexpr (EPI == EPI_F32 || EPI == EPI_GELU_F32 || EPI == EPI_BIAS_GELU_F32) {
 #pragma unroll 1
@@ -279,9 +324,9 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         }
       }
       if (valid) {
-        __half* o = p.out16 + static_cast<size_t>(row) * p.ld16 + gcol;
-        store_half32(o, v);
-        store_half32(o + 32, w2);
+        const size_t o = static_cast<size_t>(row) * p.ld16 + gcol;
+        store_half32_split(p.out16 + o, p.out16_lo ? p.out16_lo + o : nullptr, v);
+        store_half32_split(p.out16 + o + 32, p.out16_lo ? p.out16_lo + o + 32 : nullptr, w2);
       }
     }
   } else if constexpr (kGeglu<EPI>) {
@@ -293,7 +338,10 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
       ld.load(4 + c, g);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = kNorm<EPI> ? gelu_erf(v[i] * rs) * (g[i] * rs) : gelu_erf(v[i]) * g[i];
-      if (valid) store_half32(p.out16 + static_cast<size_t>(row) * p.ld16 + n_tile * 128 + c * 32, v);
+      if (valid) {
+        const size_t o = static_cast<size_t>(row) * p.ld16 + n_tile * 128 + c * 32;
+        store_half32_split(p.out16 + o, p.out16_lo ? p.out16_lo + o : nullptr, v);
+      }
     }
   } else if constexpr (EPI == EPI_SPLADE) {
     // max_rows log1p(relu(x + b)) = log1p(relu(max_rows(x) + b)): the bias is per column and log1p(relu(.)) is monotone,
@@ -371,6 +419,25 @@ struct BoxStager {
     }
     ++issued;
   }
+  // Split-precision outputs: the warp's two boxes are filled together (box 0 = hi plane, box 1 = lo plane) and stored
+  // as one bulk group, so both must have been read out before the next fill.
+  __device__ __forceinline__ uint8_t* acquire_both(int lane) {
+    if (issued > 0) {
+      if (elect_one()) bulk_wait_read<0>();
+    }
+    __syncwarp();
+    return base;
+  }
+  __device__ __forceinline__ void submit_both(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, int x, int y) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_2d(tm_hi, base, x, y);
+      tma_store_2d(tm_lo, base + EPI_BOX_BYTES, x, y);
+      bulk_commit();
+    }
+    issued += 2;
+  }
 };
 
 // write 32 fp32 values as 16 halves-pairs = 64 bytes = chunks [4*half_idx, 4*half_idx+4) of this thread's box row
@@ -392,8 +459,25 @@ __device__ __forceinline__ void box_put_float32(uint8_t* box, int r, const float
         make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-template <int EPI>
-__device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st,
+// the same 64 bytes of this thread's row in the hi box and in the lo box (split-precision planes)
+__device__ __forceinline__ void box_put_half32_split(uint8_t* box_hi, uint8_t* box_lo, int r, int half_idx,
+                                                     const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u, l;
+    split_half2(v[8 * i + 0], v[8 * i + 1], u.x, l.x);
+    split_half2(v[8 * i + 2], v[8 * i + 3], u.y, l.y);
+    split_half2(v[8 * i + 4], v[8 * i + 5], u.z, l.z);
+    split_half2(v[8 * i + 6], v[8 * i + 7], u.w, l.w);
+    const int off = r * 128 + (((half_idx * 4 + i) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(box_hi + off) = u;
+    *reinterpret_cast<uint4*>(box_lo + off) = l;
+  }
+}
+
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CUtensorMap* tmOut,
+                                                const CUtensorMap* tmOutLo, BoxStager& st,
                                                 int m0, int n_tile, const TmemLoader& ld, int lane, int half,
                                                 float rs /* kNormBias: rstd of this thread's row, fetched by the caller
                                                             before it waits for the accumulators */) {
@@ -403,7 +487,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
   if constexpr (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kNormBias<EPI>) {
 #pragma unroll 1
     for (int b = 2 * half; b < 2 * half + 2; ++b) {
-      uint8_t* box = st.acquire(lane);
+      uint8_t* box = SPLIT ? st.acquire_both(lane) : st.acquire(lane);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         ld.load(2 * b + h, v);
@@ -423,9 +507,11 @@ __device__ __forceinline__ void staged_epilogue(const GemmEpiParams& p, const CU
 #pragma unroll
           for (int i = 0; i < 16; ++i) f2_unpack(gelu2(f2_pack(v[2 * i], v[2 * i + 1])), v[2 * i], v[2 * i + 1]);
         }
-        box_put_half32(box, r, h, v);
+        if constexpr (SPLIT) box_put_half32_split(box, box + EPI_BOX_BYTES, r, h, v);
+        else box_put_half32(box, r, h, v);
       }
-      st.submit<false>(tmOut, box, col0 + b * 64, m0, lane);
+      if constexpr (SPLIT) st.submit_both(tmOut, tmOutLo, col0 + b * 64, m0);
+      else st.submit<false>(tmOut, box, col0 + b * 64, m0, lane);
     }
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
@@ -474,6 +560,21 @@ __device__ __forceinline__ void box_put_half16(uint8_t* box, int r, int chunk0, 
     u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
     u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
     *reinterpret_cast<uint4*>(box + r * 128 + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+  }
+}
+
+__device__ __forceinline__ void box_put_half16_split(uint8_t* box_hi, uint8_t* box_lo, int r, int chunk0,
+                                                     const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u, l;
+    split_half2(v[8 * i + 0], v[8 * i + 1], u.x, l.x);
+    split_half2(v[8 * i + 2], v[8 * i + 3], u.y, l.y);
+    split_half2(v[8 * i + 4], v[8 * i + 5], u.z, l.z);
+    split_half2(v[8 * i + 6], v[8 * i + 7], u.w, l.w);
+    const int off = r * 128 + (((chunk0 + i) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(box_hi + off) = u;
+    *reinterpret_cast<uint4*>(box_lo + off) = l;
   }
 }
 
@@ -539,8 +640,9 @@ __device__ __forceinline__ void rope_prefetch(const GemmEpiParams& p, const CUte
 }
 
 // Wqkv tail.  Step s = 0..3: head 2*half + (s >> 1), dims [16j, 16j+16) and [32+16j, 32+16j+16), j = s & 1.
-template <int EPI>
-__device__ __forceinline__ void rope_body(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st, int m0,
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ void rope_body(const GemmEpiParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmOutLo,
+                                          BoxStager& st, int m0,
                                           int n_tile, uint32_t taddr, int lane, int half, float rs,
                                           const float (&cs)[32], const float (&sn)[32], const AccRelease& release) {
   const int col0 = n_tile * BN;
@@ -563,7 +665,7 @@ __device__ __forceinline__ void rope_body(const GemmEpiParams& p, const CUtensor
     } else {
       release(lane);   // every accumulator column of this warp is in registers
     }
-    if (j == 0) box = st.acquire(lane);
+    if (j == 0) box = SPLIT ? st.acquire_both(lane) : st.acquire(lane);
     float o1[16], o2[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -576,23 +678,30 @@ __device__ __forceinline__ void rope_body(const GemmEpiParams& p, const CUtensor
       o1[e] = rotate ? x1 * c - x2 * sv : x1;
       o2[e] = rotate ? x2 * c + x1 * sv : x2;
     }
-    box_put_half16(box, r, 2 * j, o1);
-    box_put_half16(box, r, 4 + 2 * j, o2);
-    if (j == 1 && p.debug_mode != 4) st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
+    if constexpr (SPLIT) {
+      box_put_half16_split(box, box + EPI_BOX_BYTES, r, 2 * j, o1);
+      box_put_half16_split(box, box + EPI_BOX_BYTES, r, 4 + 2 * j, o2);
+      if (j == 1) st.submit_both(tmOut, tmOutLo, col0 + h * 64, m0);
+    } else {
+      box_put_half16(box, r, 2 * j, o1);
+      box_put_half16(box, r, 4 + 2 * j, o2);
+      if (j == 1 && p.debug_mode != 4) st.submit<false>(tmOut, box, col0 + h * 64, m0, lane);
+    }
   }
 }
 
 // Wi tail.  This warp owns output columns [64*half, 64*half+64) of the tile's 128: step s = 0..3 takes input columns
 // 64*half + 16s .. +16 and the matching gate columns 128 + 64*half + 16s.
-template <int EPI>
-__device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtensorMap* tmOut, BoxStager& st, int m0,
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmOutLo,
+                                           BoxStager& st, int m0,
                                            int n_tile, uint32_t taddr, int lane, int half, float rs,
                                            const AccRelease& release) {
   const int r = lane;
   uint32_t a[2][16], g[2][16];
   tmem_ld_32x32b_x16(taddr + 64 * half, a[0]);
   tmem_ld_32x32b_x16(taddr + 128 + 64 * half, g[0]);
-  uint8_t* box = st.acquire(lane);
+  uint8_t* box = SPLIT ? st.acquire_both(lane) : st.acquire(lane);
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     tmem_ld_wait();
@@ -616,9 +725,11 @@ __device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtenso
       }
       f2_unpack(f2_mul(gelu2(x2), y2), o[2 * e], o[2 * e + 1]);
     }
-    box_put_half16(box, r, 2 * s, o);   // (debug_mode 4 keeps the math and the smem staging, drops the TMA store)
+    if constexpr (SPLIT) box_put_half16_split(box, box + EPI_BOX_BYTES, r, 2 * s, o);
+    else box_put_half16(box, r, 2 * s, o);   // (debug_mode 4 keeps the math and the smem staging, drops the TMA store)
   }
-  if (p.debug_mode != 4) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
+  if constexpr (SPLIT) st.submit_both(tmOut, tmOutLo, n_tile * 128 + half * 64, m0);
+  else if (p.debug_mode != 4) st.submit<false>(tmOut, box, n_tile * 128 + half * 64, m0, lane);
 }
 
 // Launched as clusters of 2 CTAs (an SM pair) that cooperate on one 256 x 256 output tile with
@@ -629,10 +740,17 @@ __device__ __forceinline__ void geglu_body(const GemmEpiParams& p, const CUtenso
 // The leader CTA (cluster rank 0) issues the MMAs; both CTAs' TMA loads signal the leader's `full` barrier; the MMA
 // commit is multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator by
 // arriving on the leader's `tmem_empty` barrier.
-template <int EPI, int STAGES>
+//
+// SPLIT (split-precision / "precise" mode, gemm.cuh): the operand ring holds units of 32 KB that alternate between the
+// hi planes (A_hi, W_hi half) and the lo planes (A_lo, W_lo half) of one k-block; the leader issues
+// A_hi W_hi as soon as the hi unit has landed, then A_lo W_hi + A_hi W_lo once the lo unit has, and releases both
+// units together.  Same shared-memory footprint as the 5-stage fp16 ring (2.5 k-blocks in flight).
+template <int EPI, int STAGES, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+                    const __grid_constant__ CUtensorMap tmOutLo,
                     int m_tiles, int n_tiles, int k_blocks, GemmEpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -666,6 +784,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (SPLIT) {
+      tma_prefetch_desc(&tmAlo);
+      tma_prefetch_desc(&tmBlo);
+    }
   }
   if (warp == 1) {
     tmem_alloc_pair(tmem_holder, TMEM_COLS);
@@ -687,16 +809,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
       const int m_idx = 2 * (pair / n_tiles) + cta_rank, n_idx = pair % n_tiles;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait_tagged(bar_empty + stage, phase ^ 1, 11);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        if (elect_one()) {
-          // one barrier in the leader tracks both CTAs' operands: 2 x (A 16 KB + W half 16 KB)
-          if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + stage, 2 * STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmA, bar_full + stage, kb * BK, m_idx * BM);
-          tma_load_2d_pair(sa + A_BYTES, &tmB, bar_full + stage, kb * BK, n_idx * BN + cta_rank * (BN / 2));
+#pragma unroll
+        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {   // SPLIT: hi unit, then lo unit of this k-block
+          mbar_wait_tagged(bar_empty + stage, phase ^ 1, 11);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          if (elect_one()) {
+            // one barrier in the leader tracks both CTAs' operands: 2 x (A 16 KB + W half 16 KB)
+            if (cta_rank == 0) mbar_arrive_expect_tx(bar_full + stage, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sa, part ? &tmAlo : &tmA, bar_full + stage, kb * BK, m_idx * BM);
+            tma_load_2d_pair(sa + A_BYTES, part ? &tmBlo : &tmB, bar_full + stage, kb * BK,
+                             n_idx * BN + cta_rank * (BN / 2));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -715,17 +841,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
-          if (elect_one()) {
+          if constexpr (!SPLIT) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+              }
+              // slot reusable (in BOTH CTAs) once these MMAs retire
+              umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
             }
-            // slot reusable (in BOTH CTAs) once these MMAs retire
-            umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          } else {
+            if (elect_one()) {   // A_hi W_hi
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            __syncwarp();
+            const int hi_stage = stage;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait_tagged(bar_full + stage, phase, 17);
+            tc_fence_after();
+            const uint32_t al_addr = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t bl_addr = al_addr + A_BYTES;
+            if (elect_one()) {   // A_lo W_hi + A_hi W_lo
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_f16_pair(d_tmem, umma_desc_sw128(al_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, 1u);
+                umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(bl_addr + k * 32), idesc, 1u);
+              }
+              umma_commit_pair(bar_empty + hi_stage, static_cast<uint16_t>(3));   // both units reusable once these retire
+              umma_commit_pair(bar_empty + stage, static_cast<uint16_t>(3));
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit_pair(bar_tfull + acc, static_cast<uint16_t>(3));   // accumulators -> epilogues
         __syncwarp();
@@ -887,6 +1041,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       BoxStager stager{my_smem, 0u};
       if (kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOut);
       if (kRope<EPI> && lane == 0) tma_prefetch_desc(&tmOut2);
+      if (SPLIT && kStaged<EPI> && lane == 0) tma_prefetch_desc(&tmOutLo);
       uint64_t* rope_bar = bar_x + STATS_BARS * (warp - 2);
       uint32_t rope_phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
@@ -906,8 +1061,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_tagged(bar_tfull + acc, acc_phase, 14);
           tc_fence_after();
           if (p.debug_mode == 3) release(lane);   // timing experiment: mainloop only
-          else if constexpr (kRope<EPI>) rope_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, cs, sn, release);
-          else geglu_body<EPI>(p, &tmOut, stager, m0, n_idx, taddr, lane, half, rs, release);
+          else if constexpr (kRope<EPI>)
+            rope_body<EPI, SPLIT>(p, &tmOut, &tmOutLo, stager, m0, n_idx, taddr, lane, half, rs, cs, sn, release);
+          else geglu_body<EPI, SPLIT>(p, &tmOut, &tmOutLo, stager, m0, n_idx, taddr, lane, half, rs, release);
         } else {
           float rs = 1.f;
           if constexpr (kNormBias<EPI>) rs = row_rstd(p, m0 + lane);   // before the accumulator wait: latency hidden
@@ -917,7 +1073,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.debug_mode == 3) {
             // timing experiment: mainloop only
           } else if constexpr (kStaged<EPI>)
-            staged_epilogue<EPI>(p, &tmOut, stager, m0, n_idx, ld, lane, half, rs);
+            staged_epilogue<EPI, SPLIT>(p, &tmOut, &tmOutLo, stager, m0, n_idx, ld, lane, half, rs);
           else
             epilogue_row<EPI>(p, m0 + lane, n_idx, ld, 4 * half, 4 * half + 4);
           release(lane);
@@ -949,33 +1105,52 @@ gemm_reference_kernel(const __half* __restrict__ A, const __half* __restrict__ W
   const int m_idx = blockIdx.x / n_tiles, n_idx = blockIdx.x % n_tiles;
   const int row = m_idx * BM + threadIdx.x;
   ReferenceLoader ld{row < p.M ? A + static_cast<size_t>(row) * K : nullptr,
-                     W + static_cast<size_t>(n_idx) * BN * K, K};
+                     W + static_cast<size_t>(n_idx) * BN * K, K,
+                     (p.a_lo && row < p.M) ? p.a_lo + static_cast<size_t>(row) * K : nullptr,
+                     p.w_lo ? p.w_lo + static_cast<size_t>(n_idx) * BN * K : nullptr};
   epilogue_row<EPI>(p, row, n_idx, ld);
 }
 
-template <int EPI, int STAGES>
+// cudaFuncSetAttribute is per device: several contexts on different GPUs may live in one process
+inline bool first_use_on_device(std::atomic<uint64_t>& mask, int device) {
+  const uint64_t bit = 1ull << (device & 63);
+  return (mask.fetch_or(bit) & bit) == 0;
+}
+
+template <int EPI, int STAGES, bool SPLIT>
 void launch_tc(vrag_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-               const CUtensorMap& tmOut2, int m_tiles, int n_tiles, int k_blocks, const GemmEpiParams& p) {
+               const CUtensorMap& tmOut2, const CUtensorMap& tmAlo, const CUtensorMap& tmBlo,
+               const CUtensorMap& tmOutLo, int m_tiles, int n_tiles, int k_blocks, const GemmEpiParams& p) {
   constexpr int SMEM_BYTES = smem_bytes(STAGES, EPI);
   static_assert(SMEM_BYTES <= 232448, "GEMM shared memory exceeds the 227 KB per-CTA limit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static std::atomic<uint64_t> attr_mask{0};
+  if (first_use_on_device(attr_mask, ctx->device))
+    VRAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    SMEM_BYTES));
-    attr_set = true;
-  }
   const int total_pairs = ((m_tiles + 1) / 2) * n_tiles;
   const int max_clusters = ctx->num_sms / 2;
   const int grid = 2 * (total_pairs < max_clusters ? total_pairs : max_clusters);   // CTA pairs (clusters of 2)
-  gemm_tcgen05_kernel<EPI, STAGES><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmOut2, m_tiles,
-                                                                                    n_tiles, k_blocks, p);
+  gemm_tcgen05_kernel<EPI, STAGES, SPLIT><<<grid, GEMM_THREADS, SMEM_BYTES, ctx->stream>>>(
+      tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p);
 }
+
+// epilogues available in split-precision mode (the deferred-LayerNorm family belongs to the two-plane fp16 + e5m2 fast path)
+template <int EPI>
+constexpr bool kSplitOk = !kResidStats<EPI> && !kNorm<EPI> && !kNormBias<EPI>;
+template <int EPI>
+constexpr bool kHalfOut = (EPI == EPI_F16 || EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || kRope<EPI> || kGeglu<EPI>);
 
 template <int EPI>
 void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int K, const GemmEpiParams& p,
               int use_reference) {
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
   ProfScope prof(ctx, PROF_GEMM);
+  const bool split = p.a_lo != nullptr || p.w_lo != nullptr;
+  if (split) {
+    VRAG_CHECK(p.a_lo && p.w_lo, VRAG_ERR_ARG, "gemm: split precision needs the low planes of both operands");
+    VRAG_CHECK(kSplitOk<EPI>, VRAG_ERR_ARG, "gemm: this epilogue has no split-precision variant");
+    VRAG_CHECK(!kHalfOut<EPI> || p.out16_lo, VRAG_ERR_ARG, "gemm: split precision needs out16_lo for fp16 outputs");
+  }
   if (use_reference) {
     gemm_reference_kernel<EPI><<<m_tiles * n_tiles, 128, 0, ctx->stream>>>(A, W, K, n_tiles, p);
   } else {
@@ -983,6 +1158,7 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
     CUtensorMap tmB = make_tmap_2d(ctx, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN / 2, BK);  // half W tile
     CUtensorMap tmOut = tmA;  // placeholder for the epilogues that write directly
     CUtensorMap tmOut2 = tmA;
+    CUtensorMap tmAlo = tmA, tmBlo = tmB, tmOutLo = tmA;   // placeholders unless split
     if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32)
       tmOut = make_tmap_2d(ctx, p.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, p.ld32, p.ld32, 32, 32);
     else if constexpr (kStaged<EPI>)
@@ -1000,12 +1176,20 @@ void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int
       tmOut2 = make_tmap_2d(ctx, p.out8_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, p.ld16, p.ld16, 32, 64,
                             CU_TENSOR_MAP_SWIZZLE_64B);
       // 12 KB of residual staging per epilogue warp leave room for 4 operand stages (the kernel is HBM-bound)
-      launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p);
+      launch_tc<EPI, 4, false>(ctx, tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p);
+    } else if (split) {
+      if constexpr (kSplitOk<EPI>) {
+        tmAlo = make_tmap_2d(ctx, p.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, K, BM, BK);
+        tmBlo = make_tmap_2d(ctx, p.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, K, BN / 2, BK);
+        if constexpr (kHalfOut<EPI>)
+          tmOutLo = make_tmap_2d(ctx, p.out16_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, p.ld16, p.ld16, 32, 64);
+        launch_tc<EPI, 5, true>(ctx, tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p);
+      }
     } else {
       switch (ctx->gemm_stages) {
-        case 3: launch_tc<EPI, 3>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
-        default: launch_tc<EPI, 5>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
-        case 4: launch_tc<EPI, 4>(ctx, tmA, tmB, tmOut, tmOut2, m_tiles, n_tiles, k_blocks, p); break;
+        case 3: launch_tc<EPI, 3, false>(ctx, tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p); break;
+        default: launch_tc<EPI, 5, false>(ctx, tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p); break;
+        case 4: launch_tc<EPI, 4, false>(ctx, tmA, tmB, tmOut, tmOut2, tmAlo, tmBlo, tmOutLo, m_tiles, n_tiles, k_blocks, p); break;
       }
     }
   }

@@ -38,6 +38,13 @@ enum GemmEpi : int {
 };
 
 struct GemmEpiParams {
+  // Split-precision ("precise") mode: every fp16 tensor is a pair of planes x = hi + lo with hi = fp16(x) and
+  // lo = fp16(x - hi) (>= 21 significant bits; absolute resolution 2^-25), and a product is evaluated as
+  // a_hi w_hi + a_lo w_hi + a_hi w_lo (three tcgen05.mma per k-step, fp32 accumulation in TMEM).  Selected by passing the
+  // low planes of BOTH operands; epilogues that write fp16 activations then also write their low plane to out16_lo.
+  const __half* a_lo = nullptr;       // [M, K] low plane of A
+  const __half* w_lo = nullptr;       // [N, K] low plane of W
+  __half* out16_lo = nullptr;         // low plane of out16 (same leading dimension)
   __half* out16 = nullptr;
   int ld16 = 0;
   uint8_t* out8_lo = nullptr;         // EPI_RESID_STATS: low plane of the residual stream, e5m2 [M, ld16]

@@ -45,8 +45,9 @@ __device__ __forceinline__ void ln_row(float4 (&v)[VEC], const float* __restrict
 
 // lo8_row (optional): the rounding remainder v - fp16(v) as e5m2, so that hi + lo carries the row to >= 14 bits
 // (the two-plane residual stream of the deferred-LayerNorm path, gemm.cuh EPI_RESID_STATS).
+// lo16_row (optional): the same remainder as fp16 -- the low plane of the split-precision ("precise") mode, gemm.cuh.
 __device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row, __half* h16_row, int lane,
-                                          uint8_t* lo8_row = nullptr) {
+                                          uint8_t* lo8_row = nullptr, __half* lo16_row = nullptr) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     if (x32_row) reinterpret_cast<float4*>(x32_row)[i * 32 + lane] = v[i];
@@ -60,6 +61,15 @@ __device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row
         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
         reinterpret_cast<uint32_t*>(lo8_row)[i * 32 + lane] =
             pack_e5m2x4(v[i].x - f0.x, v[i].y - f0.y, v[i].z - f1.x, v[i].w - f1.y);
+      }
+      if (lo16_row) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v[i].x - f0.x, v[i].y - f0.y);
+        const __half2 l1 = __floats2half2_rn(v[i].z - f1.x, v[i].w - f1.y);
+        uint2 ul;
+        ul.x = *reinterpret_cast<const uint32_t*>(&l0);
+        ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+        reinterpret_cast<uint2*>(lo16_row)[i * 32 + lane] = ul;
       }
     }
   }
@@ -91,7 +101,7 @@ __global__ void token_meta_kernel(const int32_t* __restrict__ cu, int nseq, int3
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* __restrict__ emb,
                 const float* __restrict__ gamma, float eps, float* __restrict__ x32, __half* __restrict__ h16,
-                uint8_t* __restrict__ lo8) {
+                uint8_t* __restrict__ lo8, __half* __restrict__ lo16) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   int id = ids[row];
@@ -102,7 +112,7 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int T, int vocab, const float* 
   for (int i = 0; i < VEC; ++i) v[i] = __ldg(e + i * 32 + lane);
   ln_row(v, gamma, nullptr, eps, lane);
   store_row(v, x32 ? x32 + static_cast<size_t>(row) * H : nullptr, h16 + static_cast<size_t>(row) * H, lane,
-            lo8 ? lo8 + static_cast<size_t>(row) * H : nullptr);
+            lo8 ? lo8 + static_cast<size_t>(row) * H : nullptr, lo16 ? lo16 + static_cast<size_t>(row) * H : nullptr);
 }
 
 // LayerNorm of the two-plane residual stream (final norm of the deferred-LayerNorm path); h16 may alias hi.
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int T, int vocab, int max_pos,
                      const float* __restrict__ wemb, const float* __restrict__ pemb, const float* __restrict__ temb0,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     float* __restrict__ x32, __half* __restrict__ h16) {
+                     float* __restrict__ x32, __half* __restrict__ h16, __half* __restrict__ lo16) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   int id = ids[row];
@@ -147,7 +157,8 @@ bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict_
     v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
   }
   ln_row(v, gamma, beta, eps, lane);
-  store_row(v, x32 + static_cast<size_t>(row) * H, h16 + static_cast<size_t>(row) * H, lane);
+  store_row(v, x32 + static_cast<size_t>(row) * H, h16 + static_cast<size_t>(row) * H, lane, nullptr,
+            lo16 ? lo16 + static_cast<size_t>(row) * H : nullptr);
 }
 
 // Deferred-LayerNorm BERT path: z = word + position + type embedding, NOT normalised -- written as the two-plane
@@ -184,7 +195,7 @@ bert_embed_raw_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict
 
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 layernorm_kernel(float* __restrict__ x32, int T, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, __half* __restrict__ h16, int write_back) {
+                 float eps, __half* __restrict__ h16, int write_back, __half* __restrict__ lo16) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   float* xr = x32 + static_cast<size_t>(row) * H;
@@ -192,7 +203,8 @@ layernorm_kernel(float* __restrict__ x32, int T, const float* __restrict__ gamma
 #pragma unroll
   for (int i = 0; i < VEC; ++i) v[i] = reinterpret_cast<const float4*>(xr)[i * 32 + lane];
   ln_row(v, gamma, beta, eps, lane);
-  store_row(v, write_back ? xr : nullptr, h16 ? h16 + static_cast<size_t>(row) * H : nullptr, lane);
+  store_row(v, write_back ? xr : nullptr, h16 ? h16 + static_cast<size_t>(row) * H : nullptr, lane, nullptr,
+            (h16 && lo16) ? lo16 + static_cast<size_t>(row) * H : nullptr);
 }
 
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
@@ -319,6 +331,16 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
   }
 }
 
+__global__ void f32_to_f16_split_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = src[i];
+  const __half h = __float2half_rn(x);
+  hi[i] = h;
+  lo[i] = __float2half_rn(x - __half2float(h));
+}
+
 inline int row_blocks(int T) { return (T + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK; }
 
 }  // namespace
@@ -336,10 +358,10 @@ void launch_token_meta(vrag_ctx* ctx, const int32_t* cu, int nseq, int total, in
   VRAG_LAUNCHED(ctx);
 }
 void launch_embed_ln(vrag_ctx* ctx, const int32_t* ids, int T, int vocab, const float* tok_emb, const float* gamma,
-                     float eps, float* x32, __half* h16, uint8_t* lo8) {
+                     float eps, float* x32, __half* h16, uint8_t* lo8, __half* h16_lo) {
   ProfScope prof(ctx, PROF_ROWOPS);
   embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, T, vocab, tok_emb, gamma, eps, x32, h16,
-                                                                           lo8);
+                                                                           lo8, h16_lo);
   VRAG_LAUNCHED(ctx);
 }
 void launch_layernorm_hilo(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, const float* gamma,
@@ -364,18 +386,18 @@ void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int 
 }
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
-                          const float* beta, float eps, float* x32, __half* h16) {
+                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo) {
   ProfScope prof(ctx, PROF_ROWOPS);
   bert_embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
                                                                                 pos_emb, type_emb0, gamma, beta, eps,
-                                                                                x32, h16);
+                                                                                x32, h16, h16_lo);
   VRAG_LAUNCHED(ctx);
 }
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps, __half* h16,
-                      bool write_back) {
+                      bool write_back, __half* h16_lo) {
   ProfScope prof(ctx, PROF_ROWOPS);
   layernorm_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
-                                                                            write_back ? 1 : 0);
+                                                                            write_back ? 1 : 0, h16_lo);
   VRAG_LAUNCHED(ctx);
 }
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
@@ -407,6 +429,12 @@ void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n) {
   ProfScope prof(ctx, PROF_ROWOPS);
   const size_t threads = (n + 3) / 4;
   f32_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(src, dst, n);
+  VRAG_LAUNCHED(ctx);
+}
+
+void launch_f32_to_f16_split(vrag_ctx* ctx, const float* src, __half* hi, __half* lo, size_t n) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  f32_to_f16_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(src, hi, lo, n);
   VRAG_LAUNCHED(ctx);
 }
 

@@ -64,8 +64,13 @@ class B200SpanExtractor(SpanExtractor):
         tokenizer=None,
         num_layers: Optional[int] = None,
         vocab_size: Optional[int] = None,
+        precision: str = "fast",
     ):
+        """``precision``: ``"fast"`` = fp16 tensor-core operands (logits within ~3.5e-3 of the reference's fp32
+        forward, identical spans except at tokens that close to the threshold); ``"precise"`` = split-precision
+        operands, logits within 1e-3 (the reference runs the model in fp32, extractors.py:151-157), ~3x the time."""
         self.model_path = model_path
+        self.precision = precision
         self.threshold = threshold
         self.extraction_mode = extraction_mode
         self.max_display_spans = max_display_spans
@@ -82,7 +87,7 @@ class B200SpanExtractor(SpanExtractor):
         self.tokenizer = tokenizer
         self._ctx = _native.default_context(self.device)   # raises NativeError without a CUDA device / library
         self._enc = _native.Encoder(self._ctx, _native.ENC_MODERNBERT_TOKCLS, weights, int(num_layers),
-                                    int(vocab_size), max_tokens=max_tokens)
+                                    int(vocab_size), max_tokens=max_tokens, precision=precision)
         self._lock = threading.Lock()  # shared across to_thread workers (extractors.py:48-54)
         self.pipeline_pairs = 512      # pairs per slice of the tokenise / forward / post-process pipeline
 

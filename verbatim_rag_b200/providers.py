@@ -23,8 +23,9 @@ from .models import parse_device, resolve_bert
 
 class _BertTextEncoder:
     def __init__(self, model_name: str, device, kind: int, max_seq_length: int, max_tokens: int,
-                 weights=None, tokenizer=None, num_layers=None, vocab_size=None):
+                 weights=None, tokenizer=None, num_layers=None, vocab_size=None, precision: str = "fast"):
         self.model_name = model_name
+        self.precision = precision
         self.device_index = parse_device(device)
         if weights is None:
             weights, tok, layers, vocab = resolve_bert(model_name)
@@ -35,7 +36,8 @@ class _BertTextEncoder:
         self.vocab_size = int(vocab_size)
         self.max_seq_length = max_seq_length
         self._ctx = _native.default_context(self.device_index)
-        self._enc = _native.Encoder(self._ctx, kind, weights, int(num_layers), int(vocab_size), max_tokens=max_tokens)
+        self._enc = _native.Encoder(self._ctx, kind, weights, int(num_layers), int(vocab_size), max_tokens=max_tokens,
+                                    precision=precision)
         self._lock = threading.Lock()
 
     def tokenize(self, texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
@@ -59,11 +61,14 @@ class B200SpladeProvider(SparseEmbeddingProvider):
     """SPLADE sparse embedding provider on the GPU (reference: embedding_providers.py:117-169)."""
 
     def __init__(self, model_name: str = "synthetic:1002", device: str = "cuda", *, max_seq_length: int = 512,
-                 max_tokens: int = 65536, weights=None, tokenizer=None, num_layers=None, vocab_size=None):
+                 max_tokens: int = 65536, weights=None, tokenizer=None, num_layers=None, vocab_size=None,
+                 precision: str = "fast"):
+        """``precision``: "fast" (fp16 tensor-core operands, weights within ~3e-3 of the fp32 reference) or "precise"
+        (split-precision operands, within 1e-3; the reference's SparseEncoder runs in fp32)."""
         self.model_name = model_name
         self.device = device
         self._te = _BertTextEncoder(model_name, device, _native.ENC_BERT_MLM, max_seq_length, max_tokens, weights,
-                                    tokenizer, num_layers, vocab_size)
+                                    tokenizer, num_layers, vocab_size, precision)
         self.pipeline_texts = 1024   # texts per slice of the tokenise / encode pipeline of embed_batch_csr
 
     def embed_text(self, text: str) -> Dict[int, float]:
@@ -113,13 +118,13 @@ class B200DenseProvider(DenseEmbeddingProvider):
 
     def __init__(self, model_name: str = "synthetic:1002", device: str = "cuda", *, pooling: str = "mean",
                  normalize: bool = True, max_seq_length: int = 512, max_tokens: int = 65536, weights=None,
-                 tokenizer=None, num_layers=None, vocab_size=None):
+                 tokenizer=None, num_layers=None, vocab_size=None, precision: str = "fast"):
         self.model_name = model_name
         self.device = device
         self.pooling = {"mean": _native.POOL_MEAN, "cls": _native.POOL_CLS}[pooling]
         self.normalize = normalize
         self._te = _BertTextEncoder(model_name, device, _native.ENC_BERT_DENSE, max_seq_length, max_tokens, weights,
-                                    tokenizer, num_layers, vocab_size)
+                                    tokenizer, num_layers, vocab_size, precision)
 
     def embed_array(self, texts: Sequence[str]) -> np.ndarray:
         if len(texts) == 0:
