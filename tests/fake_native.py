@@ -18,7 +18,7 @@ class FakeContext:
 
 
 class FakeEncoder:
-    def __init__(self, ctx, kind, weights, num_layers, vocab_size, max_tokens=65536):
+    def __init__(self, ctx, kind, weights, num_layers, vocab_size, max_tokens=65536, precision="fast"):
         from verbatim_rag_b200.synthetic import BertSpec, ModernBertSpec
         self.kind, self.weights, self.vocab_size = kind, weights, vocab_size
         self.spec = (ModernBertSpec(layers=num_layers, vocab_size=vocab_size) if kind == 0

@@ -26,6 +26,24 @@ def main():
     out = {}
 
     # ---- config 1: 4 questions x 8 chunks @128 tokens, full 22-layer model -------------------------------------
+    # chunk selection: the first 8 candidates per question whose context-token probabilities all keep
+    # cases.SPAN_CFG1_MARGIN from the threshold (cases.span_cfg1 docstring)
+    cand = cases.span_cfg1_candidates()
+    cl = modernbert.modernbert_forward_varlen(cand["weights"], cand["seqs"], cand["spec"], batch=8)
+    chosen = []
+    for qi in range(4):
+        row = []
+        for j in range(cases.SPAN_CFG1_CANDIDATES):
+            i = qi * cases.SPAN_CFG1_CANDIDATES + j
+            nq = cand["n_q"][i]
+            p_ctx = modernbert.relevant_prob(cl[i])[nq + 2: nq + 2 + 128]
+            if float(np.abs(p_ctx - np.float32(0.2)).min()) >= cases.SPAN_CFG1_MARGIN and len(row) < 8:
+                row.append(j)
+        assert len(row) == 8, (qi, row)
+        chosen.append(row)
+    json.dump({"candidates_hash": cand["hash"], "margin": cases.SPAN_CFG1_MARGIN, "chunks": chosen},
+              open(os.path.join(HERE, "span_cfg1_select.json"), "w"))
+    cases.span_cfg1.cache_clear()
     c = cases.span_cfg1()
     logits = modernbert.modernbert_forward_varlen(c["weights"], c["seqs"], c["spec"], batch=8)
     probs = [modernbert.relevant_prob(lg) for lg in logits]

@@ -13,8 +13,11 @@ from conftest import ROOT  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(HERE, "golden")
-PROB_TOL = 2e-3   # fp16 tensor-core operands through 22 layers: measured max 1.07e-3 over 4.7k tokens
-LOGIT_TOL = 5e-3
+# FAST mode (fp16 tensor-core operands through 22 layers).  Bars = measured maxima on these fixtures + 20 %
+# (logits 3.34e-3, probabilities 1.05e-3).  The north-star 1e-3 is met by the precise mode and
+# asserted at 1e-3 in tests/test_gpu_precise.py on the same fixtures.
+PROB_TOL = 1.3e-3
+LOGIT_TOL = 4.0e-3
 
 
 def _diag(**kw):
@@ -50,18 +53,14 @@ def test_span_extractor_config1_vs_golden():
         mine = [(s["start"], s["end"], s["tok_start"], s["tok_end"]) for s in spans]
         for s in spans:
             assert s["text"] == c["pairs"][i][1][s["start"]:s["end"]]          # verbatim substrings
-        if mine != exp[i]:
-            mismatched_pairs += 1
-            # every disagreement must be explained by a token whose oracle probability is within the
-            # probability tolerance of the threshold
-            nq = c["n_q"][i]
-            a = g["cu"][i] + nq + 2
-            near = np.abs(p_ref[a:a + 128] - np.float32(0.2)) < PROB_TOL
-            assert near.any(), (i, mine, exp[i])
+        mismatched_pairs += mine != exp[i]
     _diag(test="span_cfg1_plugin", logit_max_err=lerr, prob_max_err=perr, pairs=len(got),
           pairs_with_span_mismatch=mismatched_pairs, golden_min_margin=float(g["min_margin_to_threshold"]))
     assert lerr < LOGIT_TOL and perr < PROB_TOL
-    assert mismatched_pairs <= 2
+    # the golden chunks keep every token >= 2.5e-3 from the threshold (tests/golden/cases.py), above the probability
+    # tolerance: char and token offsets must be identical on all 32 pairs
+    assert float(g["min_margin_to_threshold"]) > PROB_TOL
+    assert mismatched_pairs == 0
     # the reference-shaped call: dict keyed by chunk text, duplicates collapse, empty contexts -> []
     class R:
         def __init__(self, t):
@@ -129,7 +128,7 @@ def test_splade_provider_vs_golden():
             worst = max(worst, abs(ref.get(t, 0.0) - d.get(t, 0.0)))
         assert all(type(k) is int and type(v) is float for k, v in d.items())
     _diag(test="splade_plugin", max_err=worst, nnz=[len(d) for d in batch])
-    assert worst < 5e-3
+    assert worst < 3.6e-3   # fast mode: measured 2.98e-3 + 20 %
     one = prov.embed_text(s["texts"][0])
     assert set(one) <= set(batch[0]) and all(abs(v) > 1e-6 for v in one.values())
     assert prov.get_dimension() == 30522

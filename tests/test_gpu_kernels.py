@@ -156,9 +156,9 @@ def test_modernbert_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, monkeypatc
           logit_std=float(ref_logits.std()),
           per_seq_err=[float(err[cu[i]:cu[i + 1]].max()) for i in range(len(lens))])
     enc.close()
-    # fp16 tensor-core operands, fp32 accumulate/residual: tolerance stated in DESIGN.md ("precision")
-    assert err.max() < 5e-3, (err.max(), layer_err)
-    assert perr.max() < 1e-3
+    # fast mode, 4 layers: measured 1.78e-3 / 5.4e-4; bars = measured + 20 % (precise mode: tests/test_gpu_precise.py)
+    assert err.max() < 2.2e-3, (err.max(), layer_err)
+    assert perr.max() < 6.5e-4
 
 
 def test_modernbert_multi_pass_equals_single_pass(ctx):
@@ -208,7 +208,7 @@ def test_span_forward_bench_shape_properties(ctx):
     err = max(float(np.abs(l1[i * L:(i + 1) * L] - r).max()) for i, r in zip(pick, ref))
     perr = max(float(np.abs(p1[i * L:(i + 1) * L] - relevant_prob(r)).max()) for i, r in zip(pick, ref))
     _diag(test="span_forward_bench_shape", nseq=nseq, logit_max_err=err, prob_max_err=perr)
-    assert err < 5e-3 and perr < 2e-3, (err, perr)
+    assert err < 3.1e-3 and perr < 1.0e-3, (err, perr)   # fast mode: measured 2.55e-3 / 8.3e-4 + 20 %
 
 
 # ------------------------------------------------------------------------------------------ SPLADE
@@ -242,7 +242,7 @@ def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, deferred_ln, m
     nnz_got = np.diff(out["indptr"])
     _diag(test="splade_vs_oracle", use_ref_gemm=use_ref_gemm, deferred_ln=deferred_ln, max_err=float(err.max()), nnz_ref=nnz_ref.tolist(),
           nnz_got=nnz_got.tolist(), ref_max=float(ref.max()))
-    assert err.max() < 5e-3
+    assert err.max() < 2.6e-3   # fast mode, 2 layers: measured 2.1e-3 + 20 %
     # CSR is exactly the non-zeros of the dense output, ascending indices
     for i in range(len(seqs)):
         a, b = out["indptr"][i], out["indptr"][i + 1]
@@ -251,7 +251,7 @@ def test_splade_forward_vs_oracle(ctx, use_ref_gemm, legacy_attn, deferred_ln, m
         assert np.array_equal(out["values"][a:b], out["dense"][i][nz])
     # support may differ from the oracle only where the value is within tolerance of zero
     sup_diff = (out["dense"] != 0) != (ref != 0)
-    assert np.all(np.maximum(np.abs(ref), np.abs(out["dense"]))[sup_diff] < 5e-3)
+    assert np.all(np.maximum(np.abs(ref), np.abs(out["dense"]))[sup_diff] < 2.6e-3)
 
 
 # ------------------------------------------------------------------------------------------ top-k
