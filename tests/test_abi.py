@@ -40,3 +40,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+
+
+def test_stale_library_is_not_loaded_silently(monkeypatch):
+    """A .so built from other sources than the tree's (build.sha256 mismatch) must be rebuilt or refused, never
+    dlopen'ed with this module's argtypes."""
+    import pytest
+    from verbatim_rag_b200 import _native, build
+    _native.load_library()
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(build, "_digest", lambda: "0" * 64)
+    with pytest.raises(_native.NativeError, match="stale"):
+        _native.load_library(build_if_missing=False)

@@ -55,11 +55,20 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        stamp = os.path.join(os.path.dirname(LIB_PATH), "build.sha256")
+        stale = (os.path.exists(LIB_PATH)
+                 and (not os.path.exists(stamp) or open(stamp).read().strip() != _build._digest()))
+        if not os.path.exists(LIB_PATH) or stale:
+            # a library built from other sources than the ones in the tree would be called with this module's argtypes
             if not build_if_missing:
-                raise NativeError(VRAG_ERR_INTERNAL, f"{LIB_PATH} not built; run python -m verbatim_rag_b200.build")
-            from .build import build
-            build()
+                raise NativeError(VRAG_ERR_INTERNAL, f"{LIB_PATH} is {'stale' if stale else 'not built'}; "
+                                                     "run python -m verbatim_rag_b200.build")
+            try:
+                _build.build()
+            except Exception as exc:
+                raise NativeError(VRAG_ERR_INTERNAL, f"{LIB_PATH} is {'stale' if stale else 'missing'} and could not "
+                                                     f"be rebuilt: {exc}") from exc
         lib = C.CDLL(LIB_PATH)
         vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
         P = C.POINTER

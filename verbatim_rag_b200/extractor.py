@@ -18,6 +18,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native
+from ._tokworker import TokenizerWorkers, encode_with
 from .interfaces import SpanExtractor
 from .models import parse_device, resolve_modernbert
 
@@ -65,6 +66,7 @@ class B200SpanExtractor(SpanExtractor):
         num_layers: Optional[int] = None,
         vocab_size: Optional[int] = None,
         precision: str = "fast",
+        tokenizer_workers: int = 2,
     ):
         """``precision``: ``"fast"`` = fp16 tensor-core operands (logits within ~3.5e-3 of the reference's fp32
         forward, identical spans except at tokens that close to the threshold); ``"precise"`` = split-precision
@@ -90,6 +92,9 @@ class B200SpanExtractor(SpanExtractor):
                                     int(vocab_size), max_tokens=max_tokens, precision=precision)
         self._lock = threading.Lock()  # shared across to_thread workers (extractors.py:48-54)
         self.pipeline_pairs = 512      # pairs per slice of the tokenise / forward / post-process pipeline
+        # batches of >= worker_min_texts distinct contexts are tokenised by worker processes (_tokworker.py)
+        self._workers = TokenizerWorkers(tokenizer.tok, tokenizer_workers)
+        self.worker_min_texts = 256
 
     # -- reference interface -------------------------------------------------------------------------
     def extract_spans(self, question: str, search_results: List[Any]) -> Dict[str, List[str]]:
@@ -98,7 +103,12 @@ class B200SpanExtractor(SpanExtractor):
     # -- batched entry point ---------------------------------------------------------------------------
     def extract_spans_batch(self, questions: Sequence[str], results_lists: Sequence[List[Any]]
                             ) -> List[Dict[str, List[str]]]:
-        """One GPU pass for many questions; element i is exactly ``extract_spans(questions[i], results_lists[i])``."""
+        """One GPU pass for many questions; element i is exactly ``extract_spans(questions[i], results_lists[i])``.
+
+        Error convention of the reference (extractors.py:225-227): a failing chunk yields ``[]`` for THAT chunk and an
+        ERROR log line, nothing else is affected.  Pairs that cannot be planned (question longer than the window,
+        ``doc_stride`` >= window capacity) are isolated at tokenisation time; if a forward fails, the batch is retried
+        one question at a time so that only the offending question's chunks come back empty."""
         pairs: List[Tuple[int, str]] = []          # (question index, context)
         outs: List[Dict[str, List[str]]] = []
         for qi, (q, results) in enumerate(zip(questions, results_lists)):
@@ -111,12 +121,25 @@ class B200SpanExtractor(SpanExtractor):
             outs.append(rel)
         if not pairs:
             return outs
-        try:
-            detailed = self.extract_detailed([(questions[qi], c) for qi, c in pairs])
-            for (qi, context), spans in zip(pairs, detailed):
+
+        def run(sub: List[Tuple[int, str]]):
+            detailed = self.extract_detailed([(questions[qi], c) for qi, c in sub])
+            for (qi, context), spans in zip(sub, detailed):
                 outs[qi][context] = [s["text"] for s in spans if s["text"].strip()]
-        except Exception as exc:  # reference convention: log and return [] (extractors.py:225-227)
-            logger.error("B200 highlighter extraction failed: %s", exc)
+
+        try:
+            run(pairs)
+        except Exception as exc:  # noqa: BLE001
+            logger.error("B200 highlighter extraction failed for a batch of %d pairs (%s); retrying per question",
+                         len(pairs), exc)
+            by_q: Dict[int, List[Tuple[int, str]]] = {}
+            for qi, c in pairs:
+                by_q.setdefault(qi, []).append((qi, c))
+            for qi, sub in by_q.items():
+                try:
+                    run(sub)
+                except Exception as exc2:  # noqa: BLE001 -- reference convention: log and return [] for these chunks
+                    logger.error("B200 highlighter extraction failed: %s", exc2)
         return outs
 
     def extract_detailed(self, pairs: Sequence[Tuple[str, str]]) -> List[List[Dict[str, Any]]]:
@@ -127,16 +150,20 @@ class B200SpanExtractor(SpanExtractor):
         if len(pairs) <= step:
             plan = self._tokenize(pairs)
             return self._postprocess(pairs, plan, self._forward(plan))
-        # Large batches: host tokenisation of slice i + 1 and span post-processing of slice i - 1 overlap the GPU forward
-        # of slice i (one worker thread owns the encoder; the tokenizers library and the ctypes call release the GIL).
-        # Every (question, context) pair is independent in every kernel, so slicing does not change any result.
+        # Large batches: host tokenisation of slices i + 1, i + 2 and span post-processing of slice i - 1 overlap the GPU
+        # forward of slice i (one thread owns the encoder, one runs ahead with the tokeniser: the tokenizers library, the
+        # worker processes and the ctypes call all release the GIL).  Every (question, context) pair is independent in
+        # every kernel, so slicing does not change any result.
         from concurrent.futures import ThreadPoolExecutor
         out: List[List[Dict[str, Any]]] = []
-        with ThreadPoolExecutor(max_workers=1) as gpu:
+        slices = [pairs[a:a + step] for a in range(0, len(pairs), step)]
+        with ThreadPoolExecutor(max_workers=1) as gpu, ThreadPoolExecutor(max_workers=1) as tk:
+            plans = [tk.submit(self._tokenize, sl) for sl in slices[:2]]
             pending = None
-            for a in range(0, len(pairs), step):
-                sl = pairs[a:a + step]
-                plan = self._tokenize(sl)
+            for i, sl in enumerate(slices):
+                plan = plans[i].result()
+                if i + 2 < len(slices):
+                    plans.append(tk.submit(self._tokenize, slices[i + 2]))
                 fut = gpu.submit(self._forward, plan)
                 if pending is not None:
                     out.extend(self._postprocess(pending[0], pending[1], pending[2].result()))
@@ -145,64 +172,115 @@ class B200SpanExtractor(SpanExtractor):
         return out
 
     def _forward(self, plan: Dict[str, Any]) -> np.ndarray:
+        if len(plan["cu"]) <= 1:
+            return np.zeros(0, np.float32)
         with self._lock:
             return self._enc.span_forward(plan["ids"], plan["cu"])
 
     # -- internals -----------------------------------------------------------------------------------------
+    def _encode_unique(self, texts: List[str]):
+        if len(texts) >= self.worker_min_texts:
+            return self._workers.encode(texts)
+        return encode_with(self.tokenizer.tok, texts)
+
     def _tokenize(self, pairs: Sequence[Tuple[str, str]]) -> Dict[str, Any]:
+        """Token ids of every window ``[CLS] q [SEP] ctx_window [SEP]`` packed back to back, plus the bookkeeping that
+        maps window tokens back to context tokens and characters.  Distinct questions / contexts are tokenised once
+        (popular chunks are retrieved for many questions of a batch)."""
         tk = self.tokenizer
-        uq = {}
-        for q, _ in pairs:
-            if q not in uq:
-                uq[q] = None
-        q_enc = tk.tok.encode_batch(list(uq.keys()), add_special_tokens=False)
-        for q, e in zip(uq.keys(), q_enc):
-            uq[q] = np.asarray(e.ids, dtype=np.int32)
-        # every distinct context is tokenised once (popular chunks are retrieved for many questions of a batch)
-        uc: Dict[str, Any] = {}
-        for _, c in pairs:
-            if c not in uc:
-                uc[c] = None
-        for c, e in zip(uc.keys(), tk.tok.encode_batch(list(uc.keys()), add_special_tokens=False)):
-            uc[c] = (np.asarray(e.ids, dtype=np.int32), np.asarray(e.offsets, dtype=np.int32).reshape(-1, 2))
-        cls_a, sep_a = np.asarray([tk.cls_id], np.int32), np.asarray([tk.sep_id], np.int32)
-        chunks: List[np.ndarray] = []
-        seq_len: List[int] = []
-        win_pair: List[int] = []       # window -> pair
-        win_range: List[Tuple[int, int]] = []
-        win_c0: List[int] = []         # offset of the first context token inside the window's sequence
-        ctx_ntok = np.zeros(len(pairs) + 1, dtype=np.int64)
-        tok_cs: List[np.ndarray] = []
-        tok_ce: List[np.ndarray] = []
+        P = len(pairs)
+        uq: Dict[str, int] = {}
+        uc: Dict[str, int] = {}
+        q_of = np.empty(P, np.int64)
+        c_of = np.empty(P, np.int64)
         for pi, (q, c) in enumerate(pairs):
-            qi = uq[q]
-            cids, off = uc[c]
-            ctx_ntok[pi + 1] = ctx_ntok[pi] + len(cids)
-            tok_cs.append(off[:, 0])
-            tok_ce.append(off[:, 1])
-            if len(cids) == 0:
-                continue
+            q_of[pi] = uq.setdefault(q, len(uq))
+            c_of[pi] = uc.setdefault(c, len(uc))
+        q_len, q_ids, _ = encode_with(tk.tok, list(uq.keys()))
+        c_len, c_ids, c_off = self._encode_unique(list(uc.keys()))
+        q_start = np.concatenate([[0], np.cumsum(q_len, dtype=np.int64)])
+        c_start = np.concatenate([[0], np.cumsum(c_len, dtype=np.int64)])
+        lq = q_len[q_of].astype(np.int64)
+        lc = c_len[c_of].astype(np.int64)
+        ctx_indptr = np.concatenate([[0], np.cumsum(lc, dtype=np.int64)])
+
+        def rep_gather(starts, lens):
+            """indices start_i .. start_i + len_i - 1 for every i, concatenated"""
+            tot = int(lens.sum())
+            base = np.repeat(starts - (np.cumsum(lens) - lens), lens)
+            return base + np.arange(tot, dtype=np.int64)
+
+        g = rep_gather(c_start[c_of], lc)
+        tok_cs = c_off[g, 0] if g.size else np.zeros(0, np.int32)
+        tok_ce = c_off[g, 1] if g.size else np.zeros(0, np.int32)
+        plan: Dict[str, Any] = {"ctx_indptr": ctx_indptr, "tok_cs": np.ascontiguousarray(tok_cs, np.int32),
+                                "tok_ce": np.ascontiguousarray(tok_ce, np.int32), "failed": []}
+        cap = self.max_length - lq - 3
+        bad = (cap <= 0) | ((lc > cap) & (cap - self.doc_stride <= 0))
+        for pi in np.nonzero(bad)[0].tolist():   # reference convention: this chunk yields [] (extractors.py:225-227)
+            logger.error("B200 highlighter extraction failed: pair %d cannot be windowed (question of %d tokens, "
+                         "max_length %d, doc_stride %d)", pi, int(lq[pi]), self.max_length, self.doc_stride)
+            plan["failed"].append(pi)
+        live = ~bad & (lc > 0)
+        if not bool(((lc > cap) & live).any()):
+            # every live pair fits one window: fully vectorised assembly
+            w_pair = np.nonzero(live)[0]
+            wq, wc = lq[w_pair], lc[w_pair]
+            seq_len = wq + wc + 3
+            cu = np.zeros(len(w_pair) + 1, dtype=np.int64)
+            np.cumsum(seq_len, out=cu[1:])
+            ids = np.empty(int(cu[-1]), np.int32)
+            s0 = cu[:-1]
+            ids[s0] = tk.cls_id
+            ids[s0 + 1 + wq] = tk.sep_id
+            ids[cu[1:] - 1] = tk.sep_id
+            ids[rep_gather(s0 + 1, wq)] = q_ids[rep_gather(q_start[q_of[w_pair]], wq)]
+            ids[rep_gather(s0 + 2 + wq, wc)] = c_ids[rep_gather(c_start[c_of[w_pair]], wc)]
+            plan.update(ids=ids, cu=cu.astype(np.int32), win_pair=w_pair, win_s=np.zeros(len(w_pair), np.int64),
+                        win_e=wc, win_c0=wq + 2, single_window=True)
+            return plan
+        # long documents: overlapping windows (doc_stride), a few pairs at most -- plain loop
+        chunks: List[np.ndarray] = []
+        seq_len_l: List[int] = []
+        win_pair: List[int] = []
+        win_s: List[int] = []
+        win_e: List[int] = []
+        win_c0: List[int] = []
+        cls_a, sep_a = np.asarray([tk.cls_id], np.int32), np.asarray([tk.sep_id], np.int32)
+        for pi in np.nonzero(live)[0].tolist():
+            qi = q_ids[q_start[q_of[pi]]:q_start[q_of[pi]] + lq[pi]]
+            cids = c_ids[c_start[c_of[pi]]:c_start[c_of[pi]] + lc[pi]]
             for s, e in plan_windows(len(qi), len(cids), self.max_length, self.doc_stride):
                 chunks.extend((cls_a, qi, sep_a, cids[s:e], sep_a))
-                seq_len.append(len(qi) + (e - s) + 3)
+                seq_len_l.append(len(qi) + (e - s) + 3)
                 win_pair.append(pi)
-                win_range.append((s, e))
+                win_s.append(s)
+                win_e.append(e)
                 win_c0.append(len(qi) + 2)
-        cu = np.zeros(len(seq_len) + 1, dtype=np.int32)
-        np.cumsum(seq_len, out=cu[1:])
-        ids = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
-        return {"ids": ids, "cu": cu, "win_pair": win_pair, "win_range": win_range, "win_c0": win_c0,
-                "ctx_indptr": ctx_ntok, "tok_cs": np.concatenate(tok_cs) if tok_cs else np.zeros(0, np.int32),
-                "tok_ce": np.concatenate(tok_ce) if tok_ce else np.zeros(0, np.int32)}
+        cu = np.zeros(len(seq_len_l) + 1, dtype=np.int32)
+        np.cumsum(seq_len_l, out=cu[1:])
+        plan.update(ids=np.concatenate(chunks) if chunks else np.zeros(0, np.int32), cu=cu,
+                    win_pair=np.asarray(win_pair, np.int64), win_s=np.asarray(win_s, np.int64),
+                    win_e=np.asarray(win_e, np.int64), win_c0=np.asarray(win_c0, np.int64), single_window=False)
+        return plan
 
     def _context_probs(self, plan: Dict[str, Any], probs: np.ndarray) -> np.ndarray:
-        """Per context token: max P(relevant) over the windows containing it."""
-        ctx_indptr, cu = plan["ctx_indptr"], plan["cu"]
+        """Per context token: max P(relevant) over the windows containing it (-1 where no window ran)."""
+        ctx_indptr, cu = plan["ctx_indptr"], plan["cu"].astype(np.int64)
         p_ctx = np.full(int(ctx_indptr[-1]), -1.0, dtype=np.float32)
-        for w, (pi, (s, e), c0) in enumerate(zip(plan["win_pair"], plan["win_range"], plan["win_c0"])):
-            a = int(cu[w]) + c0
-            dst = p_ctx[ctx_indptr[pi] + s: ctx_indptr[pi] + e]
-            np.maximum(dst, probs[a:a + (e - s)], out=dst)
+        wp, ws, we, c0 = plan["win_pair"], plan["win_s"], plan["win_e"], plan["win_c0"]
+        if len(wp) == 0:
+            return p_ctx
+        if plan["single_window"]:
+            n = we - ws
+            tot = int(n.sum())
+            off = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(n) - n, n)
+            p_ctx[np.repeat(ctx_indptr[wp], n) + off] = probs[np.repeat(cu[:-1] + c0, n) + off]
+            return p_ctx
+        for w in range(len(wp)):
+            a = int(cu[w] + c0[w])
+            dst = p_ctx[ctx_indptr[wp[w]] + ws[w]: ctx_indptr[wp[w]] + we[w]]
+            np.maximum(dst, probs[a:a + int(we[w] - ws[w])], out=dst)
         return p_ctx
 
     def _postprocess(self, pairs, plan, probs) -> List[List[Dict[str, Any]]]:

@@ -99,6 +99,8 @@ class B200VectorStore(VectorStore):
         self._lock = threading.RLock()
         self._mask_cache: Optional[tuple] = None   # (filter, rows, deletions) -> exclude mask
         self._n_deleted = 0
+        self._broken: Optional[str] = None       # set when a failed insert left the store in a state it cannot repair
+        self._columns: Dict[Any, Any] = {}       # filter pushdown: payload columns as numpy arrays (see _column)
         self._store: Optional[_DiskStore] = None
         if db_path:
             self._store = _DiskStore(db_path, collection_name, dense_dim if enable_dense else 0,
@@ -126,7 +128,10 @@ class B200VectorStore(VectorStore):
             self._meta.append(row["metadata"])
             self._promoted.append(row["promoted"])
             self._alive.append(True)
-        dead = [r for r in st.read_tombstones() if 0 <= r < n]
+        all_dead = st.read_tombstones()
+        dead = [r for r in all_dead if 0 <= r < n]
+        if len(dead) != len(all_dead):   # tombstones past the recovered rows (crash mid-insert): new rows will reuse those
+            st.rewrite_tombstones(dead)  # numbers, so the stale entries must not survive
         self._kill_rows(sorted(set(dead)), persist=False)
         for r in dead:
             if self._row_of.get(self._ids[r]) == r:
@@ -146,12 +151,14 @@ class B200VectorStore(VectorStore):
             indptr = np.zeros(len(ids) + 1, dtype=np.int64)
             idx: List[int] = []
             val: List[float] = []
+            if len(sparse_vectors) != len(ids):
+                raise ValueError(f"{len(sparse_vectors)} sparse vectors for {len(ids)} ids")
             for i, sv in enumerate(sparse_vectors):
                 ks = sorted(sv.keys())
                 idx.extend(int(k) for k in ks)
                 val.extend(float(sv[k]) for k in ks)
                 indptr[i + 1] = len(idx)
-            csr = (indptr, np.asarray(idx, dtype=np.int32), np.asarray(val, dtype=np.float32))
+            csr = (indptr, np.asarray(idx, dtype=np.int64), np.asarray(val, dtype=np.float32))
         dense = np.asarray(dense_vectors, dtype=np.float32) if self.enable_dense else None
         self._insert(ids, dense, csr, texts, enhanced_texts, metadatas)
 
@@ -160,36 +167,101 @@ class B200VectorStore(VectorStore):
         self._insert(ids, dense, (indptr, indices, values), texts, enhanced_texts, metadatas)
 
     def _insert(self, ids, dense, csr, texts, enhanced_texts, metadatas):
+        """All-or-nothing insert.  Everything that can be wrong with the INPUT is checked before the device is touched
+        (list lengths, dense shape, CSR shape / monotonicity, term ids inside [0, sparse_dim)), and the host payload is
+        prepared first.  A failure after that point can only come from the device (out of memory) or the disk; the
+        rows that were already appended to one index are then tombstoned and padded so that the dense block, the
+        sparse block and the payload lists keep the same row numbering."""
         n = len(ids)
+        if not (len(texts) == len(enhanced_texts) == len(metadatas) == n):
+            raise ValueError(f"ids / texts / enhanced_texts / metadatas must have the same length ({n}, {len(texts)}, "
+                             f"{len(enhanced_texts)}, {len(metadatas)})")
+        if self._broken:
+            raise RuntimeError(f"B200VectorStore is unusable after a failed insert: {self._broken}")
+        if self._dense is not None:
+            if dense is None:
+                raise ValueError(f"dense vectors must be [{n}, {self.dense_dim}]")
+            dense = np.ascontiguousarray(dense, dtype=np.float32)
+            if dense.shape != (n, self.dense_dim):
+                raise ValueError(f"dense vectors must be [{n}, {self.dense_dim}]")
+        if self._sparse is not None:
+            if csr is None or len(csr[0]) != n + 1:
+                raise ValueError("sparse vectors missing / wrong row count")
+            indptr = np.ascontiguousarray(csr[0], dtype=np.int64)
+            indices, values = np.asarray(csr[1]), np.ascontiguousarray(csr[2], dtype=np.float32)
+            a, b = int(indptr[0]), int(indptr[-1])
+            if a < 0 or b > len(indices) or len(indices) != len(values) or (n and bool((np.diff(indptr) < 0).any())):
+                raise ValueError("sparse vectors: indptr must be non-decreasing and stay inside indices / values")
+            if b > a and (int(indices[a:b].min()) < 0 or int(indices[a:b].max()) >= self.sparse_dim):
+                raise ValueError(f"sparse vectors: term ids must lie in [0, {self.sparse_dim})")
+            csr = (indptr, np.ascontiguousarray(indices, dtype=np.int32), values)
+        rows = []
+        for i in range(n):   # host payload first: metadata that cannot be handled fails before anything is stored
+            promoted, cleaned = promote_metadata(metadatas[i])
+            rows.append((ids[i], _truncate(texts[i], "text", ids[i]), _truncate(enhanced_texts[i], "enhanced_text", ids[i]),
+                         json_serialize_safe(cleaned), promoted))
         with self._lock:
-            if self._dense is not None:
-                if dense is None or dense.shape != (n, self.dense_dim):
-                    raise ValueError(f"dense vectors must be [{n}, {self.dense_dim}]")
-                self._dense.add_dense(dense)
-            if self._sparse is not None:
-                if csr is None or len(csr[0]) != n + 1:
-                    raise ValueError("sparse vectors missing / wrong row count")
-                self._sparse.add_sparse(*csr)
             first_row = len(self._ids)
-            for i in range(n):
-                promoted, cleaned = promote_metadata(metadatas[i])
-                cid = ids[i]
+            try:
+                if self._dense is not None:
+                    self._dense.add_dense(dense)
+                if self._sparse is not None:
+                    self._sparse.add_sparse(*csr)
+            except Exception as exc:
+                self._rollback(first_row, n, exc)
+                raise
+            dead: List[int] = []
+            for cid, text, enh, meta, promoted in rows:
                 old = self._row_of.get(cid)
                 if old is not None:   # primary-key upsert: the newest row wins
-                    self._kill_rows([old])
+                    dead.append(old)
                 self._row_of[cid] = len(self._ids)
                 self._ids.append(cid)
-                self._texts.append(_truncate(texts[i], "text", cid))
-                self._enh.append(_truncate(enhanced_texts[i], "enhanced_text", cid))
-                self._meta.append(json_serialize_safe(cleaned))
+                self._texts.append(text)
+                self._enh.append(enh)
+                self._meta.append(meta)
                 self._promoted.append(promoted)
                 self._alive.append(True)
+            self._kill_rows(dead, persist=False)
             if self._store is not None:
-                self._store.append_rows(
-                    dense if self._dense is not None else None, csr if self._sparse is not None else None,
-                    [{"id": self._ids[r], "text": self._texts[r], "enhanced_text": self._enh[r],
-                      "metadata": self._meta[r], "promoted": self._promoted[r]} for r in range(first_row, first_row + n)])
+                try:
+                    self._store.append_rows(
+                        dense if self._dense is not None else None, csr if self._sparse is not None else None,
+                        [{"id": r[0], "text": r[1], "enhanced_text": r[2], "metadata": r[3], "promoted": r[4]} for r in rows])
+                    if dead:   # tombstones only after the rows they may refer to are durable
+                        self._store.append_tombstones(dead)
+                except Exception as exc:
+                    # memory now holds rows the disk does not: searches keep working, persistence cannot be trusted
+                    self._broken = f"disk append failed ({exc}); reopen the store from {self.db_path}"
+                    raise
         logger.info("Added %d vectors to B200VectorStore", n)
+
+    def _rollback(self, first_row: int, n: int, exc: Exception):
+        """Bring both indexes to first_row + n rows, all n of them tombstoned, with dead placeholder payload, so that
+        row numbers stay aligned after a device-side failure in the middle of an insert."""
+        try:
+            for ix, kind in ((self._dense, "dense"), (self._sparse, "sparse")):
+                if ix is None:
+                    continue
+                missing = first_row + n - len(ix)
+                if missing > 0:
+                    if kind == "dense":
+                        ix.add_dense(np.zeros((missing, self.dense_dim), np.float32))
+                    else:
+                        ix.add_sparse(np.zeros(missing + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32))
+                ix.mark_deleted(list(range(first_row, first_row + n)))
+            for i in range(n):
+                self._ids.append(f"__failed_insert_{first_row + i}")
+                self._texts.append("")
+                self._enh.append("")
+                self._meta.append({})
+                self._promoted.append({})
+                self._alive.append(False)
+            self._n_deleted += n
+            if self._store is not None:
+                self._broken = f"insert failed on the device ({exc}); the on-disk store was left untouched, reopen it"
+        except Exception as exc2:  # the padding failed too (e.g. still out of memory): refuse further use
+            self._broken = f"insert failed ({exc}) and the indexes could not be re-aligned ({exc2})"
 
     def _kill_rows(self, rows: Sequence[int], persist: bool = True):
         rows = [r for r in rows if self._alive[r]]
@@ -324,6 +396,26 @@ class B200VectorStore(VectorStore):
             return self._to_results(hits)
 
     # -- metadata filter pushdown -------------------------------------------------------
+    def _column(self, meta_key: Optional[str], field: Optional[str]) -> np.ndarray:
+        """Payload column as an object array, row-aligned (built once per field and extended as rows arrive), so that a
+        filter expression costs a few vectorised numpy passes instead of a Python call per row."""
+        key = (meta_key, field)
+        have = self._columns.get(key)
+        n = len(self._ids)
+        start = 0 if have is None else len(have)
+        if start < n:
+            if meta_key is not None:
+                new = [self._meta[r].get(meta_key) for r in range(start, n)]
+            elif field == "id":
+                new = self._ids[start:n]
+            else:
+                new = [self._promoted[r].get(field, self._meta[r].get(field)) for r in range(start, n)]
+            col = np.empty(n - start, dtype=object)
+            col[:] = new
+            have = col if have is None else np.concatenate([have, col])
+            self._columns[key] = have
+        return have
+
     def _exclude_mask(self, filter: Optional[str]) -> Optional[np.ndarray]:
         """Row mask for the scan kernels: 1 = skip.  Evaluated on the host payload columns, cached per
         (expression, store state)."""
@@ -332,11 +424,29 @@ class B200VectorStore(VectorStore):
         key = (filter, len(self._ids), self._n_deleted)
         if self._mask_cache is not None and self._mask_cache[0] == key:
             return self._mask_cache[1]
-        pred = _compile_filter(filter)
-        mask = np.ones(len(self._ids), np.uint8)
-        for r in range(len(self._ids)):
-            if self._alive[r] and pred({"id": self._ids[r], **self._promoted[r]}, self._meta[r]):
-                mask[r] = 0
+        keep = np.asarray(self._alive, dtype=bool)
+        for mk, f, op, val in _parse_filter(filter):
+            col = self._column(mk, f)
+            if op == "in":
+                members = set(val) if _hashable_all(val) else list(val)
+                ok = np.fromiter((x in members for x in col), bool, count=len(col))
+            elif op in ("==", "!="):
+                ok = col == val
+                if not isinstance(ok, np.ndarray):   # numpy falls back to a scalar for exotic operands
+                    ok = np.fromiter((x == val for x in col), bool, count=len(col))
+                if op == "!=":
+                    ok = ~ok
+            else:   # ordering: rows whose value cannot be compared with the literal do not match (TypeError -> False)
+                num = isinstance(val, (int, float))   # Python semantics, as in the row predicate: bool is an int
+                comparable = np.fromiter((isinstance(x, (int, float)) if num else isinstance(x, type(val)) for x in col),
+                                         bool, count=len(col))
+                ok = np.zeros(len(col), bool)
+                if comparable.any():
+                    sub = col[comparable]
+                    arr = sub.astype(np.float64) if num else sub
+                    ok[comparable] = {">=": arr >= val, "<=": arr <= val, ">": arr > val, "<": arr < val}[op]
+            keep &= ok
+        mask = (~keep).astype(np.uint8)
         self._mask_cache = (key, mask)
         return mask
 
@@ -571,13 +681,16 @@ class _DiskStore:
         if self.dense_dim and self._size("dense.f32") != n * 4 * self.dense_dim:
             with open(self._p("dense.f32"), "ab") as f:
                 f.truncate(n * 4 * self.dense_dim)
-        if self.sparse_dim and self._size("sparse.indptr.i64") != n * 8:
+        if self.sparse_dim:
+            # indices / values are written BEFORE indptr: a crash in between leaves an orphan tail on them even though
+            # indptr has its expected size, so each file is checked against its own expected length
             nnz = 0
             if n:
                 nnz = int(np.memmap(self._p("sparse.indptr.i64"), np.int64, "r", shape=(n,))[n - 1])
             for name, item in (("sparse.indptr.i64", n * 8), ("sparse.indices.i32", nnz * 4), ("sparse.values.f32", nnz * 4)):
-                with open(self._p(name), "ab") as f:
-                    f.truncate(item)
+                if self._size(name) != item:
+                    with open(self._p(name), "ab") as f:
+                        f.truncate(item)
         if os.path.exists(self._p("payload.jsonl")):
             with open(self._p("payload.jsonl"), "rb") as f:
                 data = f.read()
@@ -613,17 +726,26 @@ class _DiskStore:
         with open(self._p("tombstones.i64"), "ab") as f:
             np.asarray(list(rows), np.int64).tofile(f)
 
+    def rewrite_tombstones(self, rows: Sequence[int]):
+        tmp = self._p("tombstones.i64.tmp")
+        with open(tmp, "wb") as f:
+            np.asarray(list(rows), np.int64).tofile(f)
+        os.replace(tmp, self._p("tombstones.i64"))
+
     def append_document(self, doc: Dict[str, Any]):
         with open(self._p("documents.jsonl"), "a", encoding="utf-8") as f:
             f.write(json.dumps(doc, ensure_ascii=False, default=str) + "\n")
 
 
-def _compile_filter(expr: Optional[str]):
-    """Tiny subset of the Milvus boolean expression language used by the reference's own callers
-    (verbatim_rag/index.py:735-738): ``field == "value"`` / ``field == number`` / ``field in [..]``,
-    ``metadata["key"] <op> value``, joined by ``and``."""
-    if not expr or not expr.strip():
-        return lambda row, md: True
+def _hashable_all(vals) -> bool:
+    try:
+        return all(isinstance(v, (str, int, float, bool)) for v in vals)
+    except TypeError:
+        return False
+
+
+def _parse_filter(expr: str):
+    """-> [(metadata key | None, field | None, op, literal)] for the clauses of ``expr`` (joined by ``and``)."""
     import ast
     import re
 
@@ -635,6 +757,16 @@ def _compile_filter(expr: Optional[str]):
             raise ValueError(f"unsupported filter clause: {c!r}")
         val = ast.literal_eval(m.group("v"))
         tests.append((m.group("mk"), m.group("f"), m.group("op"), val))
+    return tests
+
+
+def _compile_filter(expr: Optional[str]):
+    """Tiny subset of the Milvus boolean expression language used by the reference's own callers
+    (verbatim_rag/index.py:735-738): ``field == "value"`` / ``field == number`` / ``field in [..]``,
+    ``metadata["key"] <op> value``, joined by ``and``."""
+    if not expr or not expr.strip():
+        return lambda row, md: True
+    tests = _parse_filter(expr)
 
     def pred(row, md):
         for mk, f, op, val in tests:
