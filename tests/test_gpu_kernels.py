@@ -313,6 +313,43 @@ def test_dense_topk_tensor_core_scan_near_ties(ctx, nq, monkeypatch):
     ix.close()
 
 
+@pytest.mark.parametrize("n,dim,nq,k", [(20011, 768, 64, 10), (5000, 384, 200, 20), (300, 768, 70, 10),
+                                         (70001, 768, 1000, 10), (9000, 768, 130, 40)])
+def test_dense_topk_batched_gemm_search(ctx, n, dim, nq, k, monkeypatch):
+    """>= 64 queries per call: scores come from ONE split-precision GEMM over fp16 hi / lo planes of the normalised
+    corpus (tensor-bound regime of SURVEY.md 8d) instead of 16-query corpus passes.  Near-tied clusters (top scores
+    ~1e-5 apart), ragged sizes (n % 256 != 0, nq % 128 != 0), rows added in two calls (planes extend), deleted rows,
+    exact duplicates, k above the register-list limit: ids equal the float64 oracle's and the scan paths', scores
+    are the same fp64 re-scored values bit for bit."""
+    from verbatim_rag_b200 import _native
+    from oracle.flat_topk import dense_cosine_scores
+    rng = np.random.default_rng(n + nq)
+    centres = rng.standard_normal((nq, dim)).astype(np.float32)
+    corpus = (centres[rng.integers(0, nq, n)] + 0.01 * rng.standard_normal((n, dim))).astype(np.float32)
+    corpus[100] = corpus[50]
+    corpus[7] = 0.0
+    queries = centres.copy()
+    ix = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    first = n // 3
+    ix.add_dense(corpus[:first])
+    ix.search_dense(queries, k)                   # planes built for the first part only
+    ix.add_dense(corpus[first:])
+    dead = [3, 50, n - 2]
+    ix.mark_deleted(dead)
+    ids_g, s_g, s64_g = ix.search_dense(queries, k, want64=True)
+    monkeypatch.setenv("VRAG_SCAN_BIG_MIN", "0")
+    ids_s, s_s, s64_s = ix.search_dense(queries, k, want64=True)
+    monkeypatch.delenv("VRAG_SCAN_BIG_MIN")
+    ix.close()
+    _diag(test="dense_topk_batched_gemm", n=n, dim=dim, nq=nq, k=k, gemm_equals_scan=bool(np.array_equal(ids_g, ids_s)))
+    assert np.array_equal(ids_g, ids_s) and np.array_equal(s64_g, s64_s) and np.array_equal(s_g, s_s)
+    sc = dense_cosine_scores(corpus, queries)
+    sc[:, dead] = -np.inf
+    for qi in range(0, nq, max(1, nq // 40)):
+        order = np.lexsort((np.arange(n), -sc[qi]))[:k]
+        assert np.array_equal(ids_g[qi], order), qi
+
+
 def test_dense_topk_ties_and_deletes(ctx):
     from verbatim_rag_b200 import _native
     from oracle.flat_topk import dense_cosine_scores, dense_cosine_topk

@@ -245,6 +245,26 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
       }
       if (valid) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32, v);
     }
+  } else if constexpr (EPI == EPI_SCORES) {
+    // out32 row = one query, columns = corpus rows: 128 contiguous bytes per thread and chunk (ld32 % 4 == 0)
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      ld.load(c, v);
+      const int n0 = col0 + c * 32;
+      if (n0 >= p.n_valid) continue;   // warp-uniform
+      if (n0 + 32 <= p.n_valid) {
+        const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(p.col_mask + n0));
+        const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(p.col_mask + n0) + 1);
+        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) v[i] = -INFINITY;
+        if (valid) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + n0, v);
+      } else if (valid) {
+        for (int i = 0; i < 32 && n0 + i < p.n_valid; ++i)
+          p.out32[static_cast<size_t>(row) * p.ld32 + n0 + i] = __ldg(p.col_mask + n0 + i) ? -INFINITY : v[i];
+      }
+    }
   } else if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
@@ -1144,7 +1164,7 @@ template <int EPI>
 void launch_t(vrag_ctx* ctx, const __half* A, const __half* W, int M, int N, int K, const GemmEpiParams& p,
               int use_reference) {
   const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN, k_blocks = K / BK;
-  ProfScope prof(ctx, PROF_GEMM);
+  ProfScope prof(ctx, p.prof_class);
   const bool split = p.a_lo != nullptr || p.w_lo != nullptr;
   if (split) {
     VRAG_CHECK(p.a_lo && p.w_lo, VRAG_ERR_ARG, "gemm: split precision needs the low planes of both operands");
@@ -1221,6 +1241,7 @@ void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M
     VRAG_CASE(EPI_NORM_BIAS_F16)
     VRAG_CASE(EPI_NORM_BIAS_GELU_F16)
     VRAG_CASE(EPI_RESID_STATS_LN)
+    VRAG_CASE(EPI_SCORES)
 #undef VRAG_CASE
     default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
   }

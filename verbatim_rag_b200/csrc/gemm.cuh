@@ -33,6 +33,8 @@ enum GemmEpi : int {
   // gamma (and beta folded into their bias), the residual GEMM normalises the old stream on the fly.
   EPI_NORM_BIAS_F16 = 14,       // out16 = rstd[row] * acc + bias                     (BERT q|k|v)
   EPI_NORM_BIAS_GELU_F16 = 15,  // out16 = gelu(rstd[row] * acc + bias)               (BERT intermediate)
+  EPI_SCORES = 17,              // similarity scan as a GEMM (topk.cu, batched dense search): out32[m][n] = acc for the
+                                // n_valid real columns, -inf where col_mask[n] != 0 (deleted / filtered corpus rows)
   EPI_RESID_STATS_LN = 16,      // EPI_RESID_STATS with x_old = ((hi + lo) - mean[row]) * rstd[row] * gamma[col] + bias[col]
                                 // (bias = beta + the dense bias); reads stats_in, writes stats_out (different buffers)
 };
@@ -59,7 +61,9 @@ struct GemmEpiParams {
   const int32_t* seq_of_row = nullptr;  // [M] sequence index of each token (SPLADE pooling)
   float* splade_out = nullptr;        // [nseq, splade_ld], zero-initialised
   int splade_ld = 0;
-  int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail)
+  int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail, EPI_SCORES corpus tail)
+  const uint8_t* col_mask = nullptr;  // EPI_SCORES: [n_valid] bytes, != 0 -> the column scores -inf
+  int prof_class = 0;                 // profiler class the launch is booked under (common.cuh ProfClass; 0 = GEMM)
   const float* stats_in = nullptr;    // EPI_NORM_*: [stats_slots][M] float2 partial row moments of the A operand's rows
   float* stats_out = nullptr;         // EPI_RESID_STATS: [N / 128][M] float2
   int stats_slots = 6;

@@ -15,7 +15,10 @@
 #include <algorithm>
 #include <memory>
 
+#include <atomic>
+
 #include "common.cuh"
+#include "gemm.cuh"
 #include "ptx.cuh"
 
 using namespace vrag;
@@ -276,6 +279,7 @@ dense_scan_tma_kernel(const float* __restrict__ rows, int64_t n, const float* __
 //                               swizzled 4 KB tiles)
 //   warps 10..13: epilogue     — tcgen05.ld, (D1[q] + D1[16+q] + D2[q]) * 1/|q| * 1/|x| -> scores[q][row] (coalesced
 //                               along rows); two TMEM accumulator buffers, so it overlaps the next tile's MMAs
+constexpr int BIG_MIN_Q = 64;                  // smallest batch sent to the split-precision GEMM search
 constexpr int TCQ = 16;
 constexpr int TC_MIN_Q = 5;                    // smallest query tile sent to the tensor-core scan
 constexpr int TC_ROWS = 128;
@@ -585,7 +589,7 @@ __device__ __forceinline__ void list_insert(uint64_t* L, int kp, uint64_t x, int
 
 template <bool FROM_SCORES>
 __global__ void __launch_bounds__(32 * SEL_WARPS)
-select_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int kp,
+select_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int64_t stride, int kp,
               uint64_t* __restrict__ keys_out /* [nq][gridDim.x][kp] */) {
   extern __shared__ uint64_t lists[];  // [SEL_WARPS][kp]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -603,10 +607,10 @@ select_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ key
     uint64_t key = 0;
     if (i < w1) {
       if (FROM_SCORES) {
-        const float s = scores[static_cast<size_t>(q) * n + i];
+        const float s = scores[static_cast<size_t>(q) * stride + i];
         key = (s == -INFINITY) ? 0 : make_key(s, static_cast<uint32_t>(i));
       } else {
-        key = keys_in[static_cast<size_t>(q) * n + i];
+        key = keys_in[static_cast<size_t>(q) * stride + i];
       }
     }
     unsigned m = __ballot_sync(0xffffffffu, key > thr);
@@ -648,8 +652,8 @@ __device__ __forceinline__ uint64_t reg_list_insert(uint64_t mine, uint64_t x, i
 
 template <bool FROM_SCORES>
 __global__ void __launch_bounds__(32 * SEL_WARPS)
-select_reg_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int kp,
-                  uint64_t* __restrict__ keys_out /* [nq][gridDim.x][kp] */) {
+select_reg_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ keys_in, int64_t n, int64_t stride,
+                  int kp, uint64_t* __restrict__ keys_out /* [nq][gridDim.x][kp] */) {
   __shared__ uint64_t lists[SEL_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.y;
@@ -668,8 +672,8 @@ select_reg_kernel(const float* __restrict__ scores, const uint64_t* __restrict__
 #pragma unroll
     for (int u = 0; u < SEL_UNROLL; ++u) {
       const int64_t i = min(i0 + u * 32 + lane, w1 - 1);
-      if (FROM_SCORES) sc[u] = __ldcs(scores + static_cast<size_t>(q) * n + i);
-      else key[u] = __ldcs(keys_in + static_cast<size_t>(q) * n + i);
+      if (FROM_SCORES) sc[u] = __ldcs(scores + static_cast<size_t>(q) * stride + i);
+      else key[u] = __ldcs(keys_in + static_cast<size_t>(q) * stride + i);
     }
 #pragma unroll
     for (int u = 0; u < SEL_UNROLL; ++u) {
@@ -899,6 +903,29 @@ dense_finish_kernel(const uint64_t* __restrict__ keys_in, int64_t n_keys, int kp
   }
 }
 
+// Batched search (vrag_index_search_dense, >= BIG_MIN_Q queries): the corpus as split-precision planes of the
+// NORMALISED rows, x / |x| = hi + lo (fp16 each, >= 21 significant bits), the B operand of the split GEMM of gemm.cu.
+__global__ void __launch_bounds__(256)
+normalize_split_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm, int64_t r0, int64_t r1,
+                       int dim, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t i4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index inside [r0, r1)
+  const int per_row = dim / 4;
+  const int64_t row = r0 + i4 / per_row;
+  if (row >= r1) return;
+  const size_t o = static_cast<size_t>(row) * dim + static_cast<size_t>(i4 % per_row) * 4;
+  const float4 x = *reinterpret_cast<const float4*>(rows + o);
+  const float s = inv_norm ? inv_norm[row] : 1.f;
+  const float v[4] = {x.x * s, x.y * s, x.z * s, x.w * s};
+  __half h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __float2half_rn(v[e]);
+    l[e] = __float2half_rn(v[e] - __half2float(h[e]));
+  }
+  *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+}
+
 __global__ void query_norm_kernel(const float* __restrict__ queries, int dim, float* __restrict__ inv_norm_q) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
@@ -920,6 +947,9 @@ struct vrag_index {
   int64_t n = 0, cap = 0;
   int64_t id_base = 0;  // added to row numbers in results (global id of this shard's row 0)
   DevBuf rows, norm64, inv32, deleted;
+  // batched search: split-precision planes of the normalised rows [planes_cap, dim] (built lazily, rows [0, planes_n))
+  DevBuf rows_hi, rows_lo, q_hi, q_lo;
+  int64_t planes_n = 0, planes_cap = 0;
   // metadata-filter pushdown (vrag_index_set_filter): masked = deleted | excluded, consulted instead of `deleted`
   DevBuf masked, excl;
   bool filter_on = false;
@@ -931,7 +961,8 @@ struct vrag_index {
   DevBuf scores, keys0, keys1, s64, crow, qdev, qnorm, qT, qip, qidx, qval, out_ids, out_s32, out_s64;
   ~vrag_index() {
     for (DevBuf* b : {&rows, &norm64, &inv32, &deleted, &masked, &excl, &indptr, &indices, &values, &scores, &keys0, &keys1, &s64,
-                      &crow, &qdev, &qnorm, &qT, &qip, &qidx, &qval, &out_ids, &out_s32, &out_s64})
+                      &crow, &qdev, &qnorm, &qT, &qip, &qidx, &qval, &out_ids, &out_s32, &out_s64, &rows_hi, &rows_lo, &q_hi,
+                      &q_lo})
       b->release();
   }
 };
@@ -953,9 +984,10 @@ void grow(vrag_ctx* ctx, DevBuf& b, size_t used_bytes, size_t need_bytes) {
 // scores [nq_tile][n] on device -> final top-k for the tile written at out offsets
 void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bool dense,
                      const float* queries_dev /*dense*/, int64_t* ids_out, float* s32_out,
-                     double* s64_out /*device, tile offset applied*/, cudaStream_t st) {
+                     double* s64_out /*device, tile offset applied*/, cudaStream_t st, int64_t stride = 0) {
   vrag_ctx* ctx = ix->ctx;
   const int64_t n = ix->n;
+  if (stride == 0) stride = n;   // floats between the score rows of consecutive queries
   const int kp = static_cast<int>(std::min<int64_t>(k + MARGIN, std::max<int64_t>(n, 1)));
   // scores per block: 16 384 with register lists (2 048 per warp = 8 rounds of 8 loads in flight per lane; ~110
   // insertions, 5 % of the keys; 16 queries x 62 blocks at 1 M rows are one wave of the GPU), 8 192 with
@@ -963,24 +995,25 @@ void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bo
   const int64_t per_blk = kp <= 32 ? SEL_REG_BLOCK : 8192;
   const int nblk0 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + per_blk - 1) / per_blk, ctx->num_sms * 4)));
   const size_t smem = static_cast<size_t>(SEL_WARPS) * kp * 8;
-  static bool smem_attr = false;
-  if (!smem_attr) {
+  static std::atomic<uint64_t> smem_attr{0};   // cudaFuncSetAttribute is per device
+  const uint64_t dev_bit = 1ull << (ctx->device & 63);
+  if ((smem_attr.fetch_or(dev_bit) & dev_bit) == 0) {
     VRAG_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     VRAG_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    smem_attr = true;
   }
   ix->keys0.reserve(static_cast<size_t>(nq_tile) * nblk0 * kp * 8);
   ix->keys1.reserve(static_cast<size_t>(nq_tile) * kp * 8);
   ProfScope prof(ctx, PROF_SELECT, st);
   if (kp <= 32)
     select_reg_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, 0, st>>>(
-        scores, nullptr, n, kp, ix->keys0.as<uint64_t>());
+        scores, nullptr, n, stride, kp, ix->keys0.as<uint64_t>());
   else
     select_kernel<true><<<dim3(nblk0, nq_tile), 32 * SEL_WARPS, smem, st>>>(
-        scores, nullptr, n, kp, ix->keys0.as<uint64_t>());
+        scores, nullptr, n, stride, kp, ix->keys0.as<uint64_t>());
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
   if (dense && kp <= 32) {   // merge + fp64 re-score + rank in one launch
+    ProfScope prof_fin(ctx, PROF_OTHER, st);
     dense_finish_kernel<<<nq_tile, 32 * FIN_WARPS, 0, st>>>(ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp,
                                                             kp, k, ix->rows.as<float>(), ix->dim,
                                                             ix->norm64.as<double>(), queries_dev, ix->id_base, ids_out,
@@ -993,10 +1026,12 @@ void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bo
   if (nblk0 > 1) {
     if (kp <= 32)
       select_reg_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, 0, st>>>(
-          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
+          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, static_cast<int64_t>(nblk0) * kp, kp,
+          ix->keys1.as<uint64_t>());
     else
       select_kernel<false><<<dim3(1, nq_tile), 32 * SEL_WARPS, smem, st>>>(
-          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, kp, ix->keys1.as<uint64_t>());
+          nullptr, ix->keys0.as<uint64_t>(), static_cast<int64_t>(nblk0) * kp, static_cast<int64_t>(nblk0) * kp, kp,
+          ix->keys1.as<uint64_t>());
     VRAG_CUDA(cudaGetLastError());
     ctx->launches++;
     final_keys = ix->keys1.as<uint64_t>();
@@ -1217,6 +1252,71 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
   query_norm_kernel<<<nq, 32, 0, _ctx->stream>>>(qd, dim, idx->qnorm.as<float>());
   VRAG_CUDA(cudaGetLastError());
   _ctx->launches++;
+  // ---- batched search, tensor-bound regime ("all 1 k queries in one pass"): >= BIG_MIN_Q queries -------
+  // scores = Q X_n^T as ONE split-precision GEMM per group of <= 1024 queries (gemm.cu, three tcgen05.mma per product
+  // over fp16 hi / lo planes: >= 21 significant bits, at the fp16 tensor rate instead of three tf32 passes).  X_n are
+  // the normalised corpus rows, kept as planes beside the fp32 originals; the fp32 rows still feed the fp64 re-scoring
+  // of the k + 16 candidates, so ids and scores are the same as on the scan paths.  Per 1024 queries the corpus planes
+  // (= N dim 4 bytes, as much as one fp32 pass) are read 4 times instead of 64.
+  const char* big_env = getenv("VRAG_SCAN_BIG_MIN");   // debug: 0 disables the GEMM path, else its smallest batch
+  const int big_min = big_env ? atoi(big_env) : BIG_MIN_Q;
+  if (big_min > 0 && nq >= big_min && dim % GEMM_BK == 0 && n < (int64_t(1) << 31) - GEMM_BN) {
+    const int64_t n_pad = (n + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+    if (idx->planes_cap < n_pad) {   // (re)allocate with head room, zero the padding rows, rebuild from row 0
+      const int64_t cap = std::max<int64_t>(n_pad, idx->planes_cap + idx->planes_cap / 2) / GEMM_BN * GEMM_BN + GEMM_BN;
+      idx->rows_hi.release();
+      idx->rows_lo.release();
+      idx->rows_hi.reserve(static_cast<size_t>(cap) * dim * 2);
+      idx->rows_lo.reserve(static_cast<size_t>(cap) * dim * 2);
+      VRAG_CUDA(cudaMemsetAsync(idx->rows_hi.p, 0, static_cast<size_t>(cap) * dim * 2, _ctx->stream));
+      VRAG_CUDA(cudaMemsetAsync(idx->rows_lo.p, 0, static_cast<size_t>(cap) * dim * 2, _ctx->stream));
+      idx->planes_cap = cap;
+      idx->planes_n = 0;
+    }
+    if (idx->planes_n < n) {
+      const int64_t cnt4 = (n - idx->planes_n) * (dim / 4);
+      normalize_split_kernel<<<static_cast<unsigned>((cnt4 + 255) / 256), 256, 0, _ctx->stream>>>(
+          idx->rows.as<float>(), idx->inv32.as<float>(), idx->planes_n, n, dim, idx->rows_hi.as<__half>(),
+          idx->rows_lo.as<__half>());
+      VRAG_CUDA(cudaGetLastError());
+      _ctx->launches++;
+      idx->planes_n = n;
+    }
+    const int group = static_cast<int>(std::max<int64_t>(GEMM_BM, std::min<int64_t>(1024, ((int64_t(4) << 30) / (n_pad * 4)) / GEMM_BM * GEMM_BM)));
+    idx->scores.reserve(static_cast<size_t>(std::min(group, nq)) * n_pad * 4);
+    idx->q_hi.reserve(static_cast<size_t>(nq) * dim * 2);
+    idx->q_lo.reserve(static_cast<size_t>(nq) * dim * 2);
+    const int64_t q4 = static_cast<int64_t>(nq) * (dim / 4);
+    normalize_split_kernel<<<static_cast<unsigned>((q4 + 255) / 256), 256, 0, _ctx->stream>>>(
+        qd, nullptr, 0, nq, dim, idx->q_hi.as<__half>(), idx->q_lo.as<__half>());
+    VRAG_CUDA(cudaGetLastError());
+    _ctx->launches++;
+    for (int q0 = 0; q0 < nq; q0 += group) {
+      const int nt = std::min(group, nq - q0);
+      GemmEpiParams gp;
+      gp.M = nt;
+      gp.out32 = idx->scores.as<float>();
+      gp.ld32 = static_cast<int>(n_pad);
+      gp.n_valid = static_cast<int>(n);
+      gp.col_mask = idx->skip();
+      gp.a_lo = idx->q_lo.as<__half>() + static_cast<size_t>(q0) * dim;
+      gp.w_lo = idx->rows_lo.as<__half>();
+      gp.prof_class = PROF_SCAN;
+      launch_gemm(_ctx, EPI_SCORES, idx->q_hi.as<__half>() + static_cast<size_t>(q0) * dim, idx->rows_hi.as<__half>(), nt,
+                  static_cast<int>(n_pad), dim, gp, 0);
+      select_and_rank(idx, idx->scores.as<float>(), nt, k, true, qd + static_cast<size_t>(q0) * dim,
+                      d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
+                      d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr, _ctx->stream, n_pad);
+    }
+    if (!on_device) {
+      VRAG_CUDA(cudaMemcpyAsync(ids_out, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+      VRAG_CUDA(cudaMemcpyAsync(scores_out, d_s32, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, _ctx->stream));
+      if (scores64_out)
+        VRAG_CUDA(cudaMemcpyAsync(scores64_out, d_s64, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+      VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+    }
+    return VRAG_OK;
+  }
   // TC_MIN_Q or more queries left: 16 per corpus pass on the tensor cores (the split query block must fit in smem);
   // fewer: the FMA scan, which is faster for 1..4 queries (measured: profiles/README.md)
   const char* tc_env = getenv("VRAG_SCAN_TC_MIN");  // debug: 0 forces the FMA path, else the smallest tile for TC
@@ -1246,11 +1346,10 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       const CUtensorMap tmX = make_tmap_2d(_ctx, idx->rows.as<float>(), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                                            static_cast<uint64_t>(n), dim, dim, TC_ROWS, 32);
       const int smem = TC_STAGES * TC_TILE_BYTES + (dim / 32) * TC_BTILE_BYTES + 256 + 1024;
-      static bool attr = false;
-      if (!attr) {
+      static std::atomic<uint64_t> attr{0};   // cudaFuncSetAttribute is per device
+      const uint64_t dev_bit = 1ull << (_ctx->device & 63);
+      if ((attr.fetch_or(dev_bit) & dev_bit) == 0)
         VRAG_CUDA(cudaFuncSetAttribute(dense_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-      }
       const int tgrid = static_cast<int>(std::min<int64_t>((n + TC_ROWS - 1) / TC_ROWS, _ctx->num_sms));
       dense_scan_tc_kernel<<<tgrid, TC_THREADS, smem, _ctx->stream>>>(tmX, n, dim, qt, nt, idx->inv32.as<float>(), qn,
                                                                       idx->skip(), scores);
