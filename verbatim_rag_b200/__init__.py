@@ -15,6 +15,7 @@ _LAZY = {
     "B200SpladeProvider": ("providers", "B200SpladeProvider"),
     "B200DenseProvider": ("providers", "B200DenseProvider"),
     "B200VectorStore": ("vector_store", "B200VectorStore"),
+    "ShardedB200VectorStore": ("sharded_store", "ShardedB200VectorStore"),
     "sharded_search_dense": ("distributed", "sharded_search_dense"),
     "sharded_search_sparse": ("distributed", "sharded_search_sparse"),
 }

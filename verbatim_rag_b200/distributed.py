@@ -3,8 +3,8 @@ Multi-GPU exact top-k: corpus row-sharded across ranks, queries replicated, ONE 
 
 One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Each rank searches its shard
 (``vrag_index_search_*`` with ``id_base`` = global id of its row 0) producing per-query top-k
-``(score64, global id)``; an ``all_gather`` of those ``[Q, k]`` blocks (120 KB per rank at 1000 queries, k = 10)
-is the only exchange on the path; every rank then merges the ``world * k`` candidates with
+``(score64, global id)``; ONE ``all_gather`` of those blocks, packed as 16-byte (score64, id) records (160 KB per rank at
+1000 queries, k = 10), is the only exchange on the path; every rank then merges the ``world * k`` candidates with
 ``vrag_topk_merge`` using the same order (score desc, id asc).  Because per-shard scores are fp64 re-scored, the
 merged result is bit-identical to the single-GPU search over the concatenated corpus.
 
@@ -41,49 +41,79 @@ def merge_host(scores64: np.ndarray, ids: np.ndarray, k: int) -> Tuple[np.ndarra
     return out_i, out_s.astype(np.float32), out_s
 
 
-def gather_and_merge(local_ids: torch.Tensor, local_s64: torch.Tensor, k: int, group=None, ctx=None):
-    """all_gather the per-rank [Q, k] (id int64, score fp64) blocks and merge to the global top-k.
+def _lib_stream(ctx, device):
+    """The library's stream as a torch stream: torch ops and the NCCL collective issued under it are ordered with the
+    search / merge kernels on the device, so nothing between scan, gather and merge waits on the host."""
+    return torch.cuda.ExternalStream(ctx.stream, device=device)
 
-    CUDA tensors + ``ctx`` (a ``_native.Context``): NCCL all_gather and the device merge kernel.
-    CPU tensors: gloo all_gather and the host merge.  Returns (ids [Q,k] int64, scores fp32, scores fp64).
+
+def gather_and_merge(local_ids: torch.Tensor, local_s64: torch.Tensor, k: int, group=None, ctx=None):
+    """all_gather the per-rank top-k blocks and merge them to the global top-k.
+
+    ONE collective: each rank contributes a packed ``[Q, k, 2]`` int64 block (fp64 score bits, global id) = 16 bytes per
+    candidate (160 KB per rank at 1000 queries, k = 10).  CUDA tensors + ``ctx`` (a ``_native.Context``): everything is
+    enqueued on the library's stream -- pack, NCCL all_gather, unpack, ``vrag_topk_merge`` -- with no host
+    synchronisation; the returned tensors are ready once that stream is (the caller's current stream is made to wait
+    for it).  CPU tensors: gloo all_gather and the host merge.  Returns (ids [Q,k] int64, scores fp32, scores fp64).
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     Q = local_ids.shape[0]
-    if world == 1:
-        all_i, all_s = local_ids, local_s64
-    else:
-        gi = torch.empty((world * Q, k), dtype=local_ids.dtype, device=local_ids.device)
-        gs = torch.empty((world * Q, k), dtype=local_s64.dtype, device=local_s64.device)
-        dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)    # rank r -> rows [r*Q, (r+1)*Q)
-        dist.all_gather_into_tensor(gs, local_s64.contiguous(), group=group)
-        all_i = gi.view(world, Q, k).permute(1, 0, 2).reshape(Q, world * k).contiguous()
-        all_s = gs.view(world, Q, k).permute(1, 0, 2).reshape(Q, world * k).contiguous()
-    if all_i.is_cuda:
-        assert ctx is not None, "device merge needs the native context"
-        out_i = torch.empty((Q, k), dtype=torch.int64, device=all_i.device)
-        out_s = torch.empty((Q, k), dtype=torch.float32, device=all_i.device)
-        out_d = torch.empty((Q, k), dtype=torch.float64, device=all_i.device)
-        torch.cuda.current_stream(all_i.device).synchronize()   # NCCL ran on torch's stream, merge runs on ours
+    if not local_ids.is_cuda:
+        packed = torch.stack((local_s64.contiguous().view(torch.int64), local_ids.contiguous()), dim=-1)
+        if world > 1:
+            g = torch.empty((world * Q, k, 2), dtype=torch.int64)
+            dist.all_gather_into_tensor(g, packed, group=group)          # rank r -> rows [r * Q, (r + 1) * Q)
+            packed = g.view(world, Q, k, 2).permute(1, 0, 2, 3).reshape(Q, world * k, 2)
+        oi, os32, os64 = merge_host(packed[..., 0].contiguous().view(torch.float64).numpy(),
+                                    packed[..., 1].contiguous().numpy(), k)
+        return torch.from_numpy(oi), torch.from_numpy(os32), torch.from_numpy(os64)
+    assert ctx is not None, "device merge needs the native context"
+    dev = local_ids.device
+    st = _lib_stream(ctx, dev)
+    st.wait_stream(torch.cuda.current_stream(dev))      # inputs produced on the caller's stream (device-side wait)
+    with torch.cuda.stream(st):
+        if world > 1:
+            packed = torch.stack((local_s64.contiguous().view(torch.int64), local_ids.contiguous()), dim=-1)
+            g = torch.empty((world * Q, k, 2), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(g, packed, group=group)          # rank r -> rows [r * Q, (r + 1) * Q)
+            g = g.view(world, Q, k, 2).permute(1, 0, 2, 3).reshape(Q, world * k, 2)
+            all_s = g[..., 0].contiguous().view(torch.float64)
+            all_i = g[..., 1].contiguous()
+        else:
+            all_s, all_i = local_s64.contiguous(), local_ids.contiguous()
+        out_i = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        out_d = torch.empty((Q, k), dtype=torch.float64, device=dev)
         ctx.topk_merge(all_s, all_i, Q, all_i.shape[1], k, out_i, out_s, out_d)
-        ctx.sync()
-        return out_i, out_s, out_d
-    oi, os32, os64 = merge_host(all_s.numpy(), all_i.numpy(), k)
-    return torch.from_numpy(oi), torch.from_numpy(os32), torch.from_numpy(os64)
+        for t in (all_s, all_i):
+            t.record_stream(st)
+    torch.cuda.current_stream(dev).wait_stream(st)
+    return out_i, out_s, out_d
 
 
-def sharded_search_dense(index, queries: torch.Tensor, k: int, group=None):
-    """``index``: this rank's ``_native.Index`` (id_base set).  ``queries`` [Q, dim] fp32 CUDA tensor, replicated."""
+def sharded_search_dense(index, queries: torch.Tensor, k: int, group=None, local_to_global: Optional[torch.Tensor] = None):
+    """``index``: this rank's ``_native.Index`` (id_base set, or ``local_to_global`` [n_local] int64 mapping its rows
+    to global ids).  ``queries`` [Q, dim] fp32 CUDA tensor, replicated.  No host synchronisation."""
     Q = queries.shape[0]
-    ids = torch.empty((Q, k), dtype=torch.int64, device=queries.device)
-    s32 = torch.empty((Q, k), dtype=torch.float32, device=queries.device)
-    s64 = torch.empty((Q, k), dtype=torch.float64, device=queries.device)
-    torch.cuda.current_stream(queries.device).synchronize()
-    index.search_dense_device(queries, Q, k, ids, s32, s64)
-    index.ctx.sync()
+    dev = queries.device
+    st = _lib_stream(index.ctx, dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(st):
+        ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        s32 = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        s64 = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        index.search_dense_device(queries, Q, k, ids, s32, s64)
+        if local_to_global is not None:
+            ids = torch.where(ids >= 0, local_to_global[ids.clamp_min(0)], ids)
+        queries.record_stream(st)
+    torch.cuda.current_stream(dev).wait_stream(st)
     return gather_and_merge(ids, s64, k, group, index.ctx)
 
 
-def sharded_search_sparse(index, q_indptr, q_indices, q_values, k: int, device, group=None):
-    """Sparse queries as host CSR (replicated); returns global (ids, fp32 scores, fp64 scores) CUDA tensors."""
+def sharded_search_sparse(index, q_indptr, q_indices, q_values, k: int, device, group=None,
+                          local_to_global: Optional[np.ndarray] = None):
+    """Sparse queries as host CSR (replicated); returns global (ids, fp32 scores, fp64 scores) tensors on ``device``."""
     ids, s32, s64 = index.search_sparse(q_indptr, q_indices, q_values, k, want64=True)
+    if local_to_global is not None:
+        ids = np.where(ids >= 0, local_to_global[np.maximum(ids, 0)], ids)
     return gather_and_merge(torch.from_numpy(ids).to(device), torch.from_numpy(s64).to(device), k, group, index.ctx)

@@ -110,6 +110,47 @@ def index_query_batch(
     return out  # type: ignore[return-value]
 
 
+def _rag_route(rag, questions: Sequence[str]):
+    """step 0 of VerbatimRAG.query (core.py:210-230): optional intent detection; -> (responses, indices still to do)"""
+    responses: List[Any] = [None] * len(questions)
+    todo: List[int] = []
+    for i, q in enumerate(questions):
+        decision = rag._detect_intent(q)
+        route = rag._decision_field(decision, "route")
+        if decision and route and route != "continue":
+            answer = rag._decision_field(decision, "answer", "") or ""
+            responses[i] = rag._build_short_circuit_response(q, answer)
+        else:
+            todo.append(i)
+    return responses, todo
+
+
+def _rag_finish(rag, questions: Sequence[str], found: Sequence[List[Any]]):
+    """steps 2-5 of VerbatimRAG.query (core.py:240-277) for questions whose retrieval is done: rerank, span extraction
+    (one batched call), template, response.  -> [(response, search_results)]"""
+    results = [rag._apply_reranker(q, r) for q, r in zip(questions, found)]
+    structured = rag.template_manager.current_mode == "structured"
+    spans: List[Dict[str, List[str]]] = []
+    if not structured and questions:
+        if hasattr(rag.extractor, "extract_spans_batch"):
+            spans = rag.extractor.extract_spans_batch(list(questions), results)
+        else:
+            spans = [rag.extractor.extract_spans(q, r) for q, r in zip(questions, results)]
+    out = []
+    for j, q in enumerate(questions):
+        if structured:
+            answer, all_spans = rag._process_structured(q, results[j])
+        else:
+            all_spans = spans[j]
+            display_spans, citation_spans = rag._rank_and_split_spans(all_spans)
+            answer = rag.template_manager.process(q, display_spans, citation_spans)
+        answer = rag.response_builder.clean_answer(answer)
+        out.append((rag.response_builder.build_response(question=q, answer=answer, search_results=results[j],
+                                                        relevant_spans=all_spans, display_span_count=len(all_spans)),
+                    results[j]))
+    return out
+
+
 def rag_query_batch(
     rag,
     questions: Sequence[str],
@@ -119,48 +160,37 @@ def rag_query_batch(
     rrf_k: int = 60,
     search_params: Optional[Dict[str, Any]] = None,
     return_search_results: bool = False,
+    group=None,
 ) -> List[Any]:
     """Batched ``VerbatimRAG.query`` (core.py:210-277): intent routing and templates stay per question (host string
-    work), retrieval and span extraction run once for the whole batch."""
+    work), retrieval and span extraction run once for the whole batch.
+
+    Under ``torch.distributed`` (one process per GPU, every rank calling this with the same questions; BASELINE
+    configs[4]) the retrieval is the sharded store's collective search over all questions, then the questions are split
+    contiguously over the ranks for span extraction + response building (independent units, no collective on that
+    path) and the responses are exchanged with one ``all_gather_object``: every rank returns the full list."""
+    import torch.distributed as dist
+    from .distributed import shard_bounds
     questions = list(questions)
     n = len(questions)
-    responses: List[Any] = [None] * n
+    responses, todo = _rag_route(rag, questions)
     results: List[List[Any]] = [[] for _ in range(n)]
-    todo: List[int] = []
-    for i, q in enumerate(questions):   # step 0: optional intent detection
-        decision = rag._detect_intent(q)
-        route = rag._decision_field(decision, "route")
-        if decision and route and route != "continue":
-            answer = rag._decision_field(decision, "answer", "") or ""
-            responses[i] = rag._build_short_circuit_response(q, answer)
-        else:
-            todo.append(i)
     if todo:
         kk = k or rag.k
         found = index_query_batch(rag.index, [questions[i] for i in todo], k=kk, filter=filter,
                                   hybrid_weights=hybrid_weights, rrf_k=rrf_k, search_params=search_params)
-        for i, r in zip(todo, found):
-            results[i] = rag._apply_reranker(questions[i], r)
-        structured = rag.template_manager.current_mode == "structured"
-        spans: Dict[int, Dict[str, List[str]]] = {}
-        if not structured:
-            if hasattr(rag.extractor, "extract_spans_batch"):
-                batch = rag.extractor.extract_spans_batch([questions[i] for i in todo], [results[i] for i in todo])
-                spans = dict(zip(todo, batch))
-            else:
-                spans = {i: rag.extractor.extract_spans(questions[i], results[i]) for i in todo}
-        for i in todo:
-            q = questions[i]
-            if structured:
-                answer, all_spans = rag._process_structured(q, results[i])
-            else:
-                all_spans = spans[i]
-                display_spans, citation_spans = rag._rank_and_split_spans(all_spans)
-                answer = rag.template_manager.process(q, display_spans, citation_spans)
-            answer = rag.response_builder.clean_answer(answer)
-            responses[i] = rag.response_builder.build_response(
-                question=q, answer=answer, search_results=results[i], relevant_spans=all_spans,
-                display_span_count=len(all_spans))
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            lo, hi = shard_bounds(len(todo), dist.get_rank(group), world)
+            mine = _rag_finish(rag, [questions[i] for i in todo[lo:hi]], found[lo:hi])
+            parts: List[Any] = [None] * world
+            dist.all_gather_object(parts, mine, group=group)
+            done = [x for part in parts for x in part]
+        else:
+            done = _rag_finish(rag, [questions[i] for i in todo], found)
+        for i, (resp, res) in zip(todo, done):
+            responses[i] = resp
+            results[i] = res
     if return_search_results:
         return [(responses[i], results[i]) for i in range(n)]
     return responses

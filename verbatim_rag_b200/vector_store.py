@@ -41,6 +41,20 @@ MAX_TEXT_LENGTH = 60000  # bytes; the reference truncates to the Milvus VARCHAR 
 _DYNAMIC_FIELDS = ["document_id", "user_id", "dataset_id"]
 
 
+def dicts_to_csr(sparse_vectors: Sequence[Dict[int, float]]):
+    """The reference's ``List[Dict[int, float]]`` sparse rows (embedding_providers.py:161-163) -> CSR (indptr int64,
+    indices int64 ascending per row, values fp32)."""
+    indptr = np.zeros(len(sparse_vectors) + 1, dtype=np.int64)
+    idx: List[int] = []
+    val: List[float] = []
+    for i, sv in enumerate(sparse_vectors):
+        ks = sorted(sv.keys())
+        idx.extend(int(k) for k in ks)
+        val.extend(float(sv[k]) for k in ks)
+        indptr[i + 1] = len(idx)
+    return indptr, np.asarray(idx, dtype=np.int64), np.asarray(val, dtype=np.float32)
+
+
 def _truncate(text: str, field: str, chunk_id: str) -> str:
     enc = text.encode("utf-8")
     if len(enc) <= MAX_TEXT_LENGTH:
@@ -148,17 +162,9 @@ class B200VectorStore(VectorStore):
             raise ValueError("Sparse vectors required but not provided")
         csr = None
         if self.enable_sparse:
-            indptr = np.zeros(len(ids) + 1, dtype=np.int64)
-            idx: List[int] = []
-            val: List[float] = []
             if len(sparse_vectors) != len(ids):
                 raise ValueError(f"{len(sparse_vectors)} sparse vectors for {len(ids)} ids")
-            for i, sv in enumerate(sparse_vectors):
-                ks = sorted(sv.keys())
-                idx.extend(int(k) for k in ks)
-                val.extend(float(sv[k]) for k in ks)
-                indptr[i + 1] = len(idx)
-            csr = (indptr, np.asarray(idx, dtype=np.int64), np.asarray(val, dtype=np.float32))
+            csr = dicts_to_csr(sparse_vectors)
         dense = np.asarray(dense_vectors, dtype=np.float32) if self.enable_dense else None
         self._insert(ids, dense, csr, texts, enhanced_texts, metadatas)
 
@@ -166,13 +172,15 @@ class B200VectorStore(VectorStore):
         """Bulk insert of sparse rows already in CSR form (``B200SpladeProvider.embed_batch_csr``)."""
         self._insert(ids, dense, (indptr, indices, values), texts, enhanced_texts, metadatas)
 
-    def _insert(self, ids, dense, csr, texts, enhanced_texts, metadatas):
-        """All-or-nothing insert.  Everything that can be wrong with the INPUT is checked before the device is touched
+    def _insert(self, ids, dense, csr, texts, enhanced_texts, metadatas, local=None):
+        """All-or-nothing insert.  ``local`` (sharded store only): ``(lo, hi)`` -- the vectors given are those of rows
+        [lo, hi) of this batch, the payload is complete.  Everything that can be wrong with the INPUT is checked before the device is touched
         (list lengths, dense shape, CSR shape / monotonicity, term ids inside [0, sparse_dim)), and the host payload is
         prepared first.  A failure after that point can only come from the device (out of memory) or the disk; the
         rows that were already appended to one index are then tombstoned and padded so that the dense block, the
         sparse block and the payload lists keep the same row numbering."""
         n = len(ids)
+        nv = n if local is None else local[1] - local[0]   # rows the vectors cover
         if not (len(texts) == len(enhanced_texts) == len(metadatas) == n):
             raise ValueError(f"ids / texts / enhanced_texts / metadatas must have the same length ({n}, {len(texts)}, "
                              f"{len(enhanced_texts)}, {len(metadatas)})")
@@ -180,17 +188,17 @@ class B200VectorStore(VectorStore):
             raise RuntimeError(f"B200VectorStore is unusable after a failed insert: {self._broken}")
         if self._dense is not None:
             if dense is None:
-                raise ValueError(f"dense vectors must be [{n}, {self.dense_dim}]")
+                raise ValueError(f"dense vectors must be [{nv}, {self.dense_dim}]")
             dense = np.ascontiguousarray(dense, dtype=np.float32)
-            if dense.shape != (n, self.dense_dim):
-                raise ValueError(f"dense vectors must be [{n}, {self.dense_dim}]")
+            if dense.shape != (nv, self.dense_dim):
+                raise ValueError(f"dense vectors must be [{nv}, {self.dense_dim}]")
         if self._sparse is not None:
-            if csr is None or len(csr[0]) != n + 1:
+            if csr is None or len(csr[0]) != nv + 1:
                 raise ValueError("sparse vectors missing / wrong row count")
             indptr = np.ascontiguousarray(csr[0], dtype=np.int64)
             indices, values = np.asarray(csr[1]), np.ascontiguousarray(csr[2], dtype=np.float32)
             a, b = int(indptr[0]), int(indptr[-1])
-            if a < 0 or b > len(indices) or len(indices) != len(values) or (n and bool((np.diff(indptr) < 0).any())):
+            if a < 0 or b > len(indices) or len(indices) != len(values) or (nv and bool((np.diff(indptr) < 0).any())):
                 raise ValueError("sparse vectors: indptr must be non-decreasing and stay inside indices / values")
             if b > a and (int(indices[a:b].min()) < 0 or int(indices[a:b].max()) >= self.sparse_dim):
                 raise ValueError(f"sparse vectors: term ids must lie in [0, {self.sparse_dim})")
@@ -203,10 +211,7 @@ class B200VectorStore(VectorStore):
         with self._lock:
             first_row = len(self._ids)
             try:
-                if self._dense is not None:
-                    self._dense.add_dense(dense)
-                if self._sparse is not None:
-                    self._sparse.add_sparse(*csr)
+                self._device_add(dense, csr, first_row, n, local)
             except Exception as exc:
                 self._rollback(first_row, n, exc)
                 raise
@@ -235,6 +240,13 @@ class B200VectorStore(VectorStore):
                     self._broken = f"disk append failed ({exc}); reopen the store from {self.db_path}"
                     raise
         logger.info("Added %d vectors to B200VectorStore", n)
+
+    def _device_add(self, dense, csr, first_row: int, n: int, local=None):
+        """Append the vectors of one insert batch to the device indexes (the sharded store keeps its slice only)."""
+        if self._dense is not None:
+            self._dense.add_dense(dense)
+        if self._sparse is not None:
+            self._sparse.add_sparse(*csr)
 
     def _rollback(self, first_row: int, n: int, exc: Exception):
         """Bring both indexes to first_row + n rows, all n of them tombstoned, with dead placeholder payload, so that
