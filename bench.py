@@ -12,10 +12,16 @@ seeded random-init weights (no checkpoint exists offline).  Weak scaling: every 
 sequences per step; no collective on this path.
 
 Printed JSON line (rank 0): the base contract keys plus
-  e2e          the same step through the C ABI with HOST buffers: ids H2D, forward, probs D2H, span post-processing
-  roofline     tensor-core GEMM: algorithmic FLOPs / summed CUDA-event kernel time, vs MEASURED_PEAKS.json
-  cpu_baseline the oracle port timed on this box's host cores (bounded sample; rank 0, N=1 only)
-  secondary    top-k scan (BASELINE 'top-k GB/s') and SPLADE encode numbers, same run
+  e2e            the same step through the C ABI with HOST buffers: ids H2D, forward, probs D2H, span post-processing
+  modes          both arithmetic modes: "fast" (fp16 operands, the headline `value`) and "precise" (split-precision
+                 operands, span logits within 1e-3 of the fp32 reference), each with value + e2e
+  roofline       tensor-core GEMM class: algorithmic FLOPs / summed CUDA-event kernel time, vs MEASURED_PEAKS.json
+  cpu_baseline   the reference-shaped CPU plugin (oracle port) on this box's host cores (bounded sample; rank 0, N=1)
+  secondary      the other BASELINE configs, same run, each with value, roofline, host-buffer e2e and cpu_baseline:
+                 cfg2 SPLADE encode (10 k chunks @256) + sparse top-10 (10 k docs, 1 k queries; 1 M-doc variant),
+                 cfg4 dense top-10 over 1 M x 768 (HBM-bound 16-query passes AND the tensor-bound batched GEMM search),
+                 cfg5 SPLADE retrieve top-20 + span extraction, 10 k chunks / 1 k queries (sharded over the ranks)
+Both arms print the same `config` dict.
 """
 from __future__ import annotations
 
@@ -26,6 +32,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -35,11 +42,23 @@ sys.path.insert(0, ROOT)
 METRIC = "(question,512-tok chunk) span-extractions/sec"
 UNIT = "extractions/s"
 SEQ_LEN, Q_LEN = 512, 29
-SEQS_PER_STEP = 256 * 16
+CTX_LEN = SEQ_LEN - Q_LEN - 3
+CHUNKS_PER_Q = 16
+SEQS_PER_STEP = 256 * CHUNKS_PER_Q
 LAYERS = 22
 FLOPS_LINEAR_PER_TOKEN = 221.78e6          # all Linear layers incl. head
 FLOPS_PER_EXTRACTION = 122.65e9            # linears + windowed attention at L = 512
+FLOPS_PER_SPLADE_CHUNK = 58.21e9           # BERT-base MLM at L = 256
 WORKLOAD = "ModernBERT-v2 span extraction: 256-query batch x 16 retrieved chunks @512 tok (configs[2])"
+
+
+def bench_config():
+    """The workload, identical in both arms (the arms differ in `impl`, `dtype` and the sample they time)."""
+    return {"workload": WORKLOAD, "seqs_per_step_per_gpu": SEQS_PER_STEP, "seq_len": SEQ_LEN, "question_tokens": Q_LEN,
+            "chunk_tokens": CTX_LEN, "layers": LAYERS, "threshold": 0.2, "min_span_chars": 30, "merge_gap_chars": 20,
+            "precision": "reference: fp32 on CPU; b200 arm: `value` = fast mode (fp16 tensor-core operands, |dlogit| <= "
+                         "4e-3), modes.precise = split-precision operands (|dlogit| <= 1e-3, tests/test_gpu_precise.py)",
+            "l2": "inputs larger than L2: >= 11.5 KB of activations per token, 24 GB per step vs 126 MB"}
 
 
 def _peaks():
@@ -49,6 +68,13 @@ def _peaks():
         return {"source": "measured (MEASURED_PEAKS.json)", "hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
                 "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"])}
     return {"source": "fallback (B200_PROFILING.md)", "hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0}
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def make_batch(nseq: int, seed: int):
@@ -62,11 +88,23 @@ def make_batch(nseq: int, seed: int):
     ids[:, Q_LEN + 1] = spec.sep_id
     ids[:, -1] = spec.sep_id
     cu = (np.arange(nseq + 1, dtype=np.int64) * SEQ_LEN).astype(np.int32)
-    n_ctx = SEQ_LEN - Q_LEN - 3
-    tok_cs = np.tile(np.arange(n_ctx, dtype=np.int32) * 7, nseq)
+    tok_cs = np.tile(np.arange(CTX_LEN, dtype=np.int32) * 7, nseq)
     tok_ce = tok_cs + 6
-    ctx_indptr = np.arange(nseq + 1, dtype=np.int64) * n_ctx
+    ctx_indptr = np.arange(nseq + 1, dtype=np.int64) * CTX_LEN
     return ids.reshape(-1), cu, tok_cs, tok_ce, ctx_indptr
+
+
+class _R:   # the only attribute the extractor contract reads from a search result (extractors.py:208)
+    def __init__(self, t):
+        self.text = t
+
+
+def make_text_batch(tk, n_questions: int, seed: int, chunks_per_q: int = CHUNKS_PER_Q, chunk_tokens: int = CTX_LEN,
+                    q_tokens: int = Q_LEN):
+    rng = np.random.default_rng(seed)
+    qs = [tk.make_question(rng, q_tokens) for _ in range(n_questions)]
+    rs = [[_R(tk.make_text(rng, chunk_tokens)) for _ in range(chunks_per_q)] for _ in range(n_questions)]
+    return qs, rs
 
 
 class ClockSampler:
@@ -111,54 +149,52 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference-shaped path (oracle port), batch-1 forward per chunk like extractors.py:207-221
+# CPU arm: the reference-shaped plugin (oracle/plugins.py OracleSpanExtractor): tokenise, ONE batch-1 forward per
+# chunk, sequentially, then the process() post-processing -- the control flow of extractors.py:203-228
 # --------------------------------------------------------------------------------------------------------------
-def cpu_extract(weights, ids, cu, tok_cs, tok_ce, ctx_indptr, nseq):
-    import torch
-    from oracle.highlighter import spans_from_token_probs
-    from oracle.modernbert import modernbert_forward, relevant_prob
-    n_ctx = SEQ_LEN - Q_LEN - 3
-    nspans = 0
-    for i in range(nseq):
-        seq = ids[cu[i]:cu[i + 1]].astype(np.int64)[None]
-        p = relevant_prob(modernbert_forward(weights, seq).numpy()[0])[Q_LEN + 2:Q_LEN + 2 + n_ctx]
-        offs = list(zip(tok_cs[:n_ctx].tolist(), tok_ce[:n_ctx].tolist()))
-        nspans += len(spans_from_token_probs("x" * (7 * n_ctx), p, offs, 0.2, 30, 20))
-    return nspans
-
-
-def time_cpu(nseq_sample: int, steps: int, warmup: int):
+def time_cpu_spans(n_pairs: int, steps: int, warmup: int):
     import torch
     try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core this process may run on
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        torch.set_num_threads(_host_cores())
     except (AttributeError, RuntimeError):
         pass
-    from verbatim_rag_b200.synthetic import make_modernbert_weights
-    weights = {k: torch.from_numpy(v) for k, v in make_modernbert_weights(1001).items()}
-    ids, cu, tcs, tce, cip = make_batch(nseq_sample, 1003)
+    from oracle.plugins import OracleSpanExtractor
+    from verbatim_rag_b200.synthetic import ModernBertSpec, SyntheticTokenizer, make_modernbert_weights
+    spec = ModernBertSpec(layers=LAYERS)
+    tk = SyntheticTokenizer("modernbert")
+    weights = {k: torch.from_numpy(v) for k, v in make_modernbert_weights(1001, spec).items()}
+    ext = OracleSpanExtractor(weights, tk, spec)
+    nq = max(1, (n_pairs + CHUNKS_PER_Q - 1) // CHUNKS_PER_Q)
+    qs, rs = make_text_batch(tk, nq, 1003)
+    flat = [(q, r) for q, row in zip(qs, rs) for r in row][:n_pairs]
     for _ in range(warmup):
-        cpu_extract(weights, ids, cu, tcs, tce, cip, 1)
+        ext.extract_spans(flat[0][0], [flat[0][1]])
     t0 = time.perf_counter()
+    nspans = 0
     for _ in range(steps):
-        cpu_extract(weights, ids, cu, tcs, tce, cip, nseq_sample)
+        for q, r in flat:
+            nspans += sum(len(v) for v in ext.extract_spans(q, [r]).values())
     dt = (time.perf_counter() - t0) / steps
-    return nseq_sample / dt, dt, torch.get_num_threads()
+    return n_pairs / dt, dt, torch.get_num_threads(), nspans // max(steps, 1)
+
+
+def cpu_baseline_block(rate, cores, sample):
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} of {SEQS_PER_STEP} (question, chunk) pairs per step, strings in: tokenise + batch-1 fp32 "
+                      "forward per chunk + span post-processing (oracle/plugins.py OracleSpanExtractor, the control flow "
+                      "of extractors.py:203-228; torch CPU, all host cores)"}
 
 
 def run_reference_arm(args, out):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    sample = args.ref_sample   # ~5-10 s of host work per step
-    rate, dt, cores = time_cpu(sample, args.steps, min(args.warmup, 1))
+    sample = args.cpu_sample
+    rate, dt, cores, _ = time_cpu_spans(sample, args.steps, min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "seq_len": SEQ_LEN, "layers": LAYERS},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {SEQS_PER_STEP} sequences per step, batch-1 forward per chunk "
-                                   "(reference control flow, oracle ModernBERT fp32 on torch CPU) + span post-processing"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(),
+        "cpu_baseline": cpu_baseline_block(rate, cores, sample),
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,114 +203,358 @@ def run_reference_arm(args, out):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm helpers
 # --------------------------------------------------------------------------------------------------------------
-def secondary_metrics(ctx, peaks, rank, world, device):
-    """Top-k scan + SPLADE encode numbers of the same run (bounded: ~10 s)."""
-    import torch
-    from verbatim_rag_b200 import _native
-    out = {}
-    st = torch.cuda.ExternalStream(ctx.stream, device=device)
+class Timer:
+    """CUDA events on the library's stream (torch.cuda.Event on an ExternalStream of ctx.stream)."""
 
-    def timed(fn, iters=3):
-        fn()
-        ctx.sync()
+    def __init__(self, ctx, device):
+        import torch
+        self.ctx, self.torch = ctx, torch
+        self.st = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def __call__(self, fn, iters=3, warm=1):
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.ctx.sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
+        e0.record(self.st)
         for _ in range(iters):
             fn()
-        e1.record(st)
-        ctx.sync()
+        e1.record(self.st)
+        self.ctx.sync()
         return e0.elapsed_time(e1) / iters
 
-    # dense cosine top-10, 1M x 768 fp32 corpus row-sharded over the ranks (configs[3])
+    def profiled(self, fn, iters=1):
+        self.ctx.profile(True)
+        for _ in range(iters):
+            fn()
+        pr = self.ctx.profile_read()
+        self.ctx.profile(False)
+        return pr
+
+
+def _all_max(x: float, device, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sec_dense(ctx, peaks, rank, world, device, cpu: bool):
+    """BASELINE configs[3]: dense cosine top-10, 1 M x 768 fp32 corpus row-sharded over the ranks, both regimes."""
+    import torch
+    import torch.distributed as dist
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.distributed import shard_bounds, sharded_search_dense
+    out = {}
+    timed = Timer(ctx, device)
     n_total, dim, k = 1_000_000, 768, 10
-    from verbatim_rag_b200.distributed import shard_bounds
     lo, hi = shard_bounds(n_total, rank, world)
+    rows = hi - lo
     g = torch.Generator(device=device).manual_seed(1004 + rank)
     ix = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
     ix.set_id_base(lo)
-    ix.add_dense(torch.randn(hi - lo, dim, device=device, generator=g))
+    ix.add_dense(torch.randn(rows, dim, device=device, generator=g))
     gq = torch.Generator(device=device).manual_seed(2004)
-    for nq in (1, 16, 1000):  # per-query API call; one tensor-core pass; the configs[3] batch (63 passes of 16)
+    pass_bytes = rows * dim * 4
+    for nq in (1, 16, 1000):   # the reference's per-query call; one HBM-bound 16-query pass; the configs[3] batch
         q = torch.randn(nq, dim, device=device, generator=gq)
         ids_o = torch.empty(nq, k, dtype=torch.int64, device=device)
         s_o = torch.empty(nq, k, dtype=torch.float32, device=device)
-        iters = 3 if nq <= 16 else 1
-        ms = timed(lambda: ix.search_dense_device(q, nq, k, ids_o, s_o), iters=iters)
-        ctx.profile(True)
-        for _ in range(iters):
-            ix.search_dense_device(q, nq, k, ids_o, s_o)
-        pr = ctx.profile_read()
-        ctx.profile(False)
-        passes = pr["scan"]["launches"] / iters                                # corpus passes per search call
-        pass_bytes = (hi - lo) * dim * 4
-        scan_ms = pr["scan"]["ms"] / max(pr["scan"]["launches"], 1)          # per corpus pass (CUDA events)
-        scan_gbs = pass_bytes / scan_ms / 1e6 if scan_ms > 0 else 0.0
-        out[f"dense_top{k}_q{nq}"] = {
-            "ms": ms, "queries_per_s": nq / ms * 1e3, "rows_per_gpu": hi - lo, "corpus_passes": passes,
-            "queries_per_pass": nq / passes if passes else 0,
-            "search_GBps_per_gpu": passes * pass_bytes / ms / 1e6,             # whole search incl. select / rescore
-            "roofline": {"bound": "hbm", "kernel": "dense_scan_tma_kernel (fp32 FMA)" if nq < 5 else
-                         "dense_scan_tc_kernel (split-tf32 tcgen05)", "achieved": scan_gbs,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_gbs / peaks["hbm_gbs"],
-                         "bytes_per_launch": pass_bytes, "avg_launch_ms": scan_ms},
-            "select_finish_ms": pr["select"]["ms"] / iters}
+        fn = lambda: ix.search_dense_device(q, nq, k, ids_o, s_o)   # noqa: E731
+        ms = timed(fn, iters=3, warm=2)
+        pr = timed.profiled(fn, iters=3)
+        scan_ms = pr["scan"]["ms"] / 3
+        launches = pr["scan"]["launches"] / 3
+        rec = {"ms": ms, "queries_per_s": nq / ms * 1e3, "rows_per_gpu": rows, "scan_launches": launches,
+               "scan_ms": scan_ms, "select_finish_ms": pr["select"]["ms"] / 3}
+        if nq <= 16:    # HBM-bound regime: one corpus pass of N*dim*4 bytes per <= 16 queries
+            gbs = launches * pass_bytes / scan_ms / 1e6 if scan_ms > 0 else 0.0
+            rec["search_GBps_per_gpu"] = launches * pass_bytes / ms / 1e6
+            rec["roofline"] = {"bound": "hbm", "kernel": "dense_scan_tma_kernel (fp32 FMA)" if nq < 5 else
+                               "dense_scan_tc_kernel (split-tf32 tcgen05, 16 queries per pass)", "achieved": gbs,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                               "bytes_per_launch": pass_bytes, "avg_launch_ms": scan_ms / max(launches, 1)}
+        else:           # tensor-bound regime: all queries against the corpus as one split-precision GEMM per 1024
+            flops = 2.0 * nq * rows * dim
+            tf = 3 * flops / scan_ms / 1e9 if scan_ms > 0 else 0.0        # three fp16 MMAs per product
+            plane_bytes = ((nq + 255) // 256) * rows * dim * 4              # hi + lo planes, read once per 256 queries
+            rec["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_SCORES, split> (3 fp16 MMAs / product)",
+                               "achieved": tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s (issued: 3 x algorithmic)",
+                               "frac": tf / peaks["bf16_burst"], "algorithmic_tflops": flops / scan_ms / 1e9,
+                               "hbm_GBps": (plane_bytes + nq * rows * 4) / scan_ms / 1e6,
+                               "hbm_frac": (plane_bytes + nq * rows * 4) / scan_ms / 1e6 / peaks["hbm_gbs"],
+                               "avg_launch_ms": scan_ms / max(launches, 1)}
+        out[f"top{k}_q{nq}"] = rec
+    # host-buffer e2e through the C ABI: queries H2D + search + ids / scores D2H inside the call
+    qh = np.random.default_rng(2004).standard_normal((1000, dim), dtype=np.float32)
+    ix.search_dense(qh[:16], k)
+    t0 = time.perf_counter()
+    ix.search_dense(qh, k)
+    dt = time.perf_counter() - t0
+    out["e2e"] = {"value": 1000 / dt, "unit": "queries/s", "h2d_bytes": int(qh.nbytes), "d2h_bytes": 1000 * k * 12,
+                  "path": "vrag_index_search_dense(host queries) -> host ids + scores, one call for 1000 queries"}
     if world > 1:
-        # configs[3] as stated: corpus row-sharded over the ranks, queries replicated, per-rank top-k, ONE NCCL all_gather
-        # of [Q, k] (fp64 score, int64 global id) + the device merge -> the global top-10 on every rank
-        import torch.distributed as dist
-        from verbatim_rag_b200.distributed import sharded_search_dense
+        # configs[3] as stated: queries replicated, per-rank top-k, ONE packed NCCL all_gather + device merge, no host sync
         q = torch.randn(1000, dim, device=device, generator=gq)
-        sharded_search_dense(ix, q, k)
+        for _ in range(2):
+            sharded_search_dense(ix, q, k)
         dist.barrier()
         torch.cuda.synchronize(device)
-        t0 = time.perf_counter()
-        gi, gs, _ = sharded_search_dense(ix, q, k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            gi, gs, _ = sharded_search_dense(ix, q, k)
+        e1.record()
         torch.cuda.synchronize(device)
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        out["dense_top10_q1000_global"] = {
-            "ms": float(dt.item()) * 1e3, "queries_per_s": 1000 / float(dt.item()), "ranks": world,
-            "rows_total": n_total, "corpus_GBps_all_gpus": 63 * n_total * dim * 4 / float(dt.item()) / 1e9,
-            "collective": "one all_gather of [1000, 10] x (f64, i64) per rank + vrag_topk_merge",
+        ms = _all_max(e0.elapsed_time(e1) / 3, device, world)
+        out["top10_q1000_global"] = {
+            "ms": ms, "queries_per_s": 1000 / ms * 1e3, "ranks": world, "rows_total": n_total,
+            "collective": "one all_gather of packed [1000, 10] x (f64 score, i64 id) per rank + vrag_topk_merge, "
+                          "device-ordered on the library stream (no host sync)",
             "ids_sorted_by_score": bool((gs[:, :-1] >= gs[:, 1:]).all().item())}
     ix.close()
+    if cpu:
+        # the reference's store is milvus-lite FLAT on the host cores, one call per query (milvus_base.py:239-248):
+        # oracle/flat_topk.py exact scan, 100 k of the 1 M rows x 32 queries
+        from oracle.flat_topk import dense_cosine_topk
+        rng = np.random.default_rng(1004)
+        sub = rng.standard_normal((100_000, dim), dtype=np.float32)
+        qs = rng.standard_normal((32, dim), dtype=np.float32)
+        dense_cosine_topk(sub, qs[:1], k)
+        t0 = time.perf_counter()
+        for i in range(32):
+            dense_cosine_topk(sub, qs[i:i + 1], k)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 32 / dt / 10.0, "unit": "queries/s over 1 M rows (scaled x 1/10 from 100 k rows)",
+                               "scan_GBps": 32 * sub.nbytes / dt / 1e9, "cores": _host_cores(), "kind": "port",
+                               "sample": "100 k of 1 M rows x 32 queries, one call per query (numpy/BLAS exact scan)"}
+    return out
 
-    if rank == 0:
-        # configs[1]: SPLADE encode of 256-token chunks (BERT-base MLM, 12 layers) + sparse-dot top-10 over 10k docs
-        from verbatim_rag_b200.synthetic import BertSpec, make_bert_mlm_weights, make_sparse_rows
-        bspec = BertSpec()
-        enc = _native.Encoder(ctx, _native.ENC_BERT_MLM, make_bert_mlm_weights(1002, bspec), bspec.layers,
-                              bspec.vocab_size, max_tokens=65536)
-        nchunk, Lc = 1024, 256
-        rng = np.random.default_rng(1002)
-        ids = rng.integers(1000, bspec.vocab_size, size=(nchunk, Lc), dtype=np.int32)
-        ids[:, 0], ids[:, -1] = bspec.cls_id, bspec.sep_id
-        cu = (np.arange(nchunk + 1) * Lc).astype(np.int32)
-        ids_d = torch.from_numpy(ids.reshape(-1)).to(device)
-        dense_d = torch.empty(nchunk, bspec.vocab_size, dtype=torch.float32, device=device)
-        ms = timed(lambda: enc.splade_forward_device(ids_d, cu, dense_d), iters=2)
-        t0 = time.perf_counter()
-        csr = enc.splade_forward(ids.reshape(-1), cu)           # host ids -> host CSR (the provider's path)
-        e2e_s = time.perf_counter() - t0
-        out["splade_encode_256tok"] = {"chunks_per_s": nchunk / ms * 1e3, "ms": ms, "chunks": nchunk,
-                                       "tflops_algorithmic": 58.21e9 * nchunk / ms / 1e9,
-                                       "e2e_chunks_per_s_host_ids_to_host_csr": nchunk / e2e_s,
-                                       "mean_nnz": float(np.diff(csr["indptr"]).mean())}
+
+def sec_splade(ctx, peaks, rank, world, device, cpu: bool, n_chunks: int):
+    """BASELINE configs[1], encode side: SPLADE encode of 256-token chunks (BERT-base MLM, 12 layers).  Every rank
+    encodes its own ``n_chunks`` (weak scaling, no collective)."""
+    import torch
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import BertSpec, make_bert_mlm_weights
+    out = {}
+    timed = Timer(ctx, device)
+    bspec = BertSpec()
+    w = make_bert_mlm_weights(1002, bspec)
+    Lc = 256
+    rng = np.random.default_rng(1002 + rank)
+    ids = rng.integers(1000, bspec.vocab_size, size=(n_chunks, Lc), dtype=np.int32)
+    ids[:, 0], ids[:, -1] = bspec.cls_id, bspec.sep_id
+    cu = (np.arange(n_chunks + 1) * Lc).astype(np.int32)
+    for prec in ("fast", "precise"):
+        nc = n_chunks if prec == "fast" else min(n_chunks, 2048)
+        enc = _native.Encoder(ctx, _native.ENC_BERT_MLM, w, bspec.layers, bspec.vocab_size, max_tokens=65536,
+                              precision=prec)
+        ids_d = torch.from_numpy(ids[:nc].reshape(-1)).to(device)
+        dense_d = torch.empty(nc, bspec.vocab_size, dtype=torch.float32, device=device)
+        fn = lambda: enc.splade_forward_device(ids_d, cu[:nc + 1], dense_d)   # noqa: E731
+        ms = _all_max(timed(fn, iters=2, warm=1), device, world)
+        pr = timed.profiled(fn, iters=1)
+        tf = FLOPS_PER_SPLADE_CHUNK * nc / ms / 1e9
+        rec = {"chunks_per_s": world * nc / ms * 1e3, "ms": ms, "chunks_per_gpu": nc, "n_gpus": world,
+               "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (BERT epilogues incl. EPI_SPLADE)",
+                            "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s algorithmic, whole encode",
+                            "frac": tf / peaks["bf16_sustained"],
+                            "share_of_encode": {k: v["ms"] / ms for k, v in pr.items() if v["launches"]}}}
+        if prec == "fast":
+            t0 = time.perf_counter()
+            csr = enc.splade_forward(ids.reshape(-1), cu)           # host ids -> host CSR (the provider's path)
+            dt = time.perf_counter() - t0
+            rec["e2e"] = {"value": n_chunks / dt, "unit": "chunks/s", "h2d_bytes": int(ids.nbytes),
+                          "d2h_bytes": int(csr["indices"].nbytes + csr["values"].nbytes + csr["indptr"].nbytes),
+                          "path": "vrag_splade_forward(host ids) -> host CSR"}
+            rec["mean_nnz"] = float(np.diff(csr["indptr"]).mean())
+        out[prec] = rec
         enc.close()
-        ip, ixs, vl = make_sparse_rows(10000, seed=1002)
-        qip, qix, qvl = make_sparse_rows(64, seed=2002, query=True)
-        sx = _native.Index(ctx, _native.INDEX_SPARSE_IP, bspec.vocab_size)
-        sx.add_sparse(ip, ixs, vl)
-        sx.search_sparse(qip, qix, qvl, 10)
+    if cpu:
+        import torch as _t
+        _t.set_num_threads(_host_cores())
+        from oracle.bert_splade import splade_encode, to_dicts_embed_batch
+        ns = 64
+        seqs = [ids[i].astype(np.int64) for i in range(ns)]
         t0 = time.perf_counter()
-        for _ in range(5):
-            sx.search_sparse(qip, qix, qvl, 10)
-        dt = (time.perf_counter() - t0) / 5
-        out["sparse_top10_10k_docs"] = {"us_per_query_e2e_host": dt / 64 * 1e6, "queries": 64, "nnz_corpus": int(ip[-1]),
-                                        "note": "12.8 MB CSR corpus is L2 resident: latency-bound, not an HBM roofline"}
-        sx.close()
+        to_dicts_embed_batch(splade_encode(w, seqs, bspec, batch_size=32))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ns / dt, "unit": "chunks/s", "cores": _host_cores(), "kind": "port",
+                               "sample": f"{ns} of {n_chunks} chunks @256 tokens, batches of 32, fp32 BertForMaskedLM-equivalent + "
+                                         "SPLADE pool + the reference's np.nonzero dict loop (embedding_providers.py:148-166)"}
+    return out
+
+
+def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
+    """BASELINE configs[1], search side: sparse inner-product top-10, 1 k queries over 10 k docs (L2-resident corpus) and
+    the HBM-resident variant SURVEY.md 8d asks for (``big_docs`` documents, 64 queries)."""
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import csr_to_dicts, make_sparse_rows, make_sparse_rows_device
+    out = {}
+    timed = Timer(ctx, device)
+    V = 30522
+    ip, ixs, vl = make_sparse_rows(10000, seed=1002)
+    qip, qix, qvl = make_sparse_rows(1000, seed=2002, query=True)
+    sx = _native.Index(ctx, _native.INDEX_SPARSE_IP, V)
+    sx.add_sparse(ip, ixs, vl)
+    sx.search_sparse(qip[:17], qix, qvl, 10)
+    t0 = time.perf_counter()
+    sx.search_sparse(qip, qix, qvl, 10)
+    dt = time.perf_counter() - t0
+    pr = timed.profiled(lambda: sx.search_sparse(qip, qix, qvl, 10))
+    passes = pr["scan"]["launches"]
+    bytes_pass = 8 * int(ip[-1]) + 8 * (len(ip))
+    out["docs10k_q1000"] = {
+        "e2e": {"value": 1000 / dt, "unit": "queries/s", "us_per_query": dt / 1000 * 1e6,
+                "path": "vrag_index_search_sparse(host CSR queries) -> host ids + scores"},
+        "nnz_corpus": int(ip[-1]), "scan_ms": pr["scan"]["ms"], "select_ms": pr["select"]["ms"], "corpus_passes": passes,
+        "roofline": {"bound": "L2 / latency", "kernel": "sparse_scan_kernel", "achieved": passes * bytes_pass / pr["scan"]["ms"] / 1e6,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": passes * bytes_pass / pr["scan"]["ms"] / 1e6 / peaks["hbm_gbs"],
+                     "note": "the 12.8 MB CSR corpus is L2-resident: the HBM fraction is not a bound here (SURVEY.md 8d); "
+                             "see docs1M for the HBM-resident variant"}}
+    sx.close()
+    if big_docs > 0:
+        bip, bix, bvl = make_sparse_rows_device(big_docs, seed=1002, device=device)
+        bx = _native.Index(ctx, _native.INDEX_SPARSE_IP, V)
+        step = 250_000
+        for a in range(0, big_docs, step):
+            bx.add_sparse(bip[a:min(big_docs, a + step) + 1], bix, bvl)
+        nq = 64
+        bx.search_sparse(qip[:9], qix, qvl, 10)
+        t0 = time.perf_counter()
+        bx.search_sparse(qip[:nq + 1], qix, qvl, 10)
+        dt = time.perf_counter() - t0
+        pr = timed.profiled(lambda: bx.search_sparse(qip[:nq + 1], qix, qvl, 10))
+        passes = pr["scan"]["launches"]
+        bytes_pass = 8 * int(bip[-1]) + 8 * (big_docs + 1)
+        gbs = passes * bytes_pass / pr["scan"]["ms"] / 1e6
+        out["docs1M_q64"] = {
+            "docs": big_docs, "nnz_corpus": int(bip[-1]), "queries": nq, "queries_per_pass": nq / max(passes, 1),
+            "e2e": {"value": nq / dt, "unit": "queries/s", "path": "vrag_index_search_sparse(host CSR queries)"},
+            "scan_ms": pr["scan"]["ms"], "select_ms": pr["select"]["ms"],
+            "roofline": {"bound": "hbm", "kernel": "sparse_scan_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": bytes_pass,
+                         "avg_launch_ms": pr["scan"]["ms"] / max(passes, 1)}}
+        bx.close()
+    if cpu:
+        from oracle.flat_topk import sparse_ip_topk
+        qd = csr_to_dicts(qip[:33], qix, qvl)
+        sparse_ip_topk(ip, ixs, vl, V, qd[:1], 10)
+        t0 = time.perf_counter()
+        for q in qd:
+            sparse_ip_topk(ip, ixs, vl, V, [q], 10)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(qd) / dt, "unit": "queries/s over 10 k docs", "cores": _host_cores(), "kind": "port",
+                               "sample": "32 of 1 k queries, one call per query (scipy CSR exact inner product, "
+                                         "milvus_base.py:250-259 control flow)"}
+    return out
+
+
+def sec_rag(ctx, rank, world, device, cpu: bool, n_chunks: int, n_queries: int):
+    """BASELINE configs[4]: SPLADE retrieve top-20 + span extraction for ``n_queries`` questions over ``n_chunks`` chunks
+    of 256 tokens, strings in / verbatim span strings out through the plugin classes.  N ranks: the index is built data-
+    parallel (each rank encodes its slice), vectors are sharded (ShardedB200VectorStore: one all-gather per search), the
+    questions are split over the ranks for extraction (pipeline.rag_query_batch's scheme)."""
+    import torch.distributed as dist
+    from verbatim_rag_b200 import B200SpanExtractor, B200SpladeProvider
+    from verbatim_rag_b200.distributed import shard_bounds
+    from verbatim_rag_b200.pipeline import index_query_batch
+    from verbatim_rag_b200.sharded_store import ShardedB200VectorStore
+    dev = f"cuda:{device.index}"
+    k = 20
+    prov = B200SpladeProvider("synthetic:1002", device=dev)
+    ext = B200SpanExtractor("synthetic:1001", device=dev, max_tokens=131072)
+    btok = prov._te.tokenizer
+    rng = np.random.default_rng(1005)
+    chunks = [btok.make_text(rng, 256) for _ in range(n_chunks)]
+    questions = [btok.make_question(rng, int(rng.integers(12, 21))) for _ in range(n_queries)]
+    ids = [f"c{i:07d}" for i in range(n_chunks)]
+    store = ShardedB200VectorStore(enable_dense=False, enable_sparse=True, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+    barrier()
+    t0 = time.perf_counter()
+    store.add_texts(ids, chunks, chunks, [{} for _ in chunks], sparse_provider=prov)
+    barrier()
+    t_index = time.perf_counter() - t0
+    index = types.SimpleNamespace(vector_store=store, sparse_provider=prov, dense_provider=None)
+    lo, hi = shard_bounds(n_queries, rank, world)
+
+    def run(qs, a, b):
+        found = index_query_batch(index, qs, k=k)                        # replicated query encode + sharded search
+        mine = ext.extract_spans_batch(qs[a:b], found[a:b])               # data-parallel over the ranks
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            mine = [x for p in parts for x in p]
+        return found, mine
+
+    w = min(n_queries, 4 * world)
+    run(questions[:w], *shard_bounds(w, rank, world))
+    best = None
+    for _ in range(2):   # the first full-size batch grows pinned / device staging buffers; report the steady state
+        barrier()
+        t1 = time.perf_counter()
+        found = index_query_batch(index, questions, k=k)
+        t2 = time.perf_counter()
+        mine = ext.extract_spans_batch(questions[lo:hi], found[lo:hi])
+        t3 = time.perf_counter()
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            spans = [x for p in parts for x in p]
+        else:
+            spans = mine
+        barrier()
+        t4 = time.perf_counter()
+        rec = (t4 - t1, t2 - t1, t3 - t2, t4 - t3)
+        best = rec if best is None or rec[0] < best[0] else best
+    n_ext = sum(len(r) for r in found)
+    out = {"chunks": n_chunks, "chunk_tokens": 256, "queries": n_queries, "k": k, "n_gpus": world, "extractions": n_ext,
+           "queries_per_s": n_queries / best[0], "extractions_per_s": n_ext / best[0],
+           "stage_ms": {"retrieve (query encode + sharded sparse top-20)": best[1] * 1e3,
+                        "extract (tokenise pairs + 22-layer forward + spans), slowest rank's share": best[2] * 1e3,
+                        "gather responses": best[3] * 1e3},
+           "index_build_chunks_per_s": n_chunks / t_index,
+           "spans": int(sum(len(v) for d in spans for v in d.values())),
+           "path": "strings in -> verbatim span strings out: B200SpladeProvider -> ShardedB200VectorStore -> "
+                   "B200SpanExtractor via pipeline.index_query_batch / extract_spans_batch (the steps of "
+                   "VerbatimRAG.query, core.py:210-277, minus template filling)"}
+    ext._workers.close()
+    if cpu and world == 1:
+        import torch as _t
+        _t.set_num_threads(_host_cores())
+        from oracle.plugins import OracleFlatStore, OracleSpanExtractor, OracleSpladeProvider
+        from verbatim_rag_b200.synthetic import (BertSpec, ModernBertSpec, SyntheticTokenizer, make_bert_mlm_weights,
+                                                 make_modernbert_weights)
+        bspec, mspec = BertSpec(), ModernBertSpec(layers=LAYERS)
+        oprov = OracleSpladeProvider(make_bert_mlm_weights(1002, bspec), btok, bspec)
+        oext = OracleSpanExtractor({k2: _t.from_numpy(v) for k2, v in make_modernbert_weights(1001, mspec).items()},
+                                   SyntheticTokenizer("modernbert"), mspec)
+        nc, nq_c, kc = 64, 2, 8
+        ostore = OracleFlatStore(enable_dense=False, enable_sparse=True)
+        t0 = time.perf_counter()
+        ostore.add_vectors(ids[:nc], None, oprov.embed_batch(chunks[:nc]), chunks[:nc], chunks[:nc], [{} for _ in range(nc)])
+        t_idx = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        n_e = 0
+        for q in questions[:nq_c]:      # the reference's loop: one query at a time (core.py:210-277)
+            res = ostore.query(sparse_query=oprov.embed_text(q), top_k=kc, search_type="sparse")
+            n_e += len(oext.extract_spans(q, res))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_e / dt, "unit": "extractions/s (retrieve + extract, per query)",
+                               "queries_per_s_at_k20": (nq_c / dt) * kc / k, "index_build_chunks_per_s": nc / t_idx,
+                               "cores": _host_cores(), "kind": "port",
+                               "sample": f"{nc} chunks indexed, {nq_c} queries x top-{kc}: OracleSpladeProvider -> OracleFlatStore "
+                                         "-> OracleSpanExtractor, one query at a time"}
     return out
 
 
@@ -296,13 +576,13 @@ def run_gpu_arm(args, out):
     peaks = _peaks()
     ctx = _native.default_context(local)
     spec = ModernBertSpec(layers=LAYERS)
-    enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, make_modernbert_weights(1001, spec), spec.layers,
-                          spec.vocab_size, max_tokens=args.max_tokens)
+    weights = make_modernbert_weights(1001, spec)
     nseq = args.seqs_per_step
     ids_h, cu, tok_cs, tok_ce, ctx_indptr = make_batch(nseq, 1003 + rank)
     T = int(cu[-1])
     ids_d = torch.from_numpy(ids_h).to(device)
     probs_d = torch.empty(T, dtype=torch.float32, device=device)
+    ids_pin = torch.from_numpy(ids_h).pin_memory().numpy()
     st = torch.cuda.ExternalStream(ctx.stream, device=device)
 
     def barrier():
@@ -311,57 +591,78 @@ def run_gpu_arm(args, out):
         torch.cuda.synchronize(device)
         ctx.sync()
 
-    def step_device():
-        enc.span_forward_device(ids_d, cu, probs_d)
+    def measure(enc, steps, warmup, profile):
+        """-> (ms per step of the device-resident step, max over ranks; profile; launches; e2e seconds per step)"""
+        for _ in range(warmup):
+            enc.span_forward_device(ids_d, cu, probs_d)
+        barrier()
+        l0 = ctx.launches
+        if profile:
+            ctx.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            enc.span_forward_device(ids_d, cu, probs_d)
+        e1.record(st)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        prof = ctx.profile_read() if profile else None
+        if profile:
+            ctx.profile(False)
+        launches = ctx.launches - l0
+        ms_step = _all_max(ms_total, device, world) / steps
 
-    # ---- value: inputs resident in HBM, CUDA events on the launching stream ------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+        # e2e: host buffers through the C ABI (H2D + forward + D2H + span post-processing)
+        def step_host():
+            p = enc.span_forward(ids_pin, cu)
+            c0 = Q_LEN + 2
+            p_ctx = np.ascontiguousarray(p.reshape(nseq, SEQ_LEN)[:, c0:c0 + CTX_LEN]).reshape(-1)
+            return _native.spans_from_probs(p_ctx, tok_cs, tok_ce, ctx_indptr, 0.2, 30, 20)
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        nsp = 0
+        reps = max(1, steps // 2)
+        for _ in range(reps):
+            nsp = len(step_host()["ctx"])
+        ctx.sync()
+        e2e_s = _all_max((time.perf_counter() - t0) / reps, device, world)
+        return ms_step, ms_total, prof, launches, e2e_s, nsp
+
+    # ---- fast mode = the headline ---------------------------------------------------------------------------------
+    enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, weights, spec.layers, spec.vocab_size,
+                          max_tokens=args.max_tokens, precision="fast")
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = ctx.launches
-    ctx.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(st)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    launches = ctx.launches - l0
+    ms_step, ms_total, prof, launches, e2e_s, nsp = measure(enc, args.steps, args.warmup, True)
     clocks = sampler.stop()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     value = world * nseq / (ms_step / 1e3)
+    e2e_value = world * nseq / e2e_s
+    modes = {"fast": {"value": value, "unit": UNIT, "ms_per_step": ms_step, "e2e": e2e_value, "dtype": "f16",
+                      "logit_tolerance": "4.0e-3 (measured 3.3e-3 on the cfg-1 goldens)"}}
 
-    # ---- e2e: host buffers through the C ABI (H2D + forward + D2H + span post-processing) -----------------------
-    ids_pin = torch.from_numpy(ids_h).pin_memory().numpy()
-    def step_host():
-        p = enc.span_forward(ids_pin, cu)
-        c0 = Q_LEN + 2
-        p_ctx = np.ascontiguousarray(p.reshape(nseq, SEQ_LEN)[:, c0:c0 + (SEQ_LEN - Q_LEN - 3)]).reshape(-1)
-        return _native.spans_from_probs(p_ctx, tok_cs, tok_ce, ctx_indptr, 0.2, 30, 20)
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    nsp = 0
-    for _ in range(max(1, args.steps // 2)):
-        nsp = len(step_host()["ctx"])
-    ctx.sync()
-    e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * nseq / float(t.item())
+    # ---- precise mode: split-precision operands, the north-star tolerance ---------------------------------------------
+    if args.precise:
+        enc_p = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, weights, spec.layers, spec.vocab_size,
+                                max_tokens=args.max_tokens, precision="precise")
+        sp2 = ClockSampler(local)
+        sp2.start()
+        p_ms, _, p_prof, _, p_e2e_s, _ = measure(enc_p, max(1, args.steps // 2), min(args.warmup, 2), True)
+        p_clocks = sp2.stop()
+        enc_p.close()
+        modes["precise"] = {"value": world * nseq / (p_ms / 1e3), "unit": UNIT, "ms_per_step": p_ms,
+                            "e2e": world * nseq / p_e2e_s, "dtype": "f16 hi + f16 lo planes, 3 tcgen05.mma per product",
+                            "logit_tolerance": "1e-3 (measured 4.7e-5 on the cfg-1 goldens)", "clocks": p_clocks,
+                            "tflops_issued": 3 * FLOPS_LINEAR_PER_TOKEN * T * max(1, args.steps // 2)
+                                             / (p_prof["gemm"]["ms"] / 1e3) / 1e12 if p_prof["gemm"]["ms"] > 0 else None,
+                            "share_of_step": {k: v["ms"] / (p_ms * max(1, args.steps // 2)) for k, v in p_prof.items() if v["launches"]}}
 
     if rank != 0:
+        enc.close()
         if args.secondary:
-            secondary_metrics(ctx, peaks, rank, world, device)
+            sec_dense(ctx, peaks, rank, world, device, False)
+            sec_splade(ctx, peaks, rank, world, device, False, args.splade_chunks)
+            sec_rag(ctx, rank, world, device, False, args.rag_chunks, args.rag_queries)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -370,21 +671,17 @@ def run_gpu_arm(args, out):
     gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
     gemm_flops = FLOPS_LINEAR_PER_TOKEN * T * args.steps
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    cfg = bench_config()
+    cfg.update({"max_tokens_per_pass": args.max_tokens, "tflops_algorithmic": value * FLOPS_PER_EXTRACTION / 1e12 / world})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "seqs_per_step_per_gpu": nseq, "seq_len": SEQ_LEN, "layers": LAYERS,
-                   "precision": "fp16 tensor-core operands, fp32 accumulate, two-plane residual stream (fp16 + e5m2, >= 14 bits)",
-                   "max_tokens_per_pass": args.max_tokens,
-                   "l2": "working set per step (>= 11.5 KB of activations per token, %.1f GB) exceeds the 126 MB L2"
-                         % (11.5e3 * T / 1e9),
-                   "tflops_algorithmic": value * FLOPS_PER_EXTRACTION / 1e12 / world},
-        "clocks": clocks,
+        "data": "synthetic", "config": cfg, "clocks": clocks, "modes": modes,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 4 + (nseq + 1) * 4),
                 "d2h_bytes_per_step": int(T * 4), "spans_per_step": int(nsp),
                 "path": "vrag_span_forward(host ids) + vrag_spans_from_probs (C ABI, host buffers)"},
@@ -392,51 +689,50 @@ def run_gpu_arm(args, out):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "peak_source": peaks["source"] + ", sustained cuBLAS bf16", "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                      "flops_per_launch_avg": gemm_flops / max(gemm_n, 1),
                      "share_of_step": {k: v["ms"] / (ms_total) for k, v in prof.items() if v["launches"]}},
     }
+    enc.close()
     if world == 1 and args.secondary:
-        # plugin level: strings in -> verbatim span strings out (B200SpanExtractor.extract_spans_batch), small sample.
-        # Host tokenisation (tokenizers library, word-level synthetic vocab) dominates this number, not the GPU.
+        # plugin level: strings in -> verbatim span strings out (B200SpanExtractor.extract_spans_batch) on half a step
+        # of fresh texts; host tokenisation (worker processes) and span post-processing overlap the GPU forward
         from verbatim_rag_b200 import B200SpanExtractor
         from verbatim_rag_b200.synthetic import SyntheticTokenizer
         tk = SyntheticTokenizer("modernbert")
-        ext = B200SpanExtractor.__new__(B200SpanExtractor)
-        ext.tokenizer, ext.threshold, ext.min_span_chars, ext.merge_gap_chars = tk, 0.2, 30, 20
-        ext.max_length, ext.doc_stride, ext._enc, ext._ctx, ext.pipeline_pairs = 8192, 256, enc, ctx, 512
-        ext._lock = threading.Lock()
-        prng = np.random.default_rng(7)
-        nq_p, nchunk_p = 32, 32
-
-        class _R:
-            def __init__(self, t):
-                self.text = t
-        qs = [tk.make_question(prng, Q_LEN) for _ in range(nq_p)]
-        rs = [[_R(tk.make_text(prng, SEQ_LEN - Q_LEN - 3)) for _ in range(nchunk_p)] for _ in range(nq_p)]
-        ext.extract_spans_batch(qs[:2], rs[:2])
+        ext = B200SpanExtractor(weights=weights, tokenizer=tk, num_layers=spec.layers, vocab_size=spec.vocab_size,
+                                max_tokens=args.max_tokens, device=f"cuda:{local}")
+        nq_p = max(2, args.plugin_pairs // CHUNKS_PER_Q)
+        qs, rs = make_text_batch(tk, nq_p, 7)
+        ext.extract_spans_batch(qs[:40], rs[:40])     # starts the tokeniser workers, grows the staging buffers
         t0 = time.perf_counter()
         res = ext.extract_spans_batch(qs, rs)
         dtp = time.perf_counter() - t0
-        line["e2e_plugin_strings"] = {"value": nq_p * nchunk_p / dtp, "unit": UNIT, "pairs": nq_p * nchunk_p,
+        line["e2e_plugin_strings"] = {"value": nq_p * CHUNKS_PER_Q / dtp, "unit": UNIT, "pairs": nq_p * CHUNKS_PER_Q,
                                       "spans": int(sum(len(v) for d in res for v in d.values())),
-                                      "note": "extract_spans_batch(strings): host tokenisation of slice i+1 overlaps the GPU forward of slice i"}
+                                      "tokenizer_workers": ext._workers.n, "host_cores": _host_cores(),
+                                      "note": "B200SpanExtractor.extract_spans_batch(strings): tokenisation of slices "
+                                              "i+1, i+2 and span post-processing of slice i-1 overlap the forward of slice i"}
+        ext._workers.close()
+        del ext
     if world == 1 and args.cpu_baseline:
-        rate, dt, cores = time_cpu(args.cpu_sample, 1, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample} of {SEQS_PER_STEP} sequences, batch-1 forward per chunk "
-                                          "(reference control flow, oracle ModernBERT fp32 on torch CPU)"}
+        rate, dt, cores, _ = time_cpu_spans(args.cpu_sample, 1, 1)
+        line["cpu_baseline"] = cpu_baseline_block(rate, cores, args.cpu_sample)
     if args.secondary:
-        line["secondary"] = secondary_metrics(ctx, peaks, rank, world, device)
-    if world == 1 and args.secondary:
-        # configs[4] shape, bounded: SPLADE retrieve top-20 + span extraction through the plugin classes (strings in)
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        try:
-            import rag_bench
-            enc.close()   # the plugins own their encoders
-            line["secondary"]["rag_e2e"] = rag_bench.run(device=f"cuda:{local}")
-        except Exception as exc:  # noqa: BLE001 -- a secondary block must not take the headline line down
-            line["secondary"]["rag_e2e"] = {"error": repr(exc)}
+        cpu = world == 1 and args.cpu_baseline
+        sec = {}
+        for name, fn in (("cfg4_dense_1Mx768", lambda: sec_dense(ctx, peaks, rank, world, device, cpu)),
+                         ("cfg2_splade_encode_256tok", lambda: sec_splade(ctx, peaks, rank, world, device, cpu, args.splade_chunks)),
+                         ("cfg2_sparse_top10", lambda: sec_sparse(ctx, peaks, device, cpu, args.sparse_docs if world == 1 else 0)),
+                         ("cfg5_rag_e2e", lambda: sec_rag(ctx, rank, world, device, cpu, args.rag_chunks, args.rag_queries))):
+            try:
+                sec[name] = fn()
+            except Exception as exc:  # noqa: BLE001 -- a secondary block must not take the headline line down
+                if world > 1:
+                    raise               # ... except where the other ranks would wait in a collective forever
+                sec[name] = {"error": repr(exc)}
+        line["secondary"] = sec
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -452,10 +748,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs-per-step", type=int, default=SEQS_PER_STEP)
     ap.add_argument("--max-tokens", type=int, default=131072)  # pass-size sweep: profiles/README.md
-    ap.add_argument("--cpu-sample", type=int, default=96)   # ~10-30 s of host work
-    ap.add_argument("--ref-sample", type=int, default=24)    # sequences per step of the --impl reference arm
+    ap.add_argument("--cpu-sample", "--ref-sample", dest="cpu_sample", type=int, default=64)   # pairs timed by the CPU arm; the same in both arms
+    ap.add_argument("--plugin-pairs", type=int, default=2048)  # pairs of the strings-in plugin measurement
+    ap.add_argument("--splade-chunks", type=int, default=10000)
+    ap.add_argument("--sparse-docs", type=int, default=1_000_000)
+    ap.add_argument("--rag-chunks", type=int, default=10000)
+    ap.add_argument("--rag-queries", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--no-precise", dest="precise", action="store_false")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries print while the run is in progress (NCCL's version
     # banner, torch warnings) goes to stderr instead

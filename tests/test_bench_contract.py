@@ -24,6 +24,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["config"]["workload"].startswith("ModernBERT-v2 span extraction")
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # both arms print the same `config` (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config()
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"].startswith(d["metric"])
 

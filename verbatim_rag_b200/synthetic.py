@@ -315,6 +315,40 @@ def make_sparse_rows(n: int, seed: int = 1002, vocab: int = 30522, mean_nnz: flo
     return indptr, indices, values
 
 
+def make_sparse_rows_device(n: int, seed: int = 1002, vocab: int = 30522, mean_nnz: float = 160.0,
+                            nnz_range: Tuple[int, int] = (16, 512), device="cuda", chunk: int = 100_000):
+    """Same distribution family as ``make_sparse_rows`` for corpora too large for its per-row Python loop (the 1 M-document
+    variant of BASELINE configs[1]): generated with torch on ``device`` in chunks, returned as host CSR.  Per row
+    ~1.25 x nnz Zipf(1.1) draws are de-duplicated, so the realised nnz is a little below the lognormal target."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    ranks = torch.arange(1, vocab + 1, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(ranks ** -1.1 / (ranks ** -1.1).sum(), 0).float()
+    perm = torch.from_numpy(np.random.default_rng(seed + 7).permutation(vocab)).to(device)
+    K = int(1.25 * nnz_range[1]) + 8
+    counts, idx_parts = [], []
+    for a in range(0, n, chunk):
+        m = min(chunk, n - a)
+        tgt = torch.exp(torch.randn(m, device=device, generator=g) * 0.35 + float(np.log(mean_nnz)))
+        tgt = tgt.round().clamp(nnz_range[0], nnz_range[1])
+        cand = (tgt * 1.25).long() + 8
+        u = torch.rand(m, K, device=device, generator=g)
+        tok = perm[torch.searchsorted(cdf, u).clamp_max(vocab - 1)]
+        tok = torch.where(torch.arange(K, device=device)[None, :] < cand[:, None], tok, torch.full_like(tok, vocab))
+        tok, _ = torch.sort(tok, dim=1)
+        keep = tok < vocab
+        keep[:, 1:] &= tok[:, 1:] != tok[:, :-1]
+        counts.append(keep.sum(1).cpu())
+        idx_parts.append(tok[keep].to(torch.int32).cpu())
+    nnz = torch.cat(counts).numpy().astype(np.int64)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(nnz, out=indptr[1:])
+    indices = torch.cat(idx_parts).numpy()
+    values = (np.abs(np.random.default_rng(seed + 11).standard_normal(indices.size, dtype=np.float32))
+              + np.float32(0.05)).astype(np.float32)
+    return indptr, indices, values
+
+
 def csr_to_dicts(indptr: np.ndarray, indices: np.ndarray, values: np.ndarray) -> List[Dict[int, float]]:
     """CSR -> the reference's ``List[Dict[int, float]]`` sparse format (embedding_providers.py:161-163)."""
     out = []
