@@ -47,6 +47,9 @@ struct vrag_encoder {
   };
   std::vector<MLayer> ml;
   float *final_g = nullptr, *head_g = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  float* cls_gw = nullptr;            // [2][768] head.norm.weight * classifier.weight (fused head, EPI_HEAD_PARTIAL)
+  float cls_g0 = 0.f, cls_g1 = 0.f;   // row sums of cls_gw
+  bool fused_head = true;             // VRAG_FUSED_HEAD=0: head.dense -> fp32 [T, 768] -> head_final_kernel (cross-check)
   __half *head_w = nullptr, *head_w_lo = nullptr;
   float *rope_g = nullptr, *rope_l = nullptr;  // [max_pos, 64] cos | sin tables (global / local theta)
   // BERT
@@ -209,6 +212,22 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
   e->cls_w = upload_f32(e, w.get("classifier.weight", 2LL * H), 2 * H);
   e->cls_b = upload_f32(e, w.get("classifier.bias", 2), 2);
+  {
+    const float* hg = w.get("head.norm.weight", H);
+    const float* cw = w.get("classifier.weight", 2LL * H);
+    std::vector<float> gw(2 * H);
+    double g0 = 0.0, g1 = 0.0;
+    for (int n = 0; n < H; ++n) {
+      gw[n] = hg[n] * cw[n];
+      gw[H + n] = hg[n] * cw[H + n];
+      g0 += static_cast<double>(gw[n]);
+      g1 += static_cast<double>(gw[H + n]);
+    }
+    e->cls_gw = upload_f32(e, gw.data(), 2 * H);
+    VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    e->cls_g0 = static_cast<float>(g0);
+    e->cls_g1 = static_cast<float>(g1);
+  }
   make_rope(e, 160000.0, e->max_pos, &e->rope_g);
   make_rope(e, 10000.0, e->max_pos, &e->rope_l);
   staging.release();
@@ -430,9 +449,18 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
   GemmEpiParams hd;
   hd.M = T; hd.out32 = e->buf32.as<float>(); hd.ld32 = H;
   hd.a_lo = h16_lo; hd.w_lo = pr ? e->head_w_lo : nullptr;
-  launch_gemm(ctx, EPI_GELU_F32, h16, e->head_w, T, H, H, hd, ref);
-  launch_head_final(ctx, e->buf32.as<float>(), T, e->head_g, 1e-5f, e->cls_w, e->cls_b, e->logits.as<float>(),
-                    e->probs.as<float>());
+  if (e->fused_head) {
+    // span-logit head in the GEMM epilogue: gelu + the LayerNorm / classifier partial sums, 96 B per token instead of
+    // a 6 KB fp32 round trip (buf32 doubles as the [6][T] float4 partial-sum buffer)
+    hd.cls_gw = e->cls_gw; hd.head_part = e->buf32.as<float>(); hd.hidden = H;
+    launch_gemm(ctx, EPI_HEAD_PARTIAL, h16, e->head_w, T, H, H, hd, ref);
+    launch_head_finish(ctx, e->buf32.as<float>(), T, H / 128, 1e-5f, e->cls_g0, e->cls_g1, e->cls_b, e->logits.as<float>(),
+                       e->probs.as<float>());
+  } else {
+    launch_gemm(ctx, EPI_GELU_F32, h16, e->head_w, T, H, H, hd, ref);
+    launch_head_final(ctx, e->buf32.as<float>(), T, e->head_g, 1e-5f, e->cls_w, e->cls_b, e->logits.as<float>(),
+                      e->probs.as<float>());
+  }
 }
 
 // BERT encoder stack: leaves the post-LN final hidden states in x32 (fp32) and h16 (fp16).
@@ -559,6 +587,8 @@ extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, i
     const char* bd = getenv("VRAG_BERT_DEFERRED_LN");   // (fp32 stream by TMA reduce-add + LayerNorm kernels)
     e->deferred_ln = e->deferred_ln && !(bd && bd[0] == '0');
   }
+  const char* fh = getenv("VRAG_FUSED_HEAD");
+  e->fused_head = !(fh && fh[0] == '0');
   if (e->precise) {   // fp32 residual stream + LayerNorm kernels; the split GEMMs have no deferred-LayerNorm epilogues
     e->deferred_ln = false;
     e->legacy_attention = false;

@@ -47,6 +47,9 @@ void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, cons
 // ModernBERT head tail: LN(buf32) * gamma -> classifier (2 x 768) + bias -> logits, P(class 1).
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
                        const float* cls_b, float* logits /*nullable*/, float* probs);
+// Fused head (gemm.cuh EPI_HEAD_PARTIAL): partial sums [slots][T] float4 -> logits, P(class 1).  g0 / g1 = sum_n cls_gw[c][n].
+void launch_head_finish(vrag_ctx* ctx, const float* head_part, int T, int slots, float eps, float g0, float g1,
+                        const float* cls_b, float* logits /*nullable*/, float* probs);
 // SPLADE CSR extraction from the dense [nseq, ld] buffer.
 void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
                          int32_t* counts);

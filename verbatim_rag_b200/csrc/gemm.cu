@@ -245,6 +245,33 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
       }
       if (valid) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32, v);
     }
+  } else if constexpr (EPI == EPI_HEAD_PARTIAL) {
+    float s1 = 0.f, s2 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      ld.load(c, v);
+      const float4* w0 = reinterpret_cast<const float4*>(p.cls_gw + col0 + c * 32);
+      const float4* w1 = reinterpret_cast<const float4*>(p.cls_gw + p.hidden + col0 + c * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = __ldg(w0 + i), b = __ldg(w1 + i);
+        const float wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float g = gelu_erf(v[4 * i + e]);
+          s1 += g;
+          s2 = fmaf(g, g, s2);
+          d0 = fmaf(g, wa[e], d0);
+          d1 = fmaf(g, wb[e], d1);
+        }
+      }
+      if ((c & 3) == 3) {   // 128 columns done: one slot
+        if (valid)
+          reinterpret_cast<float4*>(p.head_part)[static_cast<size_t>(2 * n_tile + (c >> 2)) * p.M + row] =
+              make_float4(s1, s2, d0, d1);
+        s1 = s2 = d0 = d1 = 0.f;
+      }
+    }
   } else if constexpr (EPI == EPI_SCORES) {
     // out32 row = one query, columns = corpus rows: 128 contiguous bytes per thread and chunk (ld32 % 4 == 0)
 #pragma unroll 1
@@ -1242,6 +1269,7 @@ void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M
     VRAG_CASE(EPI_NORM_BIAS_GELU_F16)
     VRAG_CASE(EPI_RESID_STATS_LN)
     VRAG_CASE(EPI_SCORES)
+    VRAG_CASE(EPI_HEAD_PARTIAL)
 #undef VRAG_CASE
     default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
   }

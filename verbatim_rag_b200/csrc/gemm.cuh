@@ -35,6 +35,12 @@ enum GemmEpi : int {
   EPI_NORM_BIAS_GELU_F16 = 15,  // out16 = gelu(rstd[row] * acc + bias)               (BERT intermediate)
   EPI_SCORES = 17,              // similarity scan as a GEMM (topk.cu, batched dense search): out32[m][n] = acc for the
                                 // n_valid real columns, -inf where col_mask[n] != 0 (deleted / filtered corpus rows)
+  EPI_HEAD_PARTIAL = 18,        // span-logit head fused into head.dense (ModernBERT prediction head + classifier):
+                                // g = gelu(acc); per row and 128 columns the four partial sums (sum g, sum g^2,
+                                // sum g * cls_gw[0][n], sum g * cls_gw[1][n]) -> head_part[slot][row] (float4, slot =
+                                // 2 * n_tile + column half).  cls_gw[c][n] = head.norm.weight[n] * classifier.weight[c][n]:
+                                // logits[c] = rstd * (D_c - mean * sum_n cls_gw[c][n]) + bias[c] needs only these sums
+                                // (rowops.cu head_finish_kernel), so the [T, 768] fp32 head activation is never stored.
   EPI_RESID_STATS_LN = 16,      // EPI_RESID_STATS with x_old = ((hi + lo) - mean[row]) * rstd[row] * gamma[col] + bias[col]
                                 // (bias = beta + the dense bias); reads stats_in, writes stats_out (different buffers)
 };
@@ -63,6 +69,8 @@ struct GemmEpiParams {
   int splade_ld = 0;
   int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail, EPI_SCORES corpus tail)
   const uint8_t* col_mask = nullptr;  // EPI_SCORES: [n_valid] bytes, != 0 -> the column scores -inf
+  const float* cls_gw = nullptr;      // EPI_HEAD_PARTIAL: [2][N] fp32
+  float* head_part = nullptr;         // EPI_HEAD_PARTIAL: [N / 128][M] float4
   int prof_class = 0;                 // profiler class the launch is booked under (common.cuh ProfClass; 0 = GEMM)
   const float* stats_in = nullptr;    // EPI_NORM_*: [stats_slots][M] float2 partial row moments of the A operand's rows
   float* stats_out = nullptr;         // EPI_RESID_STATS: [N / 128][M] float2

@@ -240,6 +240,31 @@ head_final_kernel(const float* __restrict__ buf32, int T, const float* __restric
   }
 }
 
+// Tail of the fused span-logit head (gemm.cuh EPI_HEAD_PARTIAL): per row the partial sums of g = gelu(head.dense x)
+// over `slots` column groups -> LayerNorm statistics -> logits[c] = rstd * (D_c - mean * G_c) + b_c, P(class 1).
+__global__ void __launch_bounds__(256)
+head_finish_kernel(const float4* __restrict__ part, int T, int slots, float inv_dim, float eps, float g0, float g1,
+                   const float* __restrict__ cb, float* __restrict__ logits, float* __restrict__ probs) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= T) return;
+  float s1 = 0.f, s2 = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int j = 0; j < slots; ++j) {
+    const float4 v = part[static_cast<size_t>(j) * T + row];
+    s1 += v.x; s2 += v.y; d0 += v.z; d1 += v.w;
+  }
+  const float mean = s1 * inv_dim;
+  const float var = fmaxf(s2 * inv_dim - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float l0 = rstd * (d0 - mean * g0) + cb[0], l1 = rstd * (d1 - mean * g1) + cb[1];
+  if (logits) {
+    logits[2 * static_cast<size_t>(row)] = l0;
+    logits[2 * static_cast<size_t>(row) + 1] = l1;
+  }
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  probs[row] = e1 / (e0 + e1);
+}
+
 // ---- SPLADE: dense [nseq, ld] -> CSR, entries > min_abs, ascending vocabulary index ----
 __global__ void splade_count_kernel(const float* __restrict__ dense, int ld, int vocab, float min_abs,
                                     int32_t* __restrict__ counts) {
@@ -405,6 +430,13 @@ void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* ga
   ProfScope prof(ctx, PROF_ROWOPS);
   head_final_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(buf32, T, gamma, eps, cls_w, cls_b, logits,
                                                                              probs);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_head_finish(vrag_ctx* ctx, const float* head_part, int T, int slots, float eps, float g0, float g1,
+                        const float* cls_b, float* logits, float* probs) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  head_finish_kernel<<<(T + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(head_part), T, slots,
+                                                                1.0f / H, eps, g0, g1, cls_b, logits, probs);
   VRAG_LAUNCHED(ctx);
 }
 void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
