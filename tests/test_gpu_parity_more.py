@@ -177,3 +177,29 @@ def test_outlier_channels_in_the_residual_stream(ctx, precision):
           stream_abs_median=stream_med, layer_rel_err=layer_rel, logit_std=float(ref.std()))
     assert np.isfinite(logits).all() and stream_max > 40.0 * stream_med
     assert err < (1e-3 if precision == "precise" else 1.4e-3), (err, layer_rel)   # fast: measured 1.13e-3 + 20 %
+
+
+def test_plugins_load_a_checkpoint_directory(tmp_path):
+    """Real-checkpoint load path on the GPU (extractors.py:151-157 / embedding_providers.py:125-136): a directory with
+    model.safetensors + tokenizer.json gives bit-identical outputs to the plugin built from the in-memory weights."""
+    import cases
+    from safetensors.numpy import save_file
+    from verbatim_rag_b200 import B200SpanExtractor, B200SpladeProvider
+    from verbatim_rag_b200.synthetic import BertSpec, ModernBertSpec, make_bert_mlm_weights, make_modernbert_weights
+    mspec, bspec = ModernBertSpec(layers=2), BertSpec(layers=2)
+    mw, bw = make_modernbert_weights(9, mspec), make_bert_mlm_weights(4, bspec)
+    mtok, btok = cases.tokenizer("modernbert"), cases.tokenizer("bert")
+    for name, w, tok in (("m", mw, mtok), ("b", bw, btok)):
+        os.makedirs(tmp_path / name)
+        save_file(w, str(tmp_path / name / "model.safetensors"))
+        tok.tok.save(str(tmp_path / name / "tokenizer.json"))
+    rng = np.random.default_rng(2)
+    q = mtok.make_question(rng, 11)
+    docs = [mtok.make_text(rng, n) for n in (120, 40, 300)]
+    a = B200SpanExtractor(str(tmp_path / "m"), max_tokens=2048)
+    b = B200SpanExtractor(weights=mw, tokenizer=mtok, num_layers=2, vocab_size=mspec.vocab_size, max_tokens=2048)
+    assert a.extract_detailed([(q, d) for d in docs]) == b.extract_detailed([(q, d) for d in docs])
+    texts = [btok.make_text(rng, n) for n in (64, 9)]
+    pa = B200SpladeProvider(str(tmp_path / "b"), max_tokens=2048)
+    pb = B200SpladeProvider(weights=bw, tokenizer=btok, num_layers=2, vocab_size=bspec.vocab_size, max_tokens=2048)
+    assert pa.embed_batch(texts) == pb.embed_batch(texts) and len(pa.embed_batch(texts)[0]) > 0
