@@ -99,6 +99,9 @@ int vrag_encoder_create(vrag_ctx* ctx, int kind, int num_layers, int vocab_size,
 #define VRAG_PRECISION_PRECISE 1
 int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, int vocab_size, int max_tokens,
                            const vrag_tensor* tensors, int num_tensors, int precision, vrag_encoder** out);
+/* Width of the encoder's hidden states = length of a vrag_dense_forward row: 768 (BERT-base / ModernBERT-base shapes)
+ * or 384 (MiniLM-class BERT encoders, the reference's default dense model: embedding_providers.py:55). */
+int vrag_encoder_hidden(vrag_encoder* enc);
 void vrag_encoder_destroy(vrag_encoder* enc);
 
 /* Token-classification forward over `nseq` unpadded sequences packed back to back:

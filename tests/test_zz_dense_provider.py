@@ -64,3 +64,55 @@ def test_dense_provider_surface():
     assert all(type(x) is float for v in batch for x in v) and all(len(v) == 768 for v in batch)
     for t, b in zip(texts, batch):
         assert prov.embed_text(t) == b
+
+
+@pytest.mark.parametrize("precision,tol", [("fast", 5e-4), ("precise", 2e-5)])
+@pytest.mark.parametrize("pooling", ["mean", "cls"])
+def test_minilm_shape_dense_forward_vs_oracle(pooling, precision, tol):
+    """The reference's DEFAULT dense model is all-MiniLM-L6-v2 (embedding_providers.py:55): BERT architecture, 6 layers,
+    hidden 384, 12 heads x 32, FFN 1536.  Same kernels: heads zero-padded to 64 dims at load time, N padded to the GEMM
+    tile with clipped stores, 384-wide row kernels."""
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import BertSpec, make_bert_mlm_weights
+    from oracle.bert_splade import dense_encode
+    spec = BertSpec(hidden=384, intermediate=1536, layers=6, heads=12, head_dim=32)
+    w = make_bert_mlm_weights(1003, spec)
+    rng = np.random.default_rng(7)
+    seqs = []
+    for L in [128, 256, 31, 2, 300, 77]:
+        s = rng.integers(1000, spec.vocab_size, size=L)
+        s[0], s[-1] = spec.cls_id, spec.sep_id
+        seqs.append(s.astype(np.int64))
+    ctx = _native.default_context(0)
+    enc = _native.Encoder(ctx, _native.ENC_BERT_DENSE, w, spec.layers, spec.vocab_size, max_tokens=2048, precision=precision)
+    assert enc.hidden == 384
+    ids, cu = _native.Encoder._pack(seqs)
+    got = enc.dense_forward(ids, cu, _native.POOL_MEAN if pooling == "mean" else _native.POOL_CLS, True)
+    enc.close()
+    ref = dense_encode(w, seqs, spec, pooling=pooling, normalize=True)
+    assert got.shape == ref.shape == (len(seqs), 384) and np.isfinite(got).all()
+    err = float(np.abs(got - ref).max())
+    assert err < tol, err
+    assert (got * ref).sum(axis=1).min() > 0.99999
+
+
+def test_minilm_shape_provider_and_store():
+    """B200DenseProvider(MiniLM shape).get_dimension() == 384 and its vectors drop into B200VectorStore(dense_dim=384),
+    the reference's default pairing (milvus_local.py:22 dense_dim=384)."""
+    from verbatim_rag_b200 import B200DenseProvider, B200VectorStore
+    from verbatim_rag_b200.synthetic import BertSpec, SyntheticTokenizer, make_bert_mlm_weights
+    spec = BertSpec(hidden=384, intermediate=1536, layers=2, heads=12, head_dim=32)
+    tok = SyntheticTokenizer("bert")
+    prov = B200DenseProvider(weights=make_bert_mlm_weights(1003, spec), tokenizer=tok, num_layers=spec.layers,
+                             vocab_size=spec.vocab_size)
+    assert prov.get_dimension() == 384
+    rng = np.random.default_rng(8)
+    texts = [tok.make_text(rng, int(n)) for n in rng.integers(10, 120, size=40)]
+    vecs = prov.embed_batch(texts)
+    assert all(len(v) == 384 for v in vecs)
+    store = B200VectorStore(dense_dim=384, enable_dense=True, enable_sparse=False)
+    ids = [f"t{i}" for i in range(len(texts))]
+    store.add_vectors(ids, vecs, None, texts, texts, [{} for _ in texts])
+    for i in (0, 17, 39):
+        hit = store.query(dense_query=prov.embed_text(texts[i]), top_k=1, search_type="dense")[0]
+        assert hit.id == ids[i] and abs(hit.score - 1.0) < 1e-5

@@ -31,7 +31,7 @@ EXPORTS = [
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
     "vrag_encoder_create_ex", "vrag_selftest_gemm_split", "vrag_bench_gemm_split", "vrag_selftest_attention_split",
-    "vrag_bench_attention_split",
+    "vrag_bench_attention_split", "vrag_encoder_hidden",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_encoder_create": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, P(vp)]),
             "vrag_encoder_create_ex": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, i32, P(vp)]),
             "vrag_encoder_destroy": (None, [vp]),
+            "vrag_encoder_hidden": (i32, [vp]),
             "vrag_selftest_gemm_split": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
             "vrag_bench_gemm_split": (i32, [vp, i32, i32, i32, i32, i32, P(f64)]),
             "vrag_selftest_attention_split": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
@@ -288,6 +289,7 @@ class Encoder:
         self.h = h
         self.num_layers = num_layers
         self.vocab_size = vocab_size
+        self.hidden = int(ctx.lib.vrag_encoder_hidden(h))
 
     @staticmethod
     def _pack(seqs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
@@ -362,7 +364,7 @@ class Encoder:
     def dense_forward(self, ids: np.ndarray, cu: np.ndarray, pooling: int = POOL_MEAN, normalize: bool = True):
         ids = _np(ids, np.int32)
         cu = _np(cu, np.int32)
-        out = np.empty((len(cu) - 1, 768), dtype=np.float32)
+        out = np.empty((len(cu) - 1, self.hidden), dtype=np.float32)
         self.ctx.check(self.ctx.lib.vrag_dense_forward(self.h, _ptr(ids), _ptr(cu), len(cu) - 1, pooling,
                                                        1 if normalize else 0, _ptr(out), 0))
         return out

@@ -22,7 +22,8 @@ using namespace vrag;
 struct vrag_encoder {
   vrag_ctx* ctx = nullptr;
   int kind = 0, layers = 0, vocab = 0, vocab_pad = 0, max_tokens = 0, max_seqs = 0, max_pos = 0;
-  int ffn = 0;  // GeGLU width (1152) or FFN width (3072)
+  int ffn = 0;  // GeGLU width (1152) or FFN width (3072 / 1536)
+  int hidden = vrag::HIDDEN;  // residual-stream width: 768, or 384 for MiniLM-class BERT encoders (12 heads x 32)
   bool use_reference_gemm = false;
   bool legacy_attention = false;
   bool deferred_ln = true;  // LayerNorm folded into the GEMMs (EPI_RESID_STATS* / EPI_NORM_*), no LN kernels in the stack
@@ -233,27 +234,57 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
   staging.release();
 }
 
+int pad256(int n) { return (n + GEMM_BN - 1) / GEMM_BN * GEMM_BN; }
+
+// BERT-architecture encoders at hidden size H = 768 (12 heads x 64) or H = 384 (12 heads x 32, the MiniLM family).
+// The attention kernel works on 12 heads x 64 dims; narrower heads are ZERO-PADDED to 64 dims when the checkpoint is
+// repacked: q | k | v rows of head h, dim d < dh go to row h * 64 + d of a [3 * 768, H] operand (rows d >= dh are zero,
+// so q k^T is unchanged and the padded dims of P V come out as exact zeros), the columns of attention.output.dense are
+// spread the same way ([H, 768]), and q is pre-scaled by sqrt(64 / dh) because the kernel's softmax scale is 1 / sqrt(64).
+// Every other Linear keeps its shape with N padded to a multiple of 256 by zero rows (TMA stores clip at the real width).
 void build_bert(vrag_encoder* e, const WeightSet& w) {
-  const int H = HIDDEN, I = 3072;
-  e->ffn = I;
-  e->max_pos = 512;
-  DevBuf staging;
   const std::string em = "bert.embeddings.";
+  auto numel = [&](const std::string& name) -> int64_t {
+    auto it = w.m.find(name);
+    if (it == w.m.end()) throw Error(VRAG_ERR_WEIGHTS, "missing tensor '" + name + "'");
+    return it->second->numel;
+  };
+  const int H = static_cast<int>(numel(em + "LayerNorm.weight"));
+  VRAG_CHECK(H == 768 || H == 384, VRAG_ERR_WEIGHTS, "BERT encoder: hidden size must be 768 or 384, got " + std::to_string(H));
+  const int I = static_cast<int>(numel("bert.encoder.layer.0.intermediate.dense.bias"));
+  VRAG_CHECK(I % GEMM_BK == 0 && I <= 4096, VRAG_ERR_WEIGHTS, "BERT encoder: unsupported intermediate size " + std::to_string(I));
+  const int heads = 12, dh = H / heads, AW = heads * 64;   // AW: padded attention width = 768
+  const float qscale = sqrtf(64.0f / static_cast<float>(dh));
+  e->hidden = H;
+  e->ffn = I;
+  e->max_pos = static_cast<int>(numel(em + "position_embeddings.weight") / H);
+  if (H != HIDDEN) e->deferred_ln = false;   // the deferred-LayerNorm epilogues are built for 768-wide rows (6 moment slots)
+  const int Hp = pad256(H), Ip = pad256(I);
+  DevBuf staging;
   const float* wemb = w.get(em + "word_embeddings.weight", (int64_t)e->vocab * H);
   e->emb = upload_f32(e, wemb, (size_t)e->vocab * H);
   e->pos_emb = upload_f32(e, w.get(em + "position_embeddings.weight", (int64_t)e->max_pos * H), (size_t)e->max_pos * H);
   e->type_emb = upload_f32(e, w.get(em + "token_type_embeddings.weight", 2LL * H), 2 * H);
   e->emb_g = upload_f32(e, w.get(em + "LayerNorm.weight", H), H);
   e->emb_b = upload_f32(e, w.get(em + "LayerNorm.bias", H), H);
-  std::vector<float> cat(static_cast<size_t>(3 * H) * H), bcat(3 * H), folded(static_cast<size_t>(I) * H), cbias(I);
+  std::vector<float> cat(static_cast<size_t>(3 * AW) * H), bcat(3 * AW), folded(static_cast<size_t>(std::max(I, 3 * AW)) * H),
+      cbias(std::max(I, 3 * AW)), wo_pad(static_cast<size_t>(H) * AW);
   for (int i = 0; i < e->layers; ++i) {
     const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
     vrag_encoder::BLayer L{};
     const char* nm[3] = {"query", "key", "value"};
+    std::fill(cat.begin(), cat.end(), 0.f);
+    std::fill(bcat.begin(), bcat.end(), 0.f);
     for (int j = 0; j < 3; ++j) {
-      memcpy(&cat[static_cast<size_t>(j) * H * H], w.get(p + "attention.self." + nm[j] + ".weight", (int64_t)H * H),
-             sizeof(float) * H * H);
-      memcpy(&bcat[static_cast<size_t>(j) * H], w.get(p + "attention.self." + nm[j] + ".bias", H), sizeof(float) * H);
+      const float* wj = w.get(p + "attention.self." + nm[j] + ".weight", (int64_t)H * H);
+      const float* bj = w.get(p + "attention.self." + nm[j] + ".bias", H);
+      const float sc = j == 0 ? qscale : 1.0f;
+      for (int h = 0; h < heads; ++h)
+        for (int d = 0; d < dh; ++d) {
+          const size_t dst = static_cast<size_t>(j * AW + h * 64 + d), src = static_cast<size_t>(h * dh + d);
+          for (int k = 0; k < H; ++k) cat[dst * H + k] = wj[src * H + k] * sc;
+          bcat[dst] = bj[src] * sc;
+        }
     }
     // LayerNorm that produced this layer's input: the embedding LayerNorm (layer 0) or the previous output.LayerNorm
     const float* ga = i == 0 ? w.get(em + "LayerNorm.weight", H)
@@ -261,17 +292,22 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
     const float* ba = i == 0 ? w.get(em + "LayerNorm.bias", H)
                              : w.get("bert.encoder.layer." + std::to_string(i - 1) + ".output.LayerNorm.bias", H);
     if (e->deferred_ln) {
-      fold_layernorm_bias(cat.data(), ba, bcat.data(), 3 * H, H, cbias.data());
-      L.cqkv = upload_f32(e, cbias.data(), 3 * H);
-      fold_layernorm(cat.data(), ga, 3 * H, H, folded.data());
-      L.wqkv = upload_f16(e, staging, folded.data(), 3 * H, H);
+      fold_layernorm_bias(cat.data(), ba, bcat.data(), 3 * AW, H, cbias.data());
+      L.cqkv = upload_f32(e, cbias.data(), 3 * AW);
+      fold_layernorm(cat.data(), ga, 3 * AW, H, folded.data());
+      L.wqkv = upload_f16(e, staging, folded.data(), 3 * AW, H);
     } else {
-      L.wqkv = upload_f16(e, staging, cat.data(), 3 * H, H, 0, &L.wqkv_lo);
+      L.wqkv = upload_f16(e, staging, cat.data(), 3 * AW, H, 0, &L.wqkv_lo);
     }
-    L.bqkv = upload_f32(e, bcat.data(), 3 * H);
+    L.bqkv = upload_f32(e, bcat.data(), 3 * AW);
     VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // bcat / cbias / folded reused next layer
-    L.wo = upload_f16(e, staging, w.get(p + "attention.output.dense.weight", (int64_t)H * H), H, H, 0, &L.wo_lo);
-    L.bo = upload_f32(e, w.get(p + "attention.output.dense.bias", H), H);
+    const float* wo = w.get(p + "attention.output.dense.weight", (int64_t)H * H);
+    std::fill(wo_pad.begin(), wo_pad.end(), 0.f);
+    for (int n = 0; n < H; ++n)
+      for (int h = 0; h < heads; ++h)
+        for (int d = 0; d < dh; ++d) wo_pad[static_cast<size_t>(n) * AW + h * 64 + d] = wo[static_cast<size_t>(n) * H + h * dh + d];
+    L.wo = upload_f16(e, staging, wo_pad.data(), H, AW, Hp, &L.wo_lo);
+    L.bo = upload_f32(e, w.get(p + "attention.output.dense.bias", H), H, Hp);
     L.g1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.weight", H), H);
     L.b1 = upload_f32(e, w.get(p + "attention.output.LayerNorm.bias", H), H);
     const float* wi = w.get(p + "intermediate.dense.weight", (int64_t)I * H);
@@ -280,9 +316,9 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
     const float* b1 = w.get(p + "attention.output.LayerNorm.bias", H);
     if (e->deferred_ln) {
       fold_layernorm_bias(wi, b1, bi, I, H, cbias.data());
-      L.ci = upload_f32(e, cbias.data(), I);
+      L.ci = upload_f32(e, cbias.data(), I, Ip);
       fold_layernorm(wi, g1, I, H, folded.data());
-      L.wi = upload_f16(e, staging, folded.data(), I, H);
+      L.wi = upload_f16(e, staging, folded.data(), I, H, Ip);
       // residual GEMMs: old stream normalised with (ga, ba) before attention.output, with (g1, b1) before output
       const float* bo = w.get(p + "attention.output.dense.bias", H);
       const float* bo2 = w.get(p + "output.dense.bias", H);
@@ -296,19 +332,20 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
       L.rb_b = upload_f32(e, t.data(), H);
       VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
     } else {
-      L.wi = upload_f16(e, staging, wi, I, H, 0, &L.wi_lo);
+      L.wi = upload_f16(e, staging, wi, I, H, Ip, &L.wi_lo);
     }
-    L.bi = upload_f32(e, bi, I);
-    L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I, 0, &L.wo2_lo);
-    L.bo2 = upload_f32(e, w.get(p + "output.dense.bias", H), H);
+    L.bi = upload_f32(e, bi, I, Ip);
+    L.wo2 = upload_f16(e, staging, w.get(p + "output.dense.weight", (int64_t)H * I), H, I, Hp, &L.wo2_lo);
+    L.bo2 = upload_f32(e, w.get(p + "output.dense.bias", H), H, Hp);
     L.g2 = upload_f32(e, w.get(p + "output.LayerNorm.weight", H), H);
     L.b2 = upload_f32(e, w.get(p + "output.LayerNorm.bias", H), H);
+    VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // wo_pad reused next layer
     e->bl.push_back(L);
   }
   if (e->kind == VRAG_ENC_BERT_MLM) {
     const std::string c = "cls.predictions.";
-    e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H, 0, &e->mlm_w_lo);
-    e->mlm_b = upload_f32(e, w.get(c + "transform.dense.bias", H), H);
+    e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H, Hp, &e->mlm_w_lo);
+    e->mlm_b = upload_f32(e, w.get(c + "transform.dense.bias", H), H, Hp);
     e->mlm_g = upload_f32(e, w.get(c + "transform.LayerNorm.weight", H), H);
     e->mlm_beta = upload_f32(e, w.get(c + "transform.LayerNorm.bias", H), H);
     // decoder is tied to the word embeddings (modeling_bert.py:471-511); pad the vocabulary to a tile multiple
@@ -320,23 +357,23 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
 }
 
 void reserve_workspace(vrag_encoder* e) {
-  const size_t T = e->max_tokens, H = HIDDEN;
+  const size_t T = e->max_tokens, H = e->hidden, AW = HIDDEN;   // AW: attention width (12 heads x 64, padded for H = 384)
   e->ids.reserve(T * 4);
   e->pos.reserve(T * 4);
   e->seqrow.reserve(T * 4);
   e->cu.reserve((static_cast<size_t>(e->max_seqs) + 1) * 4);
   e->x32.reserve(T * H * 4);
   e->h16.reserve(T * H * 2);
-  e->qkv16.reserve(T * 3 * H * 2);
-  e->o16.reserve(T * H * 2);
+  e->qkv16.reserve(T * 3 * AW * 2);
+  e->o16.reserve(T * AW * 2);
   e->w16.reserve(T * e->ffn * 2);
   e->buf32.reserve(T * H * 4);
   e->probs.reserve(T * 4);
   e->logits.reserve(T * 8);
   if (e->precise) {
     e->h16_lo.reserve(T * H * 2);
-    e->qkv16_lo.reserve(T * 3 * H * 2);
-    e->o16_lo.reserve(T * H * 2);
+    e->qkv16_lo.reserve(T * 3 * AW * 2);
+    e->o16_lo.reserve(T * AW * 2);
     e->w16_lo.reserve(T * e->ffn * 2);
   }
   if (e->deferred_ln) {
@@ -466,7 +503,8 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
 // BERT encoder stack: leaves the post-LN final hidden states in x32 (fp32) and h16 (fp16).
 void bert_stack(vrag_encoder* e, const Pass& ps) {
   vrag_ctx* ctx = e->ctx;
-  const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0, H = HIDDEN, I = e->ffn;
+  const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0, H = e->hidden, I = e->ffn, AW = HIDDEN;
+  const int Hp = pad256(H), Ip = pad256(I);   // GEMM N (weights zero-padded); outputs keep their real widths
   const int ref = e->use_reference_gemm ? 1 : 0;
   float* x32 = e->x32.as<float>();
   __half *h16 = e->h16.as<__half>(), *qkv = e->qkv16.as<__half>(), *o16 = e->o16.as<__half>(), *f16 = e->w16.as<__half>();
@@ -509,28 +547,28 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
   __half* o16_lo = pr ? e->o16_lo.as<__half>() : nullptr;
   __half* f16_lo = pr ? e->w16_lo.as<__half>() : nullptr;
   launch_bert_embed_ln(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
-                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16, h16_lo);
+                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16, h16_lo, H);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->bl[i];
     GemmEpiParams p;
-    p.M = T; p.out16 = qkv; p.ld16 = 3 * H; p.bias = L.bqkv;
+    p.M = T; p.out16 = qkv; p.ld16 = 3 * AW; p.bias = L.bqkv;
     p.a_lo = h16_lo; p.w_lo = pr ? L.wqkv_lo : nullptr; p.out16_lo = qkv_lo;
-    launch_gemm(ctx, EPI_BIAS_F16, h16, L.wqkv, T, 3 * H, H, p, ref);
+    launch_gemm(ctx, EPI_BIAS_F16, h16, L.wqkv, T, 3 * AW, H, p, ref);
     e->attention(qkv, o16, ns, T, ps.max_len, -1);
     GemmEpiParams r;
-    r.M = T; r.out32 = x32; r.ld32 = H; r.bias = L.bo;
+    r.M = T; r.out32 = x32; r.ld32 = H; r.bias = L.bo; r.n_valid = H;
     r.a_lo = o16_lo; r.w_lo = pr ? L.wo_lo : nullptr;
-    launch_gemm(ctx, EPI_BIAS_RESID_F32, o16, L.wo, T, H, H, r, ref);
-    launch_layernorm(ctx, x32, T, L.g1, L.b1, 1e-12f, h16, true, h16_lo);
+    launch_gemm(ctx, EPI_BIAS_RESID_F32, o16, L.wo, T, Hp, AW, r, ref);
+    launch_layernorm(ctx, x32, T, L.g1, L.b1, 1e-12f, h16, true, h16_lo, H);
     GemmEpiParams f;
-    f.M = T; f.out16 = f16; f.ld16 = I; f.bias = L.bi;
+    f.M = T; f.out16 = f16; f.ld16 = I; f.bias = L.bi; f.n_valid = I;
     f.a_lo = h16_lo; f.w_lo = pr ? L.wi_lo : nullptr; f.out16_lo = f16_lo;
-    launch_gemm(ctx, EPI_BIAS_GELU_F16, h16, L.wi, T, I, H, f, ref);
+    launch_gemm(ctx, EPI_BIAS_GELU_F16, h16, L.wi, T, Ip, H, f, ref);
     GemmEpiParams r2;
-    r2.M = T; r2.out32 = x32; r2.ld32 = H; r2.bias = L.bo2;
+    r2.M = T; r2.out32 = x32; r2.ld32 = H; r2.bias = L.bo2; r2.n_valid = H;
     r2.a_lo = f16_lo; r2.w_lo = pr ? L.wo2_lo : nullptr;
-    launch_gemm(ctx, EPI_BIAS_RESID_F32, f16, L.wo2, T, H, I, r2, ref);
-    launch_layernorm(ctx, x32, T, L.g2, L.b2, 1e-12f, h16, true, h16_lo);
+    launch_gemm(ctx, EPI_BIAS_RESID_F32, f16, L.wo2, T, Hp, I, r2, ref);
+    launch_layernorm(ctx, x32, T, L.g2, L.b2, 1e-12f, h16, true, h16_lo, H);
   }
 }
 
@@ -602,6 +640,8 @@ extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, i
   VRAG_API_END()
 }
 
+extern "C" int vrag_encoder_hidden(vrag_encoder* enc) { return enc ? enc->hidden : -1; }
+
 extern "C" void vrag_encoder_destroy(vrag_encoder* enc) {
   if (!enc) return;
   cudaSetDevice(enc->ctx->device);
@@ -662,7 +702,7 @@ extern "C" int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const 
     VRAG_CHECK(cu[i + 1] > cu[i], VRAG_ERR_ARG, "splade_forward: empty sequence");
     VRAG_CHECK(cu[i + 1] - cu[i] <= enc->max_pos, VRAG_ERR_ARG, "splade_forward: sequence longer than 512 tokens");
   }
-  const int H = HIDDEN, V = enc->vocab, VP = enc->vocab_pad;
+  const int H = enc->hidden, V = enc->vocab, VP = enc->vocab_pad;
   const int ref = enc->use_reference_gemm ? 1 : 0;
   // the dense pooled buffer is [seqs_per_pass, VP] fp32: bound sequences per pass to 512 (60 MB)
   auto passes = plan_passes(cu, nseq, enc->max_tokens, std::min(enc->max_seqs, 512));
@@ -674,11 +714,11 @@ extern "C" int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const 
     bert_stack(enc, ps);
     GemmEpiParams t;
     __half* h16_lo = enc->precise ? enc->h16_lo.as<__half>() : nullptr;
-    t.M = T; t.out32 = enc->buf32.as<float>(); t.ld32 = H; t.bias = enc->mlm_b;
+    t.M = T; t.out32 = enc->buf32.as<float>(); t.ld32 = H; t.bias = enc->mlm_b; t.n_valid = H;
     t.a_lo = h16_lo; t.w_lo = enc->precise ? enc->mlm_w_lo : nullptr;
-    launch_gemm(_ctx, EPI_BIAS_GELU_F32, enc->h16.as<__half>(), enc->mlm_w, T, H, H, t, ref);
+    launch_gemm(_ctx, EPI_BIAS_GELU_F32, enc->h16.as<__half>(), enc->mlm_w, T, pad256(H), H, t, ref);
     launch_layernorm(_ctx, enc->buf32.as<float>(), T, enc->mlm_g, enc->mlm_beta, 1e-12f, enc->h16.as<__half>(), false,
-                     h16_lo);
+                     h16_lo, H);
     enc->splade.reserve(static_cast<size_t>(ns) * VP * 4);
     VRAG_CUDA(cudaMemsetAsync(enc->splade.p, 0, static_cast<size_t>(ns) * VP * 4, _ctx->stream));
     GemmEpiParams sp;
@@ -742,9 +782,10 @@ extern "C" int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const i
     const int ns = ps.s1 - ps.s0;
     stage_pass(enc, ps, ids, cu, on_device);
     bert_stack(enc, ps);
-    enc->pooled.reserve(static_cast<size_t>(ns) * HIDDEN * 4);
-    launch_pool(_ctx, enc->x32.as<float>(), enc->cu.as<int32_t>(), ns, pooling, normalize, enc->pooled.as<float>());
-    VRAG_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(ps.s0) * HIDDEN, enc->pooled.p, static_cast<size_t>(ns) * HIDDEN * 4,
+    const int H = enc->hidden;
+    enc->pooled.reserve(static_cast<size_t>(ns) * H * 4);
+    launch_pool(_ctx, enc->x32.as<float>(), enc->cu.as<int32_t>(), ns, pooling, normalize, enc->pooled.as<float>(), H);
+    VRAG_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(ps.s0) * H, enc->pooled.p, static_cast<size_t>(ns) * H * 4,
                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, _ctx->stream));
     VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
   }

@@ -5,7 +5,9 @@
 
 namespace vrag {
 
-constexpr int HIDDEN = 768;  // all supported encoders are *-base: H = 768, 12 heads x 64
+constexpr int HIDDEN = 768;  // ModernBERT-base / BERT-base: H = 768, 12 heads x 64.  BERT encoders also run at H = 384
+                             // (12 heads x 32: the MiniLM family, the reference's default dense model,
+                             // embedding_providers.py:55) on the same kernels: heads are zero-padded to 64 dims.
 
 // attention.cu
 void launch_attention(vrag_ctx* ctx, const __half* qkv, __half* out, const int32_t* cu_seqlens_dev, int nseq,
@@ -39,11 +41,12 @@ void launch_bert_embed_raw(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos
 void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int T, float* x32);
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
-                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo = nullptr);
+                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo = nullptr,
+                          int hidden = HIDDEN);
 // h16 = LN(x32) * gamma (+ beta); if write_back, x32 is overwritten with the normalised row too (post-LN residual).
 // h16_lo (nullable): low plane of h16 (split-precision mode).
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps,
-                      __half* h16, bool write_back, __half* h16_lo = nullptr);
+                      __half* h16, bool write_back, __half* h16_lo = nullptr, int hidden = HIDDEN);
 // ModernBERT head tail: LN(buf32) * gamma -> classifier (2 x 768) + bias -> logits, P(class 1).
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
                        const float* cls_b, float* logits /*nullable*/, float* probs);
@@ -56,7 +59,7 @@ void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, in
 void launch_splade_fill(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,
                         const int64_t* indptr_dev, int32_t* indices, float* values);
 void launch_pool(vrag_ctx* ctx, const float* x32, const int32_t* cu_seqlens_dev, int nseq, int pooling,
-                 int normalize, float* out);
+                 int normalize, float* out, int hidden = HIDDEN);
 void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n);
 
 }  // namespace vrag

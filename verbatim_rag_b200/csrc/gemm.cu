@@ -198,6 +198,11 @@ struct ReferenceLoader {  // SIMT dot products (debug / self test)
   }
 };
 
+// Direct-store epilogues: N may be padded to a multiple of 256 (weights zero-padded) while the output is narrower --
+// chunks of 32 columns at or beyond n_valid (a multiple of 32; 0 = no limit) are not stored.  (The TMA-store epilogues
+// need no check: boxes outside the tensor map are clipped by the hardware.)
+__device__ __forceinline__ bool col_in(const GemmEpiParams& p, int col) { return p.n_valid == 0 || col < p.n_valid; }
+
 // The fused tail for one thread == one output row of one 128x256 tile.  All 32 lanes of a warp call this together.
 template <int EPI, typename Loader>
 __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, int n_tile, const Loader& ld,
@@ -226,7 +231,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (valid) {
+      if (valid && col_in(p, col0 + c * 32)) {
         const size_t o = static_cast<size_t>(row) * p.ld16 + col0 + c * 32;
         store_half32_split(p.out16 + o, p.out16_lo ? p.out16_lo + o : nullptr, v);
       }
@@ -243,7 +248,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (valid) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32, v);
+      if (valid && col_in(p, col0 + c * 32)) store_float32(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32, v);
     }
   } else if constexpr (EPI == EPI_HEAD_PARTIAL) {
     float s1 = 0.f, s2 = 0.f, d0 = 0.f, d1 = 0.f;
@@ -296,7 +301,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       ld.load(c, v);
-      if (valid) {
+      if (valid && col_in(p, col0 + c * 32)) {
         float4* x4 = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(row) * p.ld32 + col0 + c * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

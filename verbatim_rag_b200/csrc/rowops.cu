@@ -9,7 +9,7 @@ namespace vrag {
 namespace {
 
 constexpr int H = HIDDEN;
-constexpr int VEC = H / 128;  // float4 per lane = 6
+constexpr int VEC = H / 128;  // float4 per lane = 6 (768-wide rows); the BERT kernels also exist for VEC = 3 (384)
 constexpr int ROWS_PER_BLOCK = 8;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -19,8 +19,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Normalise the row held as v[VEC] float4 per lane (element index = (i*32 + lane)*4 + e).
+template <int VEC>
 __device__ __forceinline__ void ln_row(float4 (&v)[VEC], const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int lane) {
+  constexpr int H = VEC * 128;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -46,6 +48,7 @@ __device__ __forceinline__ void ln_row(float4 (&v)[VEC], const float* __restrict
 // lo8_row (optional): the rounding remainder v - fp16(v) as e5m2, so that hi + lo carries the row to >= 14 bits
 // (the two-plane residual stream of the deferred-LayerNorm path, gemm.cuh EPI_RESID_STATS).
 // lo16_row (optional): the same remainder as fp16 -- the low plane of the split-precision ("precise") mode, gemm.cuh.
+template <int VEC>
 __device__ __forceinline__ void store_row(const float4 (&v)[VEC], float* x32_row, __half* h16_row, int lane,
                                           uint8_t* lo8_row = nullptr, __half* lo16_row = nullptr) {
 #pragma unroll
@@ -136,11 +139,13 @@ hilo_to_f32_kernel(const __half* __restrict__ hi, const uint8_t* __restrict__ lo
   store_row(v, x32 + static_cast<size_t>(row) * H, nullptr, lane);
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int T, int vocab, int max_pos,
                      const float* __restrict__ wemb, const float* __restrict__ pemb, const float* __restrict__ temb0,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      float* __restrict__ x32, __half* __restrict__ h16, __half* __restrict__ lo16) {
+  constexpr int H = VEC * 128;
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   int id = ids[row];
@@ -193,9 +198,11 @@ bert_embed_raw_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict
     reinterpret_cast<float2*>(stats)[static_cast<size_t>(lane) * T + row] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 layernorm_kernel(float* __restrict__ x32, int T, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, __half* __restrict__ h16, int write_back, __half* __restrict__ lo16) {
+  constexpr int H = VEC * 128;
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   float* xr = x32 + static_cast<size_t>(row) * H;
@@ -315,13 +322,14 @@ splade_fill_kernel(const float* __restrict__ dense, int ld, int vocab, float min
 // ---- sentence pooling over the fp32 final hidden states ----
 __global__ void __launch_bounds__(256)
 pool_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int pooling, int normalize,
-            float* __restrict__ out) {
+            float* __restrict__ out, int H) {
   const int s = blockIdx.x;
   const int a = cu[s], b = cu[s + 1];
   __shared__ float red[256];
-  float acc[3] = {0.f, 0.f, 0.f};
+  float acc[3] = {0.f, 0.f, 0.f};   // H <= 768
   for (int j = 0; j < 3; ++j) {
     const int c = threadIdx.x + j * 256;
+    if (c >= H) continue;
     if (pooling == VRAG_POOL_CLS) {
       acc[j] = b > a ? x32[static_cast<size_t>(a) * H + c] : 0.f;
     } else {
@@ -340,7 +348,8 @@ pool_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int p
     }
     scale = 1.f / fmaxf(sqrtf(red[0]), 1e-12f);
   }
-  for (int j = 0; j < 3; ++j) out[static_cast<size_t>(s) * H + threadIdx.x + j * 256] = acc[j] * scale;
+  for (int j = 0; j < 3; ++j)
+    if (threadIdx.x + j * 256 < H) out[static_cast<size_t>(s) * H + threadIdx.x + j * 256] = acc[j] * scale;
 }
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
@@ -411,18 +420,29 @@ void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int 
 }
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
-                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo) {
+                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo, int hidden) {
   ProfScope prof(ctx, PROF_ROWOPS);
-  bert_embed_ln_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
-                                                                                pos_emb, type_emb0, gamma, beta, eps,
-                                                                                x32, h16, h16_lo);
+  VRAG_CHECK(hidden == 768 || hidden == 384, VRAG_ERR_ARG, "row kernels: hidden size must be 768 or 384");
+  if (hidden == 768)
+    bert_embed_ln_kernel<6><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
+                                                                                   pos_emb, type_emb0, gamma, beta, eps,
+                                                                                   x32, h16, h16_lo);
+  else
+    bert_embed_ln_kernel<3><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
+                                                                                   pos_emb, type_emb0, gamma, beta, eps,
+                                                                                   x32, h16, h16_lo);
   VRAG_LAUNCHED(ctx);
 }
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps, __half* h16,
-                      bool write_back, __half* h16_lo) {
+                      bool write_back, __half* h16_lo, int hidden) {
   ProfScope prof(ctx, PROF_ROWOPS);
-  layernorm_kernel<<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
-                                                                            write_back ? 1 : 0, h16_lo);
+  VRAG_CHECK(hidden == 768 || hidden == 384, VRAG_ERR_ARG, "row kernels: hidden size must be 768 or 384");
+  if (hidden == 768)
+    layernorm_kernel<6><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
+                                                                               write_back ? 1 : 0, h16_lo);
+  else
+    layernorm_kernel<3><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(x32, T, gamma, beta, eps, h16,
+                                                                               write_back ? 1 : 0, h16_lo);
   VRAG_LAUNCHED(ctx);
 }
 void launch_head_final(vrag_ctx* ctx, const float* buf32, int T, const float* gamma, float eps, const float* cls_w,
@@ -452,9 +472,9 @@ void launch_splade_fill(vrag_ctx* ctx, const float* dense, int nseq, int ld, int
   VRAG_LAUNCHED(ctx);
 }
 void launch_pool(vrag_ctx* ctx, const float* x32, const int32_t* cu, int nseq, int pooling, int normalize,
-                 float* out) {
+                 float* out, int hidden) {
   ProfScope prof(ctx, PROF_ROWOPS);
-  pool_kernel<<<nseq, 256, 0, ctx->stream>>>(x32, cu, pooling, normalize, out);
+  pool_kernel<<<nseq, 256, 0, ctx->stream>>>(x32, cu, pooling, normalize, out, hidden);
   VRAG_LAUNCHED(ctx);
 }
 void launch_f32_to_f16(vrag_ctx* ctx, const float* src, __half* dst, size_t n) {

@@ -128,7 +128,7 @@ class B200DenseProvider(DenseEmbeddingProvider):
 
     def embed_array(self, texts: Sequence[str]) -> np.ndarray:
         if len(texts) == 0:
-            return np.zeros((0, 768), np.float32)
+            return np.zeros((0, self.get_dimension()), np.float32)
         ids, cu = self._te.tokenize(texts)
         with self._te._lock:
             return self._te._enc.dense_forward(ids, cu, self.pooling, self.normalize)
@@ -140,4 +140,4 @@ class B200DenseProvider(DenseEmbeddingProvider):
         return self.embed_array(texts).tolist()
 
     def get_dimension(self) -> int:
-        return 768
+        return int(getattr(self._te._enc, "hidden", 768))
