@@ -341,13 +341,43 @@ def test_dense_topk_batched_gemm_search(ctx, n, dim, nq, k, monkeypatch):
     ids_s, s_s, s64_s = ix.search_dense(queries, k, want64=True)
     monkeypatch.delenv("VRAG_SCAN_BIG_MIN")
     ix.close()
-    _diag(test="dense_topk_batched_gemm", n=n, dim=dim, nq=nq, k=k, gemm_equals_scan=bool(np.array_equal(ids_g, ids_s)))
+    monkeypatch.setenv("VRAG_SCAN_FUSED_SELECT", "0")    # full score matrix + streaming selection instead of the fused epilogue
+    ix2 = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    ix2.add_dense(corpus)
+    ix2.mark_deleted(dead)
+    ids_u, s_u, s64_u = ix2.search_dense(queries, k, want64=True)
+    ix2.close()
+    monkeypatch.delenv("VRAG_SCAN_FUSED_SELECT")
+    _diag(test="dense_topk_batched_gemm", n=n, dim=dim, nq=nq, k=k, gemm_equals_scan=bool(np.array_equal(ids_g, ids_s)),
+          fused_equals_unfused=bool(np.array_equal(ids_g, ids_u)))
     assert np.array_equal(ids_g, ids_s) and np.array_equal(s64_g, s64_s) and np.array_equal(s_g, s_s)
+    assert np.array_equal(ids_g, ids_u) and np.array_equal(s64_g, s64_u)
     sc = dense_cosine_scores(corpus, queries)
     sc[:, dead] = -np.inf
     for qi in range(0, nq, max(1, nq // 40)):
         order = np.lexsort((np.arange(n), -sc[qi]))[:k]
         assert np.array_equal(ids_g[qi], order), qi
+
+
+def test_dense_topk_batched_search_adversarial_row_order(ctx):
+    """The fused selection takes its thresholds from the FIRST rows of the corpus.  Worst case: every good row sits after
+    the sample (corpus sorted by ascending similarity) -- the candidate lists overflow and the call must fall back to
+    the full-score path, with the same exact answer."""
+    from verbatim_rag_b200 import _native
+    from oracle.flat_topk import dense_cosine_scores
+    rng = np.random.default_rng(5)
+    n, dim, nq, k = 40000, 768, 70, 10
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    mix = np.linspace(-0.2, 0.9, n, dtype=np.float32)[:, None]        # similarity to the mean query rises along the corpus
+    corpus = (base + 30.0 * mix * q.mean(axis=0, keepdims=True)).astype(np.float32)
+    ix = _native.Index(ctx, _native.INDEX_DENSE_COSINE, dim)
+    ix.add_dense(corpus)
+    ids, s32, s64 = ix.search_dense(q, k, want64=True)
+    ix.close()
+    sc = dense_cosine_scores(corpus, q)
+    for qi in range(nq):
+        assert np.array_equal(ids[qi], np.lexsort((np.arange(n), -sc[qi]))[:k]), qi
 
 
 def test_dense_topk_ties_and_deletes(ctx):

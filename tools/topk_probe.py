@@ -45,7 +45,7 @@ def main():
             ms = e0.elapsed_time(e1) / 3
             rec = {"n": n, "nq": nq, "path": "gemm" if env is None and nq >= 64 else "scan", "ms": round(ms, 3),
                    "queries_per_s": round(nq / ms * 1e3), "scan_ms": round(pr["scan"]["ms"] / 3, 3),
-                   "select_ms": round(pr["select"]["ms"] / 3, 3), "tflops_algorithmic": round(2 * nq * n * dim / ms / 1e9, 1)}
+                   "select_ms": round(pr["select"]["ms"] / 3, 3), "finish_ms": round(pr["other"]["ms"] / 3, 3), "tflops_algorithmic": round(2 * nq * n * dim / ms / 1e9, 1)}
             out.append(rec)
             print(rec, flush=True)
     os.environ.pop("VRAG_SCAN_BIG_MIN", None)

@@ -277,6 +277,34 @@ __device__ __forceinline__ void epilogue_row(const GemmEpiParams& p, int row, in
         s1 = s2 = d0 = d1 = 0.f;
       }
     }
+  } else if constexpr (EPI == EPI_SCORES_THRESH) {
+    const float tau = valid ? __ldg(p.thr + row) : INFINITY;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      ld.load(c, v);
+      const int n0 = col0 + c * 32;
+      if (n0 >= p.n_valid) continue;   // warp-uniform
+      uint32_t hits = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) hits |= (v[i] >= tau ? 1u : 0u) << i;
+      if (hits == 0) continue;          // the common case: nothing in these 32 columns reaches the threshold
+      const int lim = p.n_valid - n0;   // columns of the ragged last chunk
+      while (hits) {
+        const int i = __ffs(hits) - 1;
+        hits &= hits - 1;
+        if (i >= lim || __ldg(p.col_mask + n0 + i)) continue;
+        float sc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc = j == i ? v[j] : sc;   // v[] stays in registers (no dynamic indexing)
+        const int pos = atomicAdd(p.cand_count + row, 1);
+        if (pos < p.cand_cap) {
+          const uint32_t b = __float_as_uint(sc);
+          const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+          p.cand[static_cast<size_t>(row) * p.cand_cap + pos] =
+              (static_cast<unsigned long long>(ord) << 32) | static_cast<unsigned long long>(~static_cast<uint32_t>(p.col_base + n0 + i));
+        }
+      }
+    }
   } else if constexpr (EPI == EPI_SCORES) {
     // out32 row = one query, columns = corpus rows: 128 contiguous bytes per thread and chunk (ld32 % 4 == 0)
 #pragma unroll 1
@@ -1275,6 +1303,7 @@ void launch_gemm(vrag_ctx* ctx, int epi, const __half* A, const __half* W, int M
     VRAG_CASE(EPI_RESID_STATS_LN)
     VRAG_CASE(EPI_SCORES)
     VRAG_CASE(EPI_HEAD_PARTIAL)
+    VRAG_CASE(EPI_SCORES_THRESH)
 #undef VRAG_CASE
     default: throw Error(VRAG_ERR_ARG, "gemm: unknown epilogue");
   }

@@ -35,6 +35,9 @@ enum GemmEpi : int {
   EPI_NORM_BIAS_GELU_F16 = 15,  // out16 = gelu(rstd[row] * acc + bias)               (BERT intermediate)
   EPI_SCORES = 17,              // similarity scan as a GEMM (topk.cu, batched dense search): out32[m][n] = acc for the
                                 // n_valid real columns, -inf where col_mask[n] != 0 (deleted / filtered corpus rows)
+  EPI_SCORES_THRESH = 19,       // EPI_SCORES with the selection fused in: nothing is stored but the (rare) scores >= thr[m],
+                                // appended as 64-bit keys (order-preserving score bits << 32 | ~row) to cand[m][..cand_cap)
+                                // through cand_count[m]; row = col_base + n.  The [M, N] score matrix never exists.
   EPI_HEAD_PARTIAL = 18,        // span-logit head fused into head.dense (ModernBERT prediction head + classifier):
                                 // g = gelu(acc); per row and 128 columns the four partial sums (sum g, sum g^2,
                                 // sum g * cls_gw[0][n], sum g * cls_gw[1][n]) -> head_part[slot][row] (float4, slot =
@@ -69,6 +72,11 @@ struct GemmEpiParams {
   int splade_ld = 0;
   int n_valid = 0;                    // columns >= n_valid are padding (SPLADE vocab tail, EPI_SCORES corpus tail)
   const uint8_t* col_mask = nullptr;  // EPI_SCORES: [n_valid] bytes, != 0 -> the column scores -inf
+  const float* thr = nullptr;         // EPI_SCORES_THRESH: [M] per-query threshold
+  unsigned long long* cand = nullptr; // EPI_SCORES_THRESH: [M][cand_cap] candidate keys
+  int* cand_count = nullptr;          // EPI_SCORES_THRESH: [M] number appended (may exceed cand_cap: overflow)
+  int cand_cap = 0;
+  int col_base = 0;                   // EPI_SCORES_THRESH: corpus row of column 0
   const float* cls_gw = nullptr;      // EPI_HEAD_PARTIAL: [2][N] fp32
   float* head_part = nullptr;         // EPI_HEAD_PARTIAL: [N / 128][M] float4
   int prof_class = 0;                 // profiler class the launch is booked under (common.cuh ProfClass; 0 = GEMM)

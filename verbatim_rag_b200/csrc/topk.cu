@@ -926,6 +926,29 @@ normalize_split_kernel(const float* __restrict__ rows, const float* __restrict__
   *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
 }
 
+// Fused selection of the batched search: per query, the kp best keys of the SAMPLE (the first rows of the corpus) seed
+// the candidate list, and the kp-th of them is the threshold every later row must reach to matter at all.
+__global__ void seed_candidates_kernel(const uint64_t* __restrict__ sample_keys /*[nq][kp] sorted desc*/, int kp, int cap,
+                                       unsigned long long* __restrict__ cand, int* __restrict__ count,
+                                       float* __restrict__ thr) {
+  const int q = blockIdx.x, j = threadIdx.x;
+  if (j < kp) cand[static_cast<size_t>(q) * cap + j] = sample_keys[static_cast<size_t>(q) * kp + j];
+  if (j == 0) {
+    count[q] = kp;
+    const uint64_t last = sample_keys[static_cast<size_t>(q) * kp + kp - 1];
+    if (last == 0) {
+      thr[q] = -INFINITY;   // fewer than kp live rows in the sample: everything is a candidate
+    } else {
+      const uint32_t u = static_cast<uint32_t>(last >> 32);
+      thr[q] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+    }
+  }
+}
+__global__ void overflow_flag_kernel(const int* __restrict__ count, int nq, int cap, int* __restrict__ flag) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && count[q] > cap) atomicExch(flag, 1);
+}
+
 __global__ void query_norm_kernel(const float* __restrict__ queries, int dim, float* __restrict__ inv_norm_q) {
   const int q = blockIdx.x;
   const int lane = threadIdx.x;
@@ -948,7 +971,7 @@ struct vrag_index {
   int64_t id_base = 0;  // added to row numbers in results (global id of this shard's row 0)
   DevBuf rows, norm64, inv32, deleted;
   // batched search: split-precision planes of the normalised rows [planes_cap, dim] (built lazily, rows [0, planes_n))
-  DevBuf rows_hi, rows_lo, q_hi, q_lo;
+  DevBuf rows_hi, rows_lo, q_hi, q_lo, cand, cand_count, cand_thr, flag;
   int64_t planes_n = 0, planes_cap = 0;
   // metadata-filter pushdown (vrag_index_set_filter): masked = deleted | excluded, consulted instead of `deleted`
   DevBuf masked, excl;
@@ -962,7 +985,7 @@ struct vrag_index {
   ~vrag_index() {
     for (DevBuf* b : {&rows, &norm64, &inv32, &deleted, &masked, &excl, &indptr, &indices, &values, &scores, &keys0, &keys1, &s64,
                       &crow, &qdev, &qnorm, &qT, &qip, &qidx, &qval, &out_ids, &out_s32, &out_s64, &rows_hi, &rows_lo, &q_hi,
-                      &q_lo})
+                      &q_lo, &cand, &cand_count, &cand_thr, &flag})
       b->release();
   }
 };
@@ -1282,8 +1305,6 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
       _ctx->launches++;
       idx->planes_n = n;
     }
-    const int group = static_cast<int>(std::max<int64_t>(GEMM_BM, std::min<int64_t>(1024, ((int64_t(4) << 30) / (n_pad * 4)) / GEMM_BM * GEMM_BM)));
-    idx->scores.reserve(static_cast<size_t>(std::min(group, nq)) * n_pad * 4);
     idx->q_hi.reserve(static_cast<size_t>(nq) * dim * 2);
     idx->q_lo.reserve(static_cast<size_t>(nq) * dim * 2);
     const int64_t q4 = static_cast<int64_t>(nq) * (dim / 4);
@@ -1291,22 +1312,100 @@ extern "C" int vrag_index_search_dense(vrag_index* idx, const float* queries, in
         qd, nullptr, 0, nq, dim, idx->q_hi.as<__half>(), idx->q_lo.as<__half>());
     VRAG_CUDA(cudaGetLastError());
     _ctx->launches++;
-    for (int q0 = 0; q0 < nq; q0 += group) {
-      const int nt = std::min(group, nq - q0);
+    auto full_scores = [&](int q0, int nt, int64_t rows, int64_t ld) {   // scores[nt][ld] of corpus rows [0, rows)
       GemmEpiParams gp;
       gp.M = nt;
       gp.out32 = idx->scores.as<float>();
-      gp.ld32 = static_cast<int>(n_pad);
-      gp.n_valid = static_cast<int>(n);
+      gp.ld32 = static_cast<int>(ld);
+      gp.n_valid = static_cast<int>(rows);
       gp.col_mask = idx->skip();
       gp.a_lo = idx->q_lo.as<__half>() + static_cast<size_t>(q0) * dim;
       gp.w_lo = idx->rows_lo.as<__half>();
       gp.prof_class = PROF_SCAN;
       launch_gemm(_ctx, EPI_SCORES, idx->q_hi.as<__half>() + static_cast<size_t>(q0) * dim, idx->rows_hi.as<__half>(), nt,
-                  static_cast<int>(n_pad), dim, gp, 0);
-      select_and_rank(idx, idx->scores.as<float>(), nt, k, true, qd + static_cast<size_t>(q0) * dim,
-                      d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
-                      d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr, _ctx->stream, n_pad);
+                  static_cast<int>(ld), dim, gp, 0);
+    };
+    // Selection fused into the GEMM epilogue (k + 16 <= 32, corpus large enough to sample): phase 1 scores a SAMPLE (the
+    // first n/16 rows) in full and selects its k' best per query -- they seed the candidate list and the k'-th of them
+    // is a threshold that at least k' rows are known to reach; phase 2 runs the GEMM over the remaining rows and its
+    // epilogue appends only the scores >= that threshold (expected 16 k' per query) to the candidate list, so the
+    // [nq, N] score matrix is neither written nor re-read; phase 3 merges, re-scores in fp64 and ranks (the same
+    // dense_finish_kernel as every other path).  A candidate list that overflows (adversarial row order: the best rows
+    // all after the sample) falls back to the full-score path for this call -- results never depend on the sample.
+    const int kp = static_cast<int>(std::min<int64_t>(k + MARGIN, n));
+    const char* fuse_env = getenv("VRAG_SCAN_FUSED_SELECT");   // debug: 0 keeps the full score matrix + streaming selection
+    bool fused = !(fuse_env && fuse_env[0] == '0') && kp <= 32 && n >= 16 * GEMM_BN * 4;
+    const int CAP = 4096;
+    if (fused) {
+      const int64_t S = std::max<int64_t>(GEMM_BN * 4, (n / 16) / GEMM_BN * GEMM_BN);   // sample rows (multiple of 256)
+      idx->scores.reserve(static_cast<size_t>(std::min(1024, nq)) * S * 4);
+      idx->cand.reserve(static_cast<size_t>(nq) * CAP * 8);
+      idx->cand_count.reserve(static_cast<size_t>(nq) * 4);
+      idx->cand_thr.reserve(static_cast<size_t>(nq) * 4);
+      idx->flag.reserve(4);
+      idx->keys1.reserve(static_cast<size_t>(nq) * kp * 8);
+      VRAG_CUDA(cudaMemsetAsync(idx->cand.p, 0, static_cast<size_t>(nq) * CAP * 8, _ctx->stream));
+      VRAG_CUDA(cudaMemsetAsync(idx->flag.p, 0, 4, _ctx->stream));
+      for (int q0 = 0; q0 < nq; q0 += 1024) {
+        const int nt = std::min(1024, nq - q0);
+        full_scores(q0, nt, S, S);
+        {   // k' best of the sample per query -> keys1[q0 + q][kp] (sorted descending)
+          ProfScope prof(_ctx, PROF_SELECT);
+          const int nblk = static_cast<int>(std::max<int64_t>(1, (S + SEL_REG_BLOCK - 1) / SEL_REG_BLOCK));
+          idx->keys0.reserve(static_cast<size_t>(nt) * nblk * kp * 8);
+          select_reg_kernel<true><<<dim3(nblk, nt), 32 * SEL_WARPS, 0, _ctx->stream>>>(idx->scores.as<float>(), nullptr, S, S, kp,
+                                                                                    idx->keys0.as<uint64_t>());
+          select_reg_kernel<false><<<dim3(1, nt), 32 * SEL_WARPS, 0, _ctx->stream>>>(
+              nullptr, idx->keys0.as<uint64_t>(), static_cast<int64_t>(nblk) * kp, static_cast<int64_t>(nblk) * kp, kp,
+              idx->keys1.as<uint64_t>() + static_cast<size_t>(q0) * kp);
+          seed_candidates_kernel<<<nt, 32, 0, _ctx->stream>>>(
+              idx->keys1.as<uint64_t>() + static_cast<size_t>(q0) * kp, kp, CAP,
+              idx->cand.as<unsigned long long>() + static_cast<size_t>(q0) * CAP, idx->cand_count.as<int>() + q0,
+              idx->cand_thr.as<float>() + q0);
+          VRAG_CUDA(cudaGetLastError());
+          _ctx->launches += 3;
+        }
+        GemmEpiParams gp;
+        gp.M = nt;
+        gp.n_valid = static_cast<int>(n - S);
+        gp.col_mask = idx->skip() + S;
+        gp.col_base = static_cast<int>(S);
+        gp.thr = idx->cand_thr.as<float>() + q0;
+        gp.cand = idx->cand.as<unsigned long long>() + static_cast<size_t>(q0) * CAP;
+        gp.cand_count = idx->cand_count.as<int>() + q0;
+        gp.cand_cap = CAP;
+        gp.a_lo = idx->q_lo.as<__half>() + static_cast<size_t>(q0) * dim;
+        gp.w_lo = idx->rows_lo.as<__half>() + static_cast<size_t>(S) * dim;
+        gp.prof_class = PROF_SCAN;
+        launch_gemm(_ctx, EPI_SCORES_THRESH, idx->q_hi.as<__half>() + static_cast<size_t>(q0) * dim,
+                    idx->rows_hi.as<__half>() + static_cast<size_t>(S) * dim, nt, static_cast<int>(n_pad - S), dim, gp, 0);
+        {
+          ProfScope prof(_ctx, PROF_SELECT);
+          overflow_flag_kernel<<<(nt + 255) / 256, 256, 0, _ctx->stream>>>(idx->cand_count.as<int>() + q0, nt, CAP,
+                                                                         idx->flag.as<int>());
+          dense_finish_kernel<<<nt, 32 * FIN_WARPS, 0, _ctx->stream>>>(
+              idx->cand.as<uint64_t>() + static_cast<size_t>(q0) * CAP, CAP, kp, k, idx->rows.as<float>(), dim,
+              idx->norm64.as<double>(), qd + static_cast<size_t>(q0) * dim, idx->id_base, d_ids + static_cast<size_t>(q0) * k,
+              d_s32 + static_cast<size_t>(q0) * k, d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr);
+          VRAG_CUDA(cudaGetLastError());
+          _ctx->launches += 2;
+        }
+      }
+      int overflow = 0;   // one 4-byte read-back per call decides whether the (rare) fallback runs
+      VRAG_CUDA(cudaMemcpyAsync(&overflow, idx->flag.p, 4, cudaMemcpyDeviceToHost, _ctx->stream));
+      VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+      fused = overflow == 0;
+    }
+    if (!fused) {
+      const int group = static_cast<int>(std::max<int64_t>(GEMM_BM, std::min<int64_t>(1024, ((int64_t(4) << 30) / (n_pad * 4)) / GEMM_BM * GEMM_BM)));
+      idx->scores.reserve(static_cast<size_t>(std::min(group, nq)) * n_pad * 4);
+      for (int q0 = 0; q0 < nq; q0 += group) {
+        const int nt = std::min(group, nq - q0);
+        full_scores(q0, nt, n, n_pad);
+        select_and_rank(idx, idx->scores.as<float>(), nt, k, true, qd + static_cast<size_t>(q0) * dim,
+                        d_ids + static_cast<size_t>(q0) * k, d_s32 + static_cast<size_t>(q0) * k,
+                        d_s64 ? d_s64 + static_cast<size_t>(q0) * k : nullptr, _ctx->stream, n_pad);
+      }
     }
     if (!on_device) {
       VRAG_CUDA(cudaMemcpyAsync(ids_out, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
