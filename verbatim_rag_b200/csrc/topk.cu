@@ -25,7 +25,9 @@ using namespace vrag;
 
 namespace {
 
-constexpr int QT = 8;          // queries per corpus pass
+constexpr int QT = 8;          // queries per corpus pass (dense FMA scans)
+constexpr int SQT = 32;        // queries per corpus pass of the sparse scan: one 128-byte line of the dense query table per
+                               // stored term (8 per pass left a 10 k-document search launch-bound: 125 passes of ~20 us)
 constexpr int MARGIN = 16;     // extra candidates kept for the fp64 re-ranking
 constexpr int MAX_K = 1024;
 constexpr int SEL_WARPS = 8;
@@ -527,14 +529,14 @@ dense_scan_generic_kernel(const float* __restrict__ rows, int64_t n, int dim, co
 }
 
 // ---------------------------------------------------------------------------------- sparse: scan
-// qT: dense query block [dim][QT] (row = vocabulary id, QT consecutive floats = one 32-byte sector per gather).
+// qT: dense query block [dim][SQT] (row = vocabulary id, SQT consecutive floats = one 128-byte line per gather).
 __global__ void sparse_scatter_query_kernel(const int64_t* __restrict__ q_indptr, const int32_t* __restrict__ q_idx,
                                             const float* __restrict__ q_val, int nq, int dim, float* __restrict__ qT) {
   const int qi = blockIdx.x;
   if (qi >= nq) return;
   for (int64_t j = q_indptr[qi] + threadIdx.x; j < q_indptr[qi + 1]; j += blockDim.x) {
     const int t = q_idx[j];
-    if (t >= 0 && t < dim) qT[static_cast<size_t>(t) * QT + qi] = q_val[j];
+    if (t >= 0 && t < dim) qT[static_cast<size_t>(t) * SQT + qi] = q_val[j];
   }
 }
 
@@ -546,25 +548,33 @@ sparse_scan_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < n; row += nwarps) {
     const int64_t a = indptr[row], b = indptr[row + 1];
-    float acc[QT];
+    float acc[SQT];
 #pragma unroll
-    for (int qi = 0; qi < QT; ++qi) acc[qi] = 0.f;
+    for (int qi = 0; qi < SQT; ++qi) acc[qi] = 0.f;
     for (int64_t j = a + lane; j < b; j += 32) {
       const int t = __ldg(indices + j);
       const float v = __ldg(values + j);
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * QT));
-      const float4 q1 = __ldg(reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * QT) + 1);
-      acc[0] += v * q0.x; acc[1] += v * q0.y; acc[2] += v * q0.z; acc[3] += v * q0.w;
-      acc[4] += v * q1.x; acc[5] += v * q1.y; acc[6] += v * q1.z; acc[7] += v * q1.w;
-    }
+      const float4* qrow = reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * SQT);
 #pragma unroll
-    for (int qi = 0; qi < QT; ++qi) acc[qi] = warp_sum(acc[qi]);
-    if (lane == 0) {
-      const bool dead = deleted[row] != 0;
-#pragma unroll
-      for (int qi = 0; qi < QT; ++qi)
-        if (qi < nq) scores[static_cast<size_t>(qi) * n + row] = dead ? -INFINITY : acc[qi];
+      for (int c = 0; c < SQT / 4; ++c) {
+        const float4 qv = __ldg(qrow + c);
+        acc[4 * c] += v * qv.x; acc[4 * c + 1] += v * qv.y; acc[4 * c + 2] += v * qv.z; acc[4 * c + 3] += v * qv.w;
+      }
     }
+    // transposing butterfly: lane l ends with the full sum of query l (31 shuffles instead of 5 per query)
+#pragma unroll
+    for (int off = 16, cnt = SQT / 2; off >= 1; off >>= 1, cnt >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) {
+        const float send = upper ? acc[i] : acc[i + cnt];
+        const float keep = upper ? acc[i + cnt] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    // (the step with lane offset `off` keeps the half of the remaining queries selected by that bit of the lane index, so
+    // lane l is left with query l in acc[0])
+    if (lane < nq) scores[static_cast<size_t>(lane) * n + row] = deleted[row] ? -INFINITY : acc[0];
   }
 }
 
@@ -749,12 +759,14 @@ dense_rescore_kernel(const float* __restrict__ rows, int dim, const double* __re
 
 __global__ void __launch_bounds__(256)
 sparse_rescore_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                      const float* __restrict__ values, const float* __restrict__ qT, int qslot,
+                      const float* __restrict__ values, const float* __restrict__ qT, size_t qT_stride, int qslot,
                       const uint64_t* __restrict__ cand, int kp, double* __restrict__ score64,
                       int64_t* __restrict__ cand_row) {
-  // grid.y = query within the tile; qslot = -1 means "slot = blockIdx.y"
+  // grid.y = query within the selection group; qslot = -1: the group's query tables lie back to back, QT queries each
+  // ([tile][dim][QT]), query q is slot q % QT of table q / QT
   const int q = blockIdx.y;
-  const int slot = qslot < 0 ? q : qslot;
+  const int slot = qslot < 0 ? (q % SQT) : qslot;
+  if (qslot < 0) qT += static_cast<size_t>(q / SQT) * qT_stride;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= kp) return;
@@ -767,7 +779,7 @@ sparse_rescore_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
   const int64_t row = key_row(key);
   double dot = 0.0;
   for (int64_t j = indptr[row] + lane; j < indptr[row + 1]; j += 32)
-    dot += static_cast<double>(values[j]) * static_cast<double>(qT[static_cast<size_t>(indices[j]) * QT + slot]);
+    dot += static_cast<double>(values[j]) * static_cast<double>(qT[static_cast<size_t>(indices[j]) * SQT + slot]);
   dot = warp_sum_d(dot);
   if (lane == 0) { score64[o] = dot; cand_row[o] = row; }
 }
@@ -1068,7 +1080,8 @@ void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bo
                                                       ix->crow.as<int64_t>());
   else
     sparse_rescore_kernel<<<g, 256, 0, st>>>(ix->indptr.as<int64_t>(), ix->indices.as<int32_t>(),
-                                                       ix->values.as<float>(), ix->qT.as<float>(), -1, final_keys, kp,
+                                                       ix->values.as<float>(), ix->qT.as<float>(),
+                                                       static_cast<size_t>(ix->dim) * SQT, -1, final_keys, kp,
                                                        ix->s64.as<double>(), ix->crow.as<int64_t>());
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1119,7 +1132,7 @@ extern "C" int vrag_index_create(vrag_ctx* ctx, int kind, int dim, vrag_index** 
   if (kind == VRAG_INDEX_SPARSE_IP) {
     ix->indptr.reserve(8);
     VRAG_CUDA(cudaMemsetAsync(ix->indptr.p, 0, 8, ctx->stream));
-    ix->qT.reserve(static_cast<size_t>(dim) * QT * 4);
+    ix->qT.reserve(static_cast<size_t>(dim) * SQT * 4);
     VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   *out = ix;
@@ -1539,27 +1552,35 @@ extern "C" int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr
   idx->out_ids.reserve(static_cast<size_t>(nq) * k * 8);
   idx->out_s32.reserve(static_cast<size_t>(nq) * k * 4);
   idx->out_s64.reserve(static_cast<size_t>(nq) * k * 8);
-  idx->scores.reserve(static_cast<size_t>(QT) * n * 4);
+  // Selection groups (as on the dense path): the score rows of up to `group` consecutive query tiles (SQT queries per corpus
+  // pass) are kept, each tile with its own dense query table, and selected / re-scored / ranked by ONE launch sequence.
+  // The selection is latency-bound; per tile it cost twice the scan on a 10 k-document corpus.
+  const size_t qT_bytes = static_cast<size_t>(idx->dim) * SQT * 4;
+  const int group = static_cast<int>(std::max<size_t>(1, std::min<size_t>(16, (size_t(512) << 20) / (static_cast<size_t>(SQT) * n * 4))));
+  idx->scores.reserve(static_cast<size_t>(group) * SQT * n * 4);
+  idx->qT.reserve(static_cast<size_t>(group) * qT_bytes);
   const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(_ctx->num_sms) * 8));
-  for (int q0 = 0; q0 < nq; q0 += QT) {
-    const int nt = std::min(QT, nq - q0);
-    VRAG_CUDA(cudaMemsetAsync(idx->qT.p, 0, static_cast<size_t>(idx->dim) * QT * 4, _ctx->stream));
-    sparse_scatter_query_kernel<<<nt, 128, 0, _ctx->stream>>>(idx->qip.as<int64_t>() + q0, idx->qidx.as<int32_t>(),
-                                                               idx->qval.as<float>(), nt, idx->dim, idx->qT.as<float>());
-    VRAG_CUDA(cudaGetLastError());
-    _ctx->launches++;
-    {
+  for (int g0 = 0; g0 < nq; g0 += group * SQT) {
+    const int ng = std::min(group * SQT, nq - g0);   // queries in this group
+    VRAG_CUDA(cudaMemsetAsync(idx->qT.p, 0, static_cast<size_t>((ng + SQT - 1) / SQT) * qT_bytes, _ctx->stream));
+    for (int t = 0; t * SQT < ng; ++t) {
+      const int q0 = g0 + t * SQT, nt = std::min(SQT, ng - t * SQT);
+      float* qT_t = idx->qT.as<float>() + static_cast<size_t>(t) * idx->dim * SQT;
+      sparse_scatter_query_kernel<<<nt, 128, 0, _ctx->stream>>>(idx->qip.as<int64_t>() + q0, idx->qidx.as<int32_t>(),
+                                                                 idx->qval.as<float>(), nt, idx->dim, qT_t);
+      VRAG_CUDA(cudaGetLastError());
+      _ctx->launches++;
       ProfScope prof(_ctx, PROF_SCAN);
       sparse_scan_kernel<<<grid, 256, 0, _ctx->stream>>>(idx->indptr.as<int64_t>(), idx->indices.as<int32_t>(),
-                                                          idx->values.as<float>(), n, idx->qT.as<float>(), nt,
-                                                          idx->skip(), idx->scores.as<float>());
+                                                          idx->values.as<float>(), n, qT_t, nt, idx->skip(),
+                                                          idx->scores.as<float>() + static_cast<size_t>(t) * SQT * n);
       VRAG_CUDA(cudaGetLastError());
       _ctx->launches++;
     }
-    select_and_rank(idx, idx->scores.as<float>(), nt, k, false, nullptr,
-                    idx->out_ids.as<int64_t>() + static_cast<size_t>(q0) * k,
-                    idx->out_s32.as<float>() + static_cast<size_t>(q0) * k,
-                    idx->out_s64.as<double>() + static_cast<size_t>(q0) * k, _ctx->stream);
+    select_and_rank(idx, idx->scores.as<float>(), ng, k, false, nullptr,
+                    idx->out_ids.as<int64_t>() + static_cast<size_t>(g0) * k,
+                    idx->out_s32.as<float>() + static_cast<size_t>(g0) * k,
+                    idx->out_s64.as<double>() + static_cast<size_t>(g0) * k, _ctx->stream);
   }
   VRAG_CUDA(cudaMemcpyAsync(ids_out, idx->out_ids.p, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, _ctx->stream));
   VRAG_CUDA(cudaMemcpyAsync(scores_out, idx->out_s32.p, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, _ctx->stream));
