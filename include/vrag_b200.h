@@ -14,6 +14,10 @@
  *   vrag_splade_forward      <- SpladeProvider.embed_batch / embed_text -> SparseEncoder.encode
  *                               verbatim_rag/embedding_providers.py:138-166
  *   vrag_dense_forward       <- SentenceTransformersProvider.embed_batch embedding_providers.py:73-77
+ *   vrag_rerank_forward      <- SentenceTransformersReranker.rerank -> CrossEncoder.predict
+ *                               verbatim_rag/rerankers.py:109-134
+ *   vrag_sentence_forward    <- ModelSpanExtractor._extract_qa_model -> QAModel.forward   extractors.py:230-283,
+ *                               packages/core/verbatim_core/extractor_models/model.py:59-117
  *   vrag_index_create        <- LocalMilvusStore._setup_client          verbatim_rag/vector_stores/milvus_local.py:58-125
  *   vrag_index_add_*         <- BaseMilvusStore.add_vectors -> client.insert   milvus_base.py:90-127
  *   vrag_index_search_dense  <- BaseMilvusStore.query dense branch -> client.search  milvus_base.py:239-248
@@ -49,6 +53,8 @@ extern "C" {
 #define VRAG_ENC_MODERNBERT_TOKCLS 0 /* ModernBERT encoder + token-classification head (span extractor) */
 #define VRAG_ENC_BERT_MLM 1          /* BERT encoder + MLM head + SPLADE pooling (sparse provider) */
 #define VRAG_ENC_BERT_DENSE 2        /* BERT encoder + mean/CLS pooling (dense provider) */
+#define VRAG_ENC_BERT_CLS 3          /* BERT encoder + pooler + 1-label classifier (cross-encoder reranker) */
+#define VRAG_ENC_MODERNBERT_SENT 4   /* ModernBERT encoder + sentence mean-pool + 2-way classifier (legacy QAModel) */
 
 #define VRAG_INDEX_DENSE_COSINE 0
 #define VRAG_INDEX_SPARSE_IP 1
@@ -123,6 +129,20 @@ int vrag_splade_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu
 /* Dense sentence embedding: encoder -> mean / CLS pooling -> optional L2 normalisation.  out [nseq, hidden]. */
 int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq, int pooling,
                        int normalize, float* out, int on_device);
+
+/* Cross-encoder reranker: pair sequences ([CLS] q [SEP] doc [SEP], type_ids 0 / 1 per token, NULL = all 0) -> one
+ * relevance logit per sequence (BertForSequenceClassification, num_labels = 1).  Needs a VRAG_ENC_BERT_CLS encoder
+ * (weights: bert.*, bert.pooler.dense.*, classifier.*). */
+int vrag_rerank_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens,
+                        int nseq, float* scores_out, int on_device);
+
+/* Sentence classifier of the legacy QAModel: per sentence j of sequence i (sent_indptr[i] <= j < sent_indptr[i + 1]) the
+ * mean of the encoder's final hidden states over tokens [sent_start[j], sent_end[j]] (indices inside the sequence, end
+ * inclusive) -> Linear(hidden, 2).  logits_out [n_sentences, 2].  Host buffers.  Needs a VRAG_ENC_MODERNBERT_SENT
+ * encoder (weights: model.*, classifier.weight [2, hidden], classifier.bias). */
+int vrag_sentence_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,
+                          const int32_t* sent_indptr, const int32_t* sent_start, const int32_t* sent_end,
+                          float* logits_out);
 
 /* Debug / test hook: run the tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (fp16 operands, fp32 accumulate) against
  * an in-library SIMT reference GEMM on random data and return the max |diff| (device-side self check). */

@@ -36,10 +36,11 @@ def bert_mlm_hidden(weights: Dict[str, np.ndarray], input_ids, attention_mask, s
 
 @torch.no_grad()
 def bert_encoder_hidden(weights: Dict[str, np.ndarray], input_ids, attention_mask, spec=None,
-                        emulate_fp16: bool = False) -> torch.Tensor:
+                        emulate_fp16: bool = False, token_type_ids=None) -> torch.Tensor:
     """Final hidden states of the encoder stack [B, L, H] (transformers BertModel.last_hidden_state,
     modeling_bert.py BertEncoder) -- the input of the sentence pooling of a dense embedding model."""
-    return _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform=False)
+    return _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform=False,
+                         token_type_ids=token_type_ids)
 
 
 @torch.no_grad()
@@ -58,7 +59,7 @@ def dense_encode(weights, seqs: List[np.ndarray], spec=None, pooling: str = "mea
     return np.stack(out).astype(np.float32)
 
 
-def _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform) -> torch.Tensor:
+def _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_transform, token_type_ids=None) -> torch.Tensor:
     from verbatim_rag_b200.synthetic import BertSpec
 
     spec = spec or BertSpec()
@@ -79,7 +80,8 @@ def _bert_forward(weights, input_ids, attention_mask, spec, emulate_fp16, mlm_tr
     e = "bert.embeddings."
     x = (_t(weights[e + "word_embeddings.weight"])[ids]
          + _t(weights[e + "position_embeddings.weight"])[:L][None]
-         + _t(weights[e + "token_type_embeddings.weight"])[0][None, None])
+         + (_t(weights[e + "token_type_embeddings.weight"])[0][None, None] if token_type_ids is None
+            else _t(weights[e + "token_type_embeddings.weight"])[_t(token_type_ids).long()]))
     x = ln(x, e + "LayerNorm")
     neg = torch.finfo(torch.float32).min
     mask = torch.zeros(B, 1, 1, L).masked_fill(~am[:, None, None, :], neg)

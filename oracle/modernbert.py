@@ -46,7 +46,7 @@ def layer_norm(x, w, eps, b=None):
 
 @torch.no_grad()
 def modernbert_forward(weights: Dict[str, np.ndarray], input_ids, attention_mask=None, spec=None,
-                       return_hidden: bool = False, emulate_fp16: bool = False):
+                       return_hidden: bool = False, emulate_fp16: bool = False, return_final: bool = False):
     """logits [B, L, 2] fp32 for padded ``input_ids`` [B, L] (attention_mask 1 = token, 0 = pad).
 
     ``emulate_fp16`` rounds every matmul operand to fp16 (fp32 accumulate) -- used only to
@@ -99,6 +99,8 @@ def modernbert_forward(weights: Dict[str, np.ndarray], input_ids, attention_mask
         x = x + lin(F.gelu(a) * gate, weights[p + "mlp.Wo.weight"])
         hidden.append(x)
     x = layer_norm(x, weights["model.final_norm.weight"], spec.norm_eps)
+    if return_final:   # ModernBertModel.last_hidden_state (the input of the legacy QAModel's sentence pooling)
+        return x
     hd = layer_norm(F.gelu(lin(x, weights["head.dense.weight"])), weights["head.norm.weight"], spec.norm_eps)
     logits = lin(hd, weights["classifier.weight"], weights["classifier.bias"])
     if return_hidden:

@@ -273,3 +273,40 @@ def test_dense_provider_and_hybrid_search_through_the_reference_index(ref_env):
     assert [r.score for r in hyb] == sorted((r.score for r in hyb), reverse=True) or \
            [r.score for r in hyb] == sorted(r.score for r in hyb)   # one monotone order (hybrid score = 1 - rrf)
     assert callable(merge_hybrid_results)
+
+
+def test_qa_model_input_builder_equals_reference_dataset(reference_pkgs):
+    """``qa_extractor.encode_question_and_sentences`` / ``split_into_sentences`` (and the oracle's restatement) against the
+    reference's own code: ``QADataset.encode_question_and_sentences_with_offsets`` (packages/core/verbatim_core/
+    extractor_models/dataset.py:108-243) and ``ModelSpanExtractor._split_into_sentences`` (extractors.py:190-195), run for
+    real on the same tokenizer wrapped as a transformers fast tokenizer."""
+    import cases
+    from transformers import PreTrainedTokenizerFast
+    from verbatim_core.extractor_models.dataset import QADataset, Sentence
+    from verbatim_core.extractors import ModelSpanExtractor
+    from verbatim_rag_b200.qa_extractor import encode_question_and_sentences, split_into_sentences
+    from oracle import heads
+    tok = cases.tokenizer("modernbert")
+    fast = PreTrainedTokenizerFast(tokenizer_object=tok.tok, cls_token="[CLS]", sep_token="[SEP]", pad_token="[PAD]",
+                                   unk_token="[UNK]")
+
+    class HF:   # transformers 4.x surface the reference calls (pinned there: transformers==4.53.3); 5.x dropped encode_plus
+        sep_token_id = fast.sep_token_id
+
+        @staticmethod
+        def encode_plus(text, **kw):
+            return fast(text, **kw)
+    hf = HF()
+    rng = np.random.default_rng(21)
+    for n_q, n_doc, max_length in ((10, 90, 512), (10, 700, 512), (12, 300, 128), (200, 60, 128), (5, 1, 64)):
+        q = tok.make_question(rng, n_q)
+        doc = tok.make_text(rng, n_doc, sentence_len=(3, 30))
+        sents = split_into_sentences(doc)
+        assert sents == ModelSpanExtractor._split_into_sentences(None, doc)
+        ref = QADataset.encode_question_and_sentences_with_offsets(
+            q, [Sentence(text=s, relevant=False, sentence_id=f"s{i}") for i, s in enumerate(sents)], hf, max_length)
+        ids, bounds = encode_question_and_sentences(tok, q, sents, max_length)
+        assert ids == ref["input_ids"].tolist(), (n_q, n_doc, max_length)
+        assert bounds == [tuple(b) for b in ref["sentence_boundaries"]]
+        oids, obounds = heads.encode_question_and_sentences(tok, q, sents, max_length)
+        assert list(oids) == ids and obounds == bounds

@@ -16,6 +16,8 @@ _LAZY = {
     "B200DenseProvider": ("providers", "B200DenseProvider"),
     "B200VectorStore": ("vector_store", "B200VectorStore"),
     "ShardedB200VectorStore": ("sharded_store", "ShardedB200VectorStore"),
+    "B200Reranker": ("rerank", "B200Reranker"),
+    "B200QAExtractor": ("qa_extractor", "B200QAExtractor"),
     "sharded_search_dense": ("distributed", "sharded_search_dense"),
     "sharded_search_sparse": ("distributed", "sharded_search_sparse"),
 }

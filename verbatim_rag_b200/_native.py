@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libvrag_b200.so")
 
 VRAG_OK, VRAG_ERR_CUDA, VRAG_ERR_ARG, VRAG_ERR_CAPACITY, VRAG_ERR_WEIGHTS, VRAG_ERR_INTERNAL = range(6)
-ENC_MODERNBERT_TOKCLS, ENC_BERT_MLM, ENC_BERT_DENSE = 0, 1, 2
+ENC_MODERNBERT_TOKCLS, ENC_BERT_MLM, ENC_BERT_DENSE, ENC_BERT_CLS, ENC_MODERNBERT_SENT = 0, 1, 2, 3, 4
 INDEX_DENSE_COSINE, INDEX_SPARSE_IP = 0, 1
 POOL_MEAN, POOL_CLS = 0, 1
 PRECISION_FAST, PRECISION_PRECISE = 0, 1
@@ -31,7 +31,7 @@ EXPORTS = [
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
     "vrag_encoder_create_ex", "vrag_selftest_gemm_split", "vrag_bench_gemm_split", "vrag_selftest_attention_split",
-    "vrag_bench_attention_split", "vrag_encoder_hidden",
+    "vrag_bench_attention_split", "vrag_encoder_hidden", "vrag_rerank_forward", "vrag_sentence_forward",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_encoder_create_ex": (i32, [vp, i32, i32, i32, i32, P(_Tensor), i32, i32, P(vp)]),
             "vrag_encoder_destroy": (None, [vp]),
             "vrag_encoder_hidden": (i32, [vp]),
+            "vrag_rerank_forward": (i32, [vp, vp, vp, vp, i32, vp, i32]),
+            "vrag_sentence_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp]),
             "vrag_selftest_gemm_split": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
             "vrag_bench_gemm_split": (i32, [vp, i32, i32, i32, i32, i32, P(f64)]),
             "vrag_selftest_attention_split": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
@@ -367,6 +369,23 @@ class Encoder:
         out = np.empty((len(cu) - 1, self.hidden), dtype=np.float32)
         self.ctx.check(self.ctx.lib.vrag_dense_forward(self.h, _ptr(ids), _ptr(cu), len(cu) - 1, pooling,
                                                        1 if normalize else 0, _ptr(out), 0))
+        return out
+
+    def rerank_forward(self, ids: np.ndarray, type_ids: np.ndarray, cu: np.ndarray) -> np.ndarray:
+        """Cross-encoder relevance logits, one per packed pair sequence (ENC_BERT_CLS encoders)."""
+        ids, type_ids, cu = _np(ids, np.int32), _np(type_ids, np.int32), _np(cu, np.int32)
+        out = np.empty(len(cu) - 1, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.vrag_rerank_forward(self.h, _ptr(ids), _ptr(type_ids), _ptr(cu), len(cu) - 1, _ptr(out), 0))
+        return out
+
+    def sentence_forward(self, ids: np.ndarray, cu: np.ndarray, sent_indptr: np.ndarray, sent_start: np.ndarray,
+                         sent_end: np.ndarray) -> np.ndarray:
+        """Sentence logits [n_sentences, 2] of the legacy QAModel head (ENC_MODERNBERT_SENT encoders)."""
+        ids, cu = _np(ids, np.int32), _np(cu, np.int32)
+        ip, s0, s1 = _np(sent_indptr, np.int32), _np(sent_start, np.int32), _np(sent_end, np.int32)
+        out = np.empty((int(ip[-1]), 2), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.vrag_sentence_forward(self.h, _ptr(ids), _ptr(cu), len(cu) - 1, _ptr(ip), _ptr(s0),
+                                                          _ptr(s1), _ptr(out)))
         return out
 
     def close(self):

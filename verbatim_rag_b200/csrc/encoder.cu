@@ -65,17 +65,19 @@ struct vrag_encoder {
   std::vector<BLayer> bl;
   float *pos_emb = nullptr, *type_emb = nullptr;
   __half *mlm_w = nullptr, *dec_w = nullptr, *mlm_w_lo = nullptr, *dec_w_lo = nullptr;
+  float *pool_w = nullptr, *pool_b = nullptr, *seq_w = nullptr, *seq_b = nullptr;   // BERT_CLS: pooler + 1-label classifier (fp32)
+  const int32_t* type_ids_host = nullptr;   // BERT_CLS: token types of the call being served (host / device per on_device)
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work, stats, stats2, xl8, h16_lo, qkv16_lo, o16_lo, w16_lo;
+      pooled, work, stats, stats2, xl8, h16_lo, qkv16_lo, o16_lo, w16_lo, types, srow0, srow1, slog;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
                       &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &stats2, &xl8, &h16_lo, &qkv16_lo,
-                      &o16_lo, &w16_lo})
+                      &o16_lo, &w16_lo, &types, &srow0, &srow1, &slog})
       b->release();
   }
   template <typename T>
@@ -209,11 +211,11 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
     e->ml.push_back(L);
   }
   e->final_g = upload_f32(e, w.get("model.final_norm.weight", H), H);
-  e->head_w = upload_f16(e, staging, w.get("head.dense.weight", (int64_t)H * H), H, H, 0, &e->head_w_lo);
-  e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
   e->cls_w = upload_f32(e, w.get("classifier.weight", 2LL * H), 2 * H);
   e->cls_b = upload_f32(e, w.get("classifier.bias", 2), 2);
-  {
+  if (e->kind == VRAG_ENC_MODERNBERT_TOKCLS) {
+    e->head_w = upload_f16(e, staging, w.get("head.dense.weight", (int64_t)H * H), H, H, 0, &e->head_w_lo);
+    e->head_g = upload_f32(e, w.get("head.norm.weight", H), H);
     const float* hg = w.get("head.norm.weight", H);
     const float* cw = w.get("classifier.weight", 2LL * H);
     std::vector<float> gw(2 * H);
@@ -229,6 +231,7 @@ void build_modernbert(vrag_encoder* e, const WeightSet& w) {
     e->cls_g0 = static_cast<float>(g0);
     e->cls_g1 = static_cast<float>(g1);
   }
+  VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));
   make_rope(e, 160000.0, e->max_pos, &e->rope_g);
   make_rope(e, 10000.0, e->max_pos, &e->rope_l);
   staging.release();
@@ -259,6 +262,7 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
   e->ffn = I;
   e->max_pos = static_cast<int>(numel(em + "position_embeddings.weight") / H);
   if (H != HIDDEN) e->deferred_ln = false;   // the deferred-LayerNorm epilogues are built for 768-wide rows (6 moment slots)
+  if (e->kind == VRAG_ENC_BERT_CLS) e->deferred_ln = false;   // pair inputs: token types enter at the embedding LayerNorm
   const int Hp = pad256(H), Ip = pad256(I);
   DevBuf staging;
   const float* wemb = w.get(em + "word_embeddings.weight", (int64_t)e->vocab * H);
@@ -342,6 +346,12 @@ void build_bert(vrag_encoder* e, const WeightSet& w) {
     VRAG_CUDA(cudaStreamSynchronize(e->ctx->stream));  // wo_pad reused next layer
     e->bl.push_back(L);
   }
+  if (e->kind == VRAG_ENC_BERT_CLS) {   // BertForSequenceClassification, num_labels = 1 (cross-encoder reranker)
+    e->pool_w = upload_f32(e, w.get("bert.pooler.dense.weight", (int64_t)H * H), (size_t)H * H);
+    e->pool_b = upload_f32(e, w.get("bert.pooler.dense.bias", H), H);
+    e->seq_w = upload_f32(e, w.get("classifier.weight", H), H);
+    e->seq_b = upload_f32(e, w.get("classifier.bias", 1), 1);
+  }
   if (e->kind == VRAG_ENC_BERT_MLM) {
     const std::string c = "cls.predictions.";
     e->mlm_w = upload_f16(e, staging, w.get(c + "transform.dense.weight", (int64_t)H * H), H, H, Hp, &e->mlm_w_lo);
@@ -379,7 +389,8 @@ void reserve_workspace(vrag_encoder* e) {
   if (e->deferred_ln) {
     e->stats.reserve(T * 6 * 8);
     e->xl8.reserve(T * H);
-    if (e->kind != VRAG_ENC_MODERNBERT_TOKCLS) e->stats2.reserve(T * 6 * 8);   // post-LN: moments are read and rewritten
+    if (e->kind != VRAG_ENC_MODERNBERT_TOKCLS && e->kind != VRAG_ENC_MODERNBERT_SENT)
+      e->stats2.reserve(T * 6 * 8);   // post-LN: moments are read and rewritten
   }
 }
 
@@ -422,13 +433,19 @@ void stage_pass(vrag_encoder* e, const Pass& ps, const int32_t* ids, const int32
     }
   e->work.reserve(static_cast<size_t>(4 * n_pairs) * 4);
   e->n_pairs = n_pairs;
+  if (e->type_ids_host) {
+    e->types.reserve(static_cast<size_t>(T) * 4);
+    VRAG_CUDA(cudaMemcpyAsync(e->types.p, e->type_ids_host + ps.t0, static_cast<size_t>(T) * 4,
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  }
   VRAG_CUDA(cudaMemcpyAsync(e->cu.p, cu_h, (static_cast<size_t>(ns) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   VRAG_CUDA(cudaMemcpyAsync(e->work.p, work_h, static_cast<size_t>(4 * n_pairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
   VRAG_CUDA(cudaStreamSynchronize(ctx->stream));  // cu_h (pinned scratch) is reused by the next pass
   launch_token_meta(ctx, e->cu.as<int32_t>(), ns, T, e->pos.as<int32_t>(), e->seqrow.as<int32_t>());
 }
 
-void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
+// final_hidden_only: stop after the final LayerNorm and leave its fp32 output in x32 (sentence head of the legacy QAModel)
+void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host, bool final_hidden_only = false) {
   vrag_ctx* ctx = e->ctx;
   const int T = ps.t1 - ps.t0, ns = ps.s1 - ps.s0, H = HIDDEN, I = e->ffn;
   const int ref = e->use_reference_gemm ? 1 : 0;
@@ -480,6 +497,11 @@ void modernbert_pass(vrag_encoder* e, const Pass& ps, float* hidden_dbg_host) {
     r.a_lo = g16_lo; r.w_lo = pr ? L.wo2_lo : nullptr;
     launch_gemm(ctx, dln ? EPI_RESID_STATS : EPI_RESID_F32, g16, L.wo2, T, H, I, r, ref);
     dump(i + 1);
+  }
+  if (final_hidden_only) {
+    if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, nullptr, 1e-5f, x32, h16);
+    else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, true, h16_lo);
+    return;
   }
   if (dln) launch_layernorm_hilo(ctx, h16, xl8, T, e->final_g, nullptr, 1e-5f, nullptr, h16);
   else launch_layernorm(ctx, x32, T, e->final_g, nullptr, 1e-5f, h16, false, h16_lo);
@@ -547,7 +569,8 @@ void bert_stack(vrag_encoder* e, const Pass& ps) {
   __half* o16_lo = pr ? e->o16_lo.as<__half>() : nullptr;
   __half* f16_lo = pr ? e->w16_lo.as<__half>() : nullptr;
   launch_bert_embed_ln(ctx, e->ids.as<int32_t>(), e->pos.as<int32_t>(), T, e->vocab, e->max_pos, e->emb, e->pos_emb,
-                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16, h16_lo, H);
+                       e->type_emb, e->emb_g, e->emb_b, 1e-12f, x32, h16, h16_lo, H,
+                       e->type_ids_host ? e->types.as<int32_t>() : nullptr);
   for (int i = 0; i < e->layers; ++i) {
     const auto& L = e->bl[i];
     GemmEpiParams p;
@@ -602,7 +625,7 @@ extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, i
                                       const vrag_tensor* tensors, int num_tensors, int precision, vrag_encoder** out) {
   if (!ctx || !out) return VRAG_ERR_ARG;
   VRAG_API_BEGIN(ctx)
-  VRAG_CHECK(kind >= 0 && kind <= 2 && num_layers > 0 && vocab_size > 0 && max_tokens >= 128, VRAG_ERR_ARG,
+  VRAG_CHECK(kind >= 0 && kind <= 4 && num_layers > 0 && vocab_size > 0 && max_tokens >= 128, VRAG_ERR_ARG,
              "encoder_create: bad kind / num_layers / vocab_size / max_tokens");
   VRAG_CHECK(precision == VRAG_PRECISION_FAST || precision == VRAG_PRECISION_PRECISE, VRAG_ERR_ARG,
              "encoder_create: precision must be VRAG_PRECISION_FAST or VRAG_PRECISION_PRECISE");
@@ -621,7 +644,8 @@ extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, i
   e->legacy_attention = leg && leg[0] == '1';
   const char* dl = getenv("VRAG_DEFERRED_LN");   // "0": separate LayerNorm kernels (cross-check path)
   e->deferred_ln = !(dl && dl[0] == '0');
-  if (kind != VRAG_ENC_MODERNBERT_TOKCLS) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=0 selects the cross-check path
+  const bool modern = kind == VRAG_ENC_MODERNBERT_TOKCLS || kind == VRAG_ENC_MODERNBERT_SENT;
+  if (!modern) {   // BERT (post-LN) stacks: VRAG_BERT_DEFERRED_LN=0 selects the cross-check path
     const char* bd = getenv("VRAG_BERT_DEFERRED_LN");   // (fp32 stream by TMA reduce-add + LayerNorm kernels)
     e->deferred_ln = e->deferred_ln && !(bd && bd[0] == '0');
   }
@@ -632,7 +656,7 @@ extern "C" int vrag_encoder_create_ex(vrag_ctx* ctx, int kind, int num_layers, i
     e->legacy_attention = false;
   }
   WeightSet w(tensors, num_tensors);
-  if (kind == VRAG_ENC_MODERNBERT_TOKCLS) build_modernbert(e.get(), w);
+  if (modern) build_modernbert(e.get(), w);
   else build_bert(e.get(), w);
   reserve_workspace(e.get());
   VRAG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -788,6 +812,88 @@ extern "C" int vrag_dense_forward(vrag_encoder* enc, const int32_t* ids, const i
     VRAG_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(ps.s0) * H, enc->pooled.p, static_cast<size_t>(ns) * H * 4,
                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, _ctx->stream));
     VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+  }
+  VRAG_API_END()
+}
+
+// Cross-encoder reranker (reference: SentenceTransformersReranker.rerank -> CrossEncoder.predict, verbatim_rag/rerankers.py:
+// 109-134): pair sequences [CLS] q [SEP] doc [SEP] with token types -> BERT stack -> pooler (tanh) -> 1-label classifier.
+extern "C" int vrag_rerank_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* type_ids, const int32_t* cu,
+                                   int nseq, float* scores_out, int on_device) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_BERT_CLS, VRAG_ERR_ARG, "rerank_forward needs a BERT_CLS encoder");
+  VRAG_CHECK(ids && cu && scores_out && nseq >= 0, VRAG_ERR_ARG, "rerank_forward: null argument");
+  if (nseq == 0) return VRAG_OK;
+  for (int i = 0; i < nseq; ++i) {
+    VRAG_CHECK(cu[i + 1] > cu[i], VRAG_ERR_ARG, "rerank_forward: empty sequence");
+    VRAG_CHECK(cu[i + 1] - cu[i] <= enc->max_pos, VRAG_ERR_ARG, "rerank_forward: sequence longer than the position table");
+  }
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, enc->max_seqs);
+  enc->type_ids_host = type_ids;
+  try {
+    for (const Pass& ps : passes) {
+      const int ns = ps.s1 - ps.s0;
+      stage_pass(enc, ps, ids, cu, on_device);
+      bert_stack(enc, ps);
+      enc->pooled.reserve(static_cast<size_t>(ns) * 4);
+      launch_cls_head(_ctx, enc->x32.as<float>(), enc->cu.as<int32_t>(), ns, enc->hidden, enc->pool_w, enc->pool_b,
+                      enc->seq_w, enc->seq_b, enc->pooled.as<float>());
+      VRAG_CUDA(cudaMemcpyAsync(scores_out + ps.s0, enc->pooled.p, static_cast<size_t>(ns) * 4,
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, _ctx->stream));
+      VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+    }
+  } catch (...) {
+    enc->type_ids_host = nullptr;
+    throw;
+  }
+  enc->type_ids_host = nullptr;
+  VRAG_API_END()
+}
+
+// Sentence classifier of the legacy QAModel (reference: QAModel.forward, packages/core/verbatim_core/extractor_models/
+// model.py:59-117, called from ModelSpanExtractor._extract_qa_model, extractors.py:230-283): encoder -> mean of the final
+// hidden states over each sentence's token range -> Linear(hidden, 2).  sent_indptr [nseq + 1] (host) counts the
+// sentences of each sequence; sent_start / sent_end are token indices INSIDE the sequence, end inclusive (the
+// reference's sentence_boundaries).  logits_out [n_sentences, 2], host.
+extern "C" int vrag_sentence_forward(vrag_encoder* enc, const int32_t* ids, const int32_t* cu, int nseq,
+                                     const int32_t* sent_indptr, const int32_t* sent_start, const int32_t* sent_end,
+                                     float* logits_out) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_MODERNBERT_SENT, VRAG_ERR_ARG, "sentence_forward needs a MODERNBERT_SENT encoder");
+  VRAG_CHECK(ids && cu && sent_indptr && nseq >= 0, VRAG_ERR_ARG, "sentence_forward: null argument");
+  if (nseq == 0) return VRAG_OK;
+  for (int i = 0; i < nseq; ++i) {
+    const int L = cu[i + 1] - cu[i];
+    VRAG_CHECK(L > 0 && L <= enc->max_pos, VRAG_ERR_ARG, "sentence_forward: bad sequence length");
+    for (int j = sent_indptr[i]; j < sent_indptr[i + 1]; ++j)
+      VRAG_CHECK(sent_start[j] >= 0 && sent_end[j] >= sent_start[j] && sent_end[j] < L, VRAG_ERR_ARG,
+                 "sentence_forward: sentence boundary outside its sequence");
+  }
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, enc->max_seqs);
+  for (const Pass& ps : passes) {
+    stage_pass(enc, ps, ids, cu, 0);
+    modernbert_pass(enc, ps, nullptr, true);
+    const int j0 = sent_indptr[ps.s0], j1 = sent_indptr[ps.s1], nsent = j1 - j0;
+    if (nsent > 0) {
+      std::vector<int32_t> r0(nsent), r1(nsent);
+      for (int i = ps.s0; i < ps.s1; ++i)
+        for (int j = sent_indptr[i]; j < sent_indptr[i + 1]; ++j) {
+          r0[j - j0] = cu[i] - ps.t0 + sent_start[j];
+          r1[j - j0] = cu[i] - ps.t0 + sent_end[j];
+        }
+      enc->srow0.reserve(static_cast<size_t>(nsent) * 4);
+      enc->srow1.reserve(static_cast<size_t>(nsent) * 4);
+      enc->slog.reserve(static_cast<size_t>(nsent) * 8);
+      VRAG_CUDA(cudaMemcpyAsync(enc->srow0.p, r0.data(), static_cast<size_t>(nsent) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+      VRAG_CUDA(cudaMemcpyAsync(enc->srow1.p, r1.data(), static_cast<size_t>(nsent) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+      launch_sentence_head(_ctx, enc->x32.as<float>(), enc->hidden, enc->srow0.as<int32_t>(), enc->srow1.as<int32_t>(), nsent,
+                           enc->cls_w, enc->cls_b, enc->slog.as<float>());
+      VRAG_CUDA(cudaMemcpyAsync(logits_out + 2 * static_cast<size_t>(j0), enc->slog.p, static_cast<size_t>(nsent) * 8,
+                                cudaMemcpyDeviceToHost, _ctx->stream));
+    }
+    VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));   // r0 / r1 are stack-owned
   }
   VRAG_API_END()
 }

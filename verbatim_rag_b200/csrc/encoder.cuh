@@ -42,7 +42,13 @@ void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int 
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
                           const float* beta, float eps, float* x32, __half* h16, __half* h16_lo = nullptr,
-                          int hidden = HIDDEN);
+                          int hidden = HIDDEN, const int32_t* type_ids = nullptr);
+// Cross-encoder head on the [CLS] rows: scores[s] = W_c tanh(W_p x_CLS + b_p) + b_c  (BertForSequenceClassification).
+void launch_cls_head(vrag_ctx* ctx, const float* x32, const int32_t* cu_seqlens_dev, int nseq, int hidden, const float* wp,
+                     const float* bp, const float* wc, const float* bc, float* scores);
+// Sentence head (legacy QAModel): mean of x32 rows [row_start, row_end] -> Linear(hidden, 2).
+void launch_sentence_head(vrag_ctx* ctx, const float* x32, int hidden, const int32_t* row_start, const int32_t* row_end,
+                          int nsent, const float* cw, const float* cb, float* logits);
 // h16 = LN(x32) * gamma (+ beta); if write_back, x32 is overwritten with the normalised row too (post-LN residual).
 // h16_lo (nullable): low plane of h16 (split-precision mode).
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps,

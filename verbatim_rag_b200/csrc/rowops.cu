@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(32 * ROWS_PER_BLOCK)
 bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int T, int vocab, int max_pos,
                      const float* __restrict__ wemb, const float* __restrict__ pemb, const float* __restrict__ temb0,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     float* __restrict__ x32, __half* __restrict__ h16, __half* __restrict__ lo16) {
+                     float* __restrict__ x32, __half* __restrict__ h16, __half* __restrict__ lo16,
+                     const int32_t* __restrict__ type_ids) {
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -154,7 +155,9 @@ bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict_
   p = p >= max_pos ? max_pos - 1 : p;
   const float4* e = reinterpret_cast<const float4*>(wemb + static_cast<size_t>(id) * H);
   const float4* pe = reinterpret_cast<const float4*>(pemb + static_cast<size_t>(p) * H);
-  const float4* te = reinterpret_cast<const float4*>(temb0);
+  // token type 1 = second segment of a pair input (cross-encoder reranker); temb0 holds both rows back to back
+  const int tt = type_ids ? (type_ids[row] != 0 ? 1 : 0) : 0;
+  const float4* te = reinterpret_cast<const float4*>(temb0 + static_cast<size_t>(tt) * H);
   float4 v[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -270,6 +273,67 @@ head_finish_kernel(const float4* __restrict__ part, int T, int slots, float inv_
   const float m = fmaxf(l0, l1);
   const float e0 = expf(l0 - m), e1 = expf(l1 - m);
   probs[row] = e1 / (e0 + e1);
+}
+
+// ---- cross-encoder head (BertForSequenceClassification, num_labels = 1: the reference's SentenceTransformersReranker,
+// verbatim_rag/rerankers.py:109-134): score = W_c tanh(W_p h_CLS + b_p) + b_c.  One block per sequence; the pooler
+// matrix (H x H fp32) streams from L2.
+__global__ void __launch_bounds__(256)
+cls_head_kernel(const float* __restrict__ x32, const int32_t* __restrict__ cu, int H, const float* __restrict__ wp,
+                const float* __restrict__ bp, const float* __restrict__ wc, const float* __restrict__ bc,
+                float* __restrict__ scores) {
+  __shared__ float xs[768];
+  __shared__ float red[8];
+  const int s = blockIdx.x;
+  const float* x = x32 + static_cast<size_t>(cu[s]) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float part = 0.f;
+  for (int n = warp; n < H; n += 8) {   // one pooler row per warp
+    const float* w = wp + static_cast<size_t>(n) * H;
+    float acc = 0.f;
+    for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(w + k), xs[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) part += __ldg(wc + n) * tanhf(acc + __ldg(bp + n));
+  }
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = bc[0];
+    for (int w = 0; w < 8; ++w) t += red[w];
+    scores[s] = t;
+  }
+}
+
+// ---- sentence head (the legacy QAModel, packages/core/verbatim_core/extractor_models/model.py:59-117): mean of the final
+// hidden states over the token rows [start, end] of a sentence -> Linear(H, 2).  One block per sentence.
+__global__ void __launch_bounds__(256)
+sentence_head_kernel(const float* __restrict__ x32, int H, const int32_t* __restrict__ row_start,
+                     const int32_t* __restrict__ row_end /*inclusive*/, const float* __restrict__ cw,
+                     const float* __restrict__ cb, float* __restrict__ logits) {
+  __shared__ float red0[8], red1[8];
+  const int s = blockIdx.x;
+  const int a = row_start[s], b = row_end[s];
+  float d0 = 0.f, d1 = 0.f;
+  const float inv = b >= a ? 1.0f / static_cast<float>(b - a + 1) : 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float t = 0.f;
+    for (int r = a; r <= b; ++r) t += x32[static_cast<size_t>(r) * H + c];
+    t *= inv;
+    d0 = fmaf(t, __ldg(cw + c), d0);
+    d1 = fmaf(t, __ldg(cw + H + c), d1);
+  }
+  d0 = warp_sum(d0);
+  d1 = warp_sum(d1);
+  if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5] = d0; red1[threadIdx.x >> 5] = d1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = cb[0], t1 = cb[1];
+    for (int w = 0; w < 8; ++w) { t0 += red0[w]; t1 += red1[w]; }
+    logits[2 * s] = t0;
+    logits[2 * s + 1] = t1;
+  }
 }
 
 // ---- SPLADE: dense [nseq, ld] -> CSR, entries > min_abs, ascending vocabulary index ----
@@ -420,17 +484,18 @@ void launch_hilo_to_f32(vrag_ctx* ctx, const __half* hi, const uint8_t* lo, int 
 }
 void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos, int T, int vocab, int max_pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
-                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo, int hidden) {
+                          const float* beta, float eps, float* x32, __half* h16, __half* h16_lo, int hidden,
+                          const int32_t* type_ids) {
   ProfScope prof(ctx, PROF_ROWOPS);
   VRAG_CHECK(hidden == 768 || hidden == 384, VRAG_ERR_ARG, "row kernels: hidden size must be 768 or 384");
   if (hidden == 768)
     bert_embed_ln_kernel<6><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
                                                                                    pos_emb, type_emb0, gamma, beta, eps,
-                                                                                   x32, h16, h16_lo);
+                                                                                   x32, h16, h16_lo, type_ids);
   else
     bert_embed_ln_kernel<3><<<row_blocks(T), 32 * ROWS_PER_BLOCK, 0, ctx->stream>>>(ids, pos, T, vocab, max_pos, word_emb,
                                                                                    pos_emb, type_emb0, gamma, beta, eps,
-                                                                                   x32, h16, h16_lo);
+                                                                                   x32, h16, h16_lo, type_ids);
   VRAG_LAUNCHED(ctx);
 }
 void launch_layernorm(vrag_ctx* ctx, float* x32, int T, const float* gamma, const float* beta, float eps, __half* h16,
@@ -457,6 +522,18 @@ void launch_head_finish(vrag_ctx* ctx, const float* head_part, int T, int slots,
   ProfScope prof(ctx, PROF_ROWOPS);
   head_finish_kernel<<<(T + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(head_part), T, slots,
                                                                 1.0f / H, eps, g0, g1, cls_b, logits, probs);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_cls_head(vrag_ctx* ctx, const float* x32, const int32_t* cu, int nseq, int hidden, const float* wp,
+                     const float* bp, const float* wc, const float* bc, float* scores) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  cls_head_kernel<<<nseq, 256, 0, ctx->stream>>>(x32, cu, hidden, wp, bp, wc, bc, scores);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_sentence_head(vrag_ctx* ctx, const float* x32, int hidden, const int32_t* row_start, const int32_t* row_end,
+                          int nsent, const float* cw, const float* cb, float* logits) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  sentence_head_kernel<<<nsent, 256, 0, ctx->stream>>>(x32, hidden, row_start, row_end, cw, cb, logits);
   VRAG_LAUNCHED(ctx);
 }
 void launch_splade_count(vrag_ctx* ctx, const float* dense, int nseq, int ld, int vocab, float min_abs,

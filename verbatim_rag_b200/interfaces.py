@@ -99,6 +99,35 @@ except Exception:  # pragma: no cover
         def delete(self, ids: List[str]): ...
 
 
+try:
+    from verbatim_rag.rerankers import BaseReranker  # type: ignore
+    USING_REFERENCE_ABCS["reranker"] = True
+except Exception:  # pragma: no cover
+    USING_REFERENCE_ABCS["reranker"] = False
+
+    class BaseReranker(ABC):  # type: ignore[no-redef]
+        """Structural mirror of verbatim_rag/rerankers.py:14-41 (Reranker + BaseReranker)."""
+
+        def __init__(self, rerank_k: int = 50, text_field: str = "text"):
+            self.rerank_k = rerank_k
+            self.text_field = text_field
+
+        @abstractmethod
+        def rerank(self, question: str, results: List[Any]) -> List[Any]: ...
+
+        async def rerank_async(self, question: str, results: List[Any]) -> List[Any]:
+            import asyncio
+            return await asyncio.to_thread(self.rerank, question, results)
+
+        def _split_results(self, results):
+            return results[: self.rerank_k], results[self.rerank_k:]
+
+        def _get_texts(self, results) -> List[str]:
+            if self.text_field == "enhanced_text":
+                return [r.enhanced_text or r.text for r in results]
+            return [r.text for r in results]
+
+
 try:  # the reference's own hybrid merge / metadata helpers are reused verbatim when present (SURVEY.md a9)
     from verbatim_rag.vector_stores.hybrid_search import merge_hybrid_results, sanitize_hybrid_weights  # type: ignore
     from verbatim_rag.vector_stores.utils import json_serialize_safe, promote_metadata  # type: ignore

@@ -36,18 +36,23 @@ def _load_safetensors(path: str) -> Dict[str, np.ndarray]:
     return {k: np.asarray(v, dtype=np.float32) for k, v in load_file(path).items()}
 
 
-def resolve_modernbert(model_path: str):
-    """-> (weights, tokenizer, num_layers, vocab_size)"""
-    from .synthetic import ModernBertSpec, SyntheticTokenizer, make_modernbert_weights
+def resolve_modernbert(model_path: str, head: str = "highlighter"):
+    """-> (weights, tokenizer, num_layers, vocab_size).  ``head``: "highlighter" (token classifier, the v2 format) or
+    "qa_model" (the legacy sentence classifier: encoder + ``classifier`` only; its checkpoints name the encoder
+    ``bert.*`` -- QAModel.bert, extractor_models/model.py:51 -- which is mapped to ``model.*`` here)."""
+    from .synthetic import (ModernBertSpec, SyntheticTokenizer, make_modernbert_weights, make_qa_model_weights)
 
     if model_path.startswith("synthetic"):
         parts = model_path.split(":")
         seed = int(parts[1]) if len(parts) > 1 and parts[1] else 1001
         layers = int(parts[2]) if len(parts) > 2 else 22
         spec = ModernBertSpec(layers=layers)
-        return make_modernbert_weights(seed, spec), SyntheticTokenizer("modernbert"), spec.layers, spec.vocab_size
+        make = make_qa_model_weights if head == "qa_model" else make_modernbert_weights
+        return make(seed, spec), SyntheticTokenizer("modernbert"), spec.layers, spec.vocab_size
     if os.path.isdir(model_path):
         w = _load_safetensors(os.path.join(model_path, "model.safetensors"))
+        if head == "qa_model" and any(k.startswith("bert.") for k in w):
+            w = {("model." + k[len("bert."):] if k.startswith("bert.") else k): v for k, v in w.items()}
         layers = 1 + max(int(k.split(".")[2]) for k in w if k.startswith("model.layers."))
         vocab = w["model.embeddings.tok_embeddings.weight"].shape[0]
         spec = ModernBertSpec()
@@ -57,16 +62,18 @@ def resolve_modernbert(model_path: str):
         f"{model_path!r}: not 'synthetic:<seed>' and not a local checkpoint directory (hub download is not available)")
 
 
-def resolve_bert(model_name: str, mlm: bool = True):
-    """-> (weights, tokenizer, num_layers, vocab_size)"""
-    from .synthetic import BertSpec, SyntheticTokenizer, make_bert_mlm_weights
+def resolve_bert(model_name: str, mlm: bool = True, head: str = "mlm"):
+    """-> (weights, tokenizer, num_layers, vocab_size).  ``head``: "mlm" (SPLADE / dense providers) or "cross_encoder"
+    (``BertForSequenceClassification`` with one label: the reranker)."""
+    from .synthetic import BertSpec, SyntheticTokenizer, make_bert_mlm_weights, make_cross_encoder_weights
 
     if model_name.startswith("synthetic"):
         parts = model_name.split(":")
-        seed = int(parts[1]) if len(parts) > 1 and parts[1] else 1002
+        seed = int(parts[1]) if len(parts) > 1 and parts[1] else (1004 if head == "cross_encoder" else 1002)
         layers = int(parts[2]) if len(parts) > 2 else 12
         spec = BertSpec(layers=layers)
-        return make_bert_mlm_weights(seed, spec), SyntheticTokenizer("bert"), spec.layers, spec.vocab_size
+        make = make_cross_encoder_weights if head == "cross_encoder" else make_bert_mlm_weights
+        return make(seed, spec), SyntheticTokenizer("bert"), spec.layers, spec.vocab_size
     if os.path.isdir(model_name):
         w = _load_safetensors(os.path.join(model_name, "model.safetensors"))
         if not any(k.startswith("bert.") for k in w):  # bare BertModel checkpoints lack the 'bert.' prefix

@@ -163,6 +163,28 @@ def make_bert_mlm_weights(seed: int = 1002, spec: BertSpec = BertSpec(),
     return w
 
 
+def make_cross_encoder_weights(seed: int = 1004, spec: BertSpec = BertSpec()) -> Dict[str, np.ndarray]:
+    """Seeded ``BertForSequenceClassification`` weights with one label (a cross-encoder reranker such as
+    cross-encoder/ms-marco-MiniLM-L-6-v2, verbatim_rag/rerankers.py:112): the BERT stack of ``make_bert_mlm_weights``
+    + ``bert.pooler.dense`` + ``classifier`` [1, H]."""
+    w = {k: v for k, v in make_bert_mlm_weights(seed, spec).items() if not k.startswith("cls.")}
+    rng = np.random.Generator(np.random.PCG64(seed + 100))
+    H = spec.hidden
+    w["bert.pooler.dense.weight"] = _normal(rng, (H, H), 0.05)
+    w["bert.pooler.dense.bias"] = _normal(rng, (H,), 0.02)
+    w["classifier.weight"] = _normal(rng, (1, H), 0.2)
+    w["classifier.bias"] = np.asarray([0.1], dtype=np.float32)
+    return w
+
+
+def make_qa_model_weights(seed: int = 1001, spec: ModernBertSpec = ModernBertSpec()) -> Dict[str, np.ndarray]:
+    """Seeded weights of the legacy ``QAModel`` (packages/core/verbatim_core/extractor_models/model.py:13-57): a
+    ModernBERT encoder + ``classifier`` Linear(H, 2) on mean-pooled sentence states -- no prediction head."""
+    w = {k: v for k, v in make_modernbert_weights(seed, spec, classifier_scale=10.0,
+                                                  classifier_bias=(0.2, -0.2)).items() if not k.startswith("head.")}
+    return w
+
+
 # --------------------------------------------------------------------------------------
 # tokenizer + text
 # --------------------------------------------------------------------------------------
