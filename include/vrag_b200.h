@@ -9,6 +9,7 @@
  *   vrag_span_forward        <- ModelSpanExtractor._extract_highlighter -> model.process()
  *                               packages/core/verbatim_core/extractors.py:203-228 (forward part)
  *   vrag_spans_from_probs    <- same call, span post-processing part (threshold / merge / min length)
+ *   vrag_span_extract        <- same call, forward + post-processing fused on the device (only spans come back)
  *   vrag_encoder_create      <- ModelSpanExtractor._init_highlighter   extractors.py:151-157
  *                               SpladeProvider._load_model              verbatim_rag/embedding_providers.py:125-136
  *   vrag_splade_forward      <- SpladeProvider.embed_batch / embed_text -> SparseEncoder.encode
@@ -196,6 +197,18 @@ int vrag_spans_from_probs(const float* probs, const int32_t* tok_char_start, con
                           int merge_gap_chars, int32_t* span_ctx, int32_t* span_char_start, int32_t* span_char_end,
                           float* span_score, int32_t* span_tok_start, int32_t* span_tok_end, int64_t cap,
                           int64_t* nspans_out);
+
+/* Span extraction with the post-processing on the device (reference: all of model.process(), extractors.py:213-224):
+ * forward + threshold / runs / gap merge / min length per sequence over its context tokens
+ * [ctx_first[i], ctx_first[i] + ctx_len[i]); tok_char_start / tok_char_end are the character offsets of the context
+ * tokens of all sequences back to back.  Only the spans come back (same outputs and rules as vrag_spans_from_probs,
+ * span_seq = sequence index; results are bit-identical to vrag_span_forward + vrag_spans_from_probs).  One sequence per
+ * context: documents that need several windows use the two-call form.  Host buffers. */
+int vrag_span_extract(vrag_encoder* enc, const int32_t* ids, const int32_t* cu_seqlens, int nseq,
+                      const int32_t* ctx_first, const int32_t* ctx_len, const int32_t* tok_char_start,
+                      const int32_t* tok_char_end, float threshold, int min_span_chars, int merge_gap_chars,
+                      int32_t* span_seq, int32_t* span_char_start, int32_t* span_char_end, float* span_score,
+                      int32_t* span_tok_start, int32_t* span_tok_end, int64_t cap, int64_t* nspans_out);
 
 /* ---- exact top-k index --------------------------------------------------------------------- */
 int vrag_index_create(vrag_ctx* ctx, int kind, int dim, vrag_index** out);

@@ -45,6 +45,30 @@ def main():
     rid, _, rd = fsx.search_sparse(qip, qix, qvl, k, want64=True)
     assert np.array_equal(sid.cpu().numpy(), rid), "sparse ids differ"
     assert np.array_equal(sd.cpu().numpy(), rd), "sparse fp64 scores differ"
+    # the plugin-level store: vectors split over the ranks, payload replicated, one all-gather per search
+    from verbatim_rag_b200 import B200VectorStore
+    from verbatim_rag_b200.sharded_store import ShardedB200VectorStore
+    from verbatim_rag_b200.synthetic import csr_to_dicts
+    m = 3001
+    cid = [f"c{i:05d}" for i in range(m)]
+    texts = [f"text {i}" for i in range(m)]
+    metas = [{"year": 2000 + i % 20} for i in range(m)]
+    sp_rows = csr_to_dicts(ip[:m + 1], ix, vl)
+    qd = csr_to_dicts(qip, qix, qvl)
+    flt = 'metadata["year"] >= 2010'
+    answers = []
+    for cls in (ShardedB200VectorStore, B200VectorStore):
+        st = cls(dense_dim=768, enable_dense=True, enable_sparse=True, device=f"cuda:{local}")
+        for a in range(0, m, 1000):
+            b = min(m, a + 1000)
+            st.add_vectors(cid[a:b], corpus[a:b].tolist(), sp_rows[a:b], texts[a:b], texts[a:b], metas[a:b])
+        st.delete([cid[7], cid[2999]])
+        answers.append((
+            [[(r.id, r.score) for r in rs] for rs in st.query_batch(dense_queries=queries[:9], top_k=k, search_type="dense")],
+            [[(r.id, r.score) for r in rs] for rs in st.query_batch(sparse_queries=qd[:9], top_k=k, search_type="sparse")],
+            [[r.id for r in rs] for rs in st.query_batch(dense_queries=queries[:9], top_k=k, search_type="dense", filter=flt)],
+            [(r.id, r.score, r.text) for r in st.query(dense_query=queries[0].tolist(), top_k=5, search_type="dense")]))
+    assert answers[0] == answers[1], "sharded store differs from the unsharded store"
     dist.barrier()
     if rank == 0:
         print("SHARDED_OK")

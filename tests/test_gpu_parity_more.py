@@ -203,3 +203,44 @@ def test_plugins_load_a_checkpoint_directory(tmp_path):
     pa = B200SpladeProvider(str(tmp_path / "b"), max_tokens=2048)
     pb = B200SpladeProvider(weights=bw, tokenizer=btok, num_layers=2, vocab_size=bspec.vocab_size, max_tokens=2048)
     assert pa.embed_batch(texts) == pb.embed_batch(texts) and len(pa.embed_batch(texts)[0]) > 0
+
+
+def test_device_span_postprocessing_equals_host(ctx):
+    """vrag_span_extract (forward + threshold / runs / gap merge / min length on the device, only spans come
+    back) must equal vrag_span_forward + vrag_spans_from_probs (the host function, itself checked against the oracle in
+    tests/test_spans_host.py) bit for bit -- ragged contexts, several passes, a context without any token, thresholds that
+    produce many / no spans."""
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import ModernBertSpec, make_modernbert_weights
+    spec = ModernBertSpec(layers=2)
+    w = make_modernbert_weights(1001, spec)
+    rng = np.random.default_rng(33)
+    lens = [512, 40, 300, 129, 64, 77, 250, 33, 400, 5]
+    nq = [29, 10, 12, 20, 3, 15, 29, 8, 11, 2]
+    seqs, first, clen, tcs, tce = [], [], [], [], []
+    for L, q in zip(lens, nq):
+        s_ = rng.integers(5, 50279, size=L).astype(np.int64)
+        s_[0], s_[q + 1], s_[-1] = spec.cls_id, spec.sep_id, spec.sep_id
+        seqs.append(s_)
+        n_ctx = max(0, L - q - 3)
+        first.append(q + 2)
+        clen.append(n_ctx)
+        starts = np.cumsum(rng.integers(2, 12, size=n_ctx)) if n_ctx else np.zeros(0, np.int64)
+        tcs.append(starts.astype(np.int32))
+        tce.append((starts + rng.integers(1, 9, size=n_ctx)).astype(np.int32))
+    clen[4] = 0                                                     # a context without tokens
+    tcs[4], tce[4] = tcs[4][:0], tce[4][:0]
+    tcs, tce = np.concatenate(tcs), np.concatenate(tce)
+    ids, cu = _native.Encoder._pack(seqs)
+    for max_tokens, thr, min_chars, gap in ((4096, 0.2, 30, 20), (640, 0.5, 1, 0), (640, 0.9999, 30, 20), (4096, 0.0, 30, 500)):
+        enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_TOKCLS, w, spec.layers, spec.vocab_size, max_tokens=max_tokens)
+        probs = enc.span_forward(ids, cu)
+        p_ctx = np.concatenate([probs[cu[i] + first[i]: cu[i] + first[i] + clen[i]] for i in range(len(seqs))])
+        indptr = np.concatenate([[0], np.cumsum(clen)]).astype(np.int64)
+        host = _native.spans_from_probs(p_ctx, tcs, tce, indptr, thr, min_chars, gap)
+        dev = enc.span_extract(ids, cu, first, clen, tcs, tce, thr, min_chars, gap)
+        enc.close()
+        for key in host:
+            assert np.array_equal(host[key], dev[key]), (key, max_tokens, thr)
+        if thr == 0.2:
+            assert len(host["ctx"]) > 5

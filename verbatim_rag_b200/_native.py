@@ -32,6 +32,7 @@ EXPORTS = [
     "vrag_topk_merge",
     "vrag_encoder_create_ex", "vrag_selftest_gemm_split", "vrag_bench_gemm_split", "vrag_selftest_attention_split",
     "vrag_bench_attention_split", "vrag_encoder_hidden", "vrag_rerank_forward", "vrag_sentence_forward",
+    "vrag_span_extract",
 ]
 
 
@@ -88,6 +89,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_encoder_hidden": (i32, [vp]),
             "vrag_rerank_forward": (i32, [vp, vp, vp, vp, i32, vp, i32]),
             "vrag_sentence_forward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp]),
+            "vrag_span_extract": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
             "vrag_selftest_gemm_split": (i32, [vp, i32, i32, i32, i32, P(f64), P(f64)]),
             "vrag_bench_gemm_split": (i32, [vp, i32, i32, i32, i32, i32, P(f64)]),
             "vrag_selftest_attention_split": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
@@ -370,6 +372,30 @@ class Encoder:
         self.ctx.check(self.ctx.lib.vrag_dense_forward(self.h, _ptr(ids), _ptr(cu), len(cu) - 1, pooling,
                                                        1 if normalize else 0, _ptr(out), 0))
         return out
+
+    def span_extract(self, ids, cu, ctx_first, ctx_len, tok_cs, tok_ce, threshold: float, min_span_chars: int,
+                     merge_gap_chars: int):
+        """Forward + span post-processing on the device (one sequence per context); same dict as ``spans_from_probs``
+        with ``ctx`` = sequence index."""
+        ids, cu = _np(ids, np.int32), _np(cu, np.int32)
+        cf, cl = _np(ctx_first, np.int32), _np(ctx_len, np.int32)
+        tcs, tce = _np(tok_cs, np.int32), _np(tok_ce, np.int32)
+        nseq = len(cu) - 1
+        cap = max(16, int(cl.sum()) // 8 + nseq)
+        n = C.c_int64()
+        while True:
+            sc, cs, ce, ts, te = (np.empty(cap, np.int32) for _ in range(5))
+            score = np.empty(cap, np.float32)
+            rc = self.ctx.lib.vrag_span_extract(self.h, _ptr(ids), _ptr(cu), nseq, _ptr(cf), _ptr(cl), _ptr(tcs), _ptr(tce),
+                                                float(threshold), int(min_span_chars), int(merge_gap_chars), _ptr(sc), _ptr(cs),
+                                                _ptr(ce), _ptr(score), _ptr(ts), _ptr(te), cap, C.byref(n))
+            if rc == VRAG_ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            self.ctx.check(rc)
+            break
+        k = int(n.value)
+        return {"ctx": sc[:k], "start": cs[:k], "end": ce[:k], "score": score[:k], "tok_start": ts[:k], "tok_end": te[:k]}
 
     def rerank_forward(self, ids: np.ndarray, type_ids: np.ndarray, cu: np.ndarray) -> np.ndarray:
         """Cross-encoder relevance logits, one per packed pair sequence (ENC_BERT_CLS encoders)."""

@@ -70,14 +70,15 @@ struct vrag_encoder {
   float *mlm_b = nullptr, *mlm_g = nullptr, *mlm_beta = nullptr, *dec_b = nullptr;
   // workspace
   DevBuf ids, cu, pos, seqrow, x32, h16, qkv16, o16, w16, buf32, probs, logits, splade, counts, indptr, sp_idx, sp_val,
-      pooled, work, stats, stats2, xl8, h16_lo, qkv16_lo, o16_lo, w16_lo, types, srow0, srow1, slog;
+      pooled, work, stats, stats2, xl8, h16_lo, qkv16_lo, o16_lo, w16_lo, types, srow0, srow1, slog, sp_meta, sp_off, sp_out;
   int n_pairs = 0;  // (sequence, 128-query tile) entries of the current pass in `work`
 
   ~vrag_encoder() {
     for (auto* b : owned) { b->release(); delete b; }
     for (DevBuf* b : {&ids, &cu, &pos, &seqrow, &x32, &h16, &qkv16, &o16, &w16, &buf32, &probs, &logits, &splade,
                       &counts, &indptr, &sp_idx, &sp_val, &pooled, &work, &stats, &stats2, &xl8, &h16_lo, &qkv16_lo,
-                      &o16_lo, &w16_lo, &types, &srow0, &srow1, &slog})
+                      &o16_lo, &w16_lo, &types, &srow0, &srow1, &slog, &sp_meta,
+                      &sp_off, &sp_out})
       b->release();
   }
   template <typename T>
@@ -895,5 +896,91 @@ extern "C" int vrag_sentence_forward(vrag_encoder* enc, const int32_t* ids, cons
     }
     VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));   // r0 / r1 are stack-owned
   }
+  VRAG_API_END()
+}
+
+// Span extraction with the post-processing on the device (reference: the whole of model.process(),
+// extractors.py:213-224): forward, then per sequence threshold -> runs -> char spans -> gap merge -> min length over its
+// context tokens [ctx_first[i], ctx_first[i] + ctx_len[i]) with the character offsets tok_char_start / tok_char_end
+// (concatenated over the sequences).  Only the spans (24 bytes each) come back instead of the probabilities (4 bytes per
+// token); outputs as in vrag_spans_from_probs with span_seq = sequence index.  Single-window inputs only (one sequence
+// per context); documents that need several windows go through vrag_span_forward + vrag_spans_from_probs.
+extern "C" int vrag_span_extract(vrag_encoder* enc, const int32_t* ids, const int32_t* cu, int nseq,
+                                 const int32_t* ctx_first, const int32_t* ctx_len, const int32_t* tok_char_start,
+                                 const int32_t* tok_char_end, float threshold, int min_span_chars, int merge_gap_chars,
+                                 int32_t* span_seq, int32_t* span_char_start, int32_t* span_char_end, float* span_score,
+                                 int32_t* span_tok_start, int32_t* span_tok_end, int64_t cap, int64_t* nspans_out) {
+  if (!enc) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(enc->ctx)
+  VRAG_CHECK(enc->kind == VRAG_ENC_MODERNBERT_TOKCLS, VRAG_ERR_ARG, "span_extract needs a MODERNBERT_TOKCLS encoder");
+  VRAG_CHECK(ids && cu && ctx_first && ctx_len && nspans_out && nseq >= 0, VRAG_ERR_ARG, "span_extract: null argument");
+  *nspans_out = 0;
+  if (nseq == 0) return VRAG_OK;
+  std::vector<int64_t> tok_base(nseq + 1, 0);
+  for (int i = 0; i < nseq; ++i) {
+    const int L = cu[i + 1] - cu[i];
+    VRAG_CHECK(L > 0 && L <= enc->max_pos, VRAG_ERR_ARG, "span_extract: bad sequence length");
+    VRAG_CHECK(ctx_first[i] >= 0 && ctx_len[i] >= 0 && ctx_first[i] + ctx_len[i] <= L, VRAG_ERR_ARG,
+               "span_extract: context range outside its sequence");
+    tok_base[i + 1] = tok_base[i] + ctx_len[i];
+  }
+  VRAG_CHECK(tok_base[nseq] == 0 || (tok_char_start && tok_char_end), VRAG_ERR_ARG, "span_extract: null offsets");
+  auto passes = plan_passes(cu, nseq, enc->max_tokens, enc->max_seqs);
+  int64_t total = 0;
+  for (const Pass& ps : passes) {
+    const int ns = ps.s1 - ps.s0;
+    const int64_t ntok = tok_base[ps.s1] - tok_base[ps.s0];
+    stage_pass(enc, ps, ids, cu, 0);
+    modernbert_pass(enc, ps, nullptr);
+    // per-pass metadata: [ctx_first ns | ctx_len ns] int32, tok_base ns int64 (relative to this pass), offsets 2 x ntok int32
+    const size_t meta_bytes = static_cast<size_t>(ns) * 16 + static_cast<size_t>(ntok) * 8;
+    enc->sp_meta.reserve(std::max<size_t>(meta_bytes, 16));
+    uint8_t* mp = enc->sp_meta.as<uint8_t>();
+    int64_t* d_base = reinterpret_cast<int64_t*>(mp);
+    int32_t* d_first = reinterpret_cast<int32_t*>(mp + static_cast<size_t>(ns) * 8);
+    int32_t* d_len = d_first + ns;
+    int32_t* d_tcs = d_len + ns;
+    int32_t* d_tce = d_tcs + ntok;
+    std::vector<int64_t> rel(ns);
+    for (int i = 0; i < ns; ++i) rel[i] = tok_base[ps.s0 + i] - tok_base[ps.s0];
+    VRAG_CUDA(cudaMemcpyAsync(d_base, rel.data(), static_cast<size_t>(ns) * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(d_first, ctx_first + ps.s0, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    VRAG_CUDA(cudaMemcpyAsync(d_len, ctx_len + ps.s0, static_cast<size_t>(ns) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    if (ntok) {
+      VRAG_CUDA(cudaMemcpyAsync(d_tcs, tok_char_start + tok_base[ps.s0], static_cast<size_t>(ntok) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+      VRAG_CUDA(cudaMemcpyAsync(d_tce, tok_char_end + tok_base[ps.s0], static_cast<size_t>(ntok) * 4, cudaMemcpyHostToDevice, _ctx->stream));
+    }
+    enc->sp_off.reserve((static_cast<size_t>(ns) * 2 + 1) * 4);
+    int32_t* d_counts = enc->sp_off.as<int32_t>();
+    int32_t* d_offs = d_counts + ns;
+    launch_span_runs(_ctx, enc->probs.as<float>(), enc->cu.as<int32_t>(), d_first, d_len, d_base, d_tcs, d_tce, ns, threshold,
+                     min_span_chars, merge_gap_chars, d_counts, d_offs, ps.s0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, false);
+    int32_t n_here = 0;
+    VRAG_CUDA(cudaMemcpyAsync(&n_here, d_offs + ns, 4, cudaMemcpyDeviceToHost, _ctx->stream));
+    VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));   // also: rel is stack-owned
+    if (n_here > 0) {
+      enc->sp_out.reserve(static_cast<size_t>(n_here) * 24);
+      int32_t* o_seq = enc->sp_out.as<int32_t>();
+      int32_t *o_cs = o_seq + n_here, *o_ce = o_cs + n_here, *o_ts = o_ce + n_here, *o_te = o_ts + n_here;
+      float* o_sc = reinterpret_cast<float*>(o_te + n_here);
+      launch_span_runs(_ctx, enc->probs.as<float>(), enc->cu.as<int32_t>(), d_first, d_len, d_base, d_tcs, d_tce, ns,
+                       threshold, min_span_chars, merge_gap_chars, nullptr, d_offs, ps.s0, o_seq, o_cs, o_ce, o_sc, o_ts,
+                       o_te, true);
+      if (total + n_here <= cap) {
+        const size_t nb = static_cast<size_t>(n_here) * 4;
+        VRAG_CUDA(cudaMemcpyAsync(span_seq + total, o_seq, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+        VRAG_CUDA(cudaMemcpyAsync(span_char_start + total, o_cs, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+        VRAG_CUDA(cudaMemcpyAsync(span_char_end + total, o_ce, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+        VRAG_CUDA(cudaMemcpyAsync(span_tok_start + total, o_ts, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+        VRAG_CUDA(cudaMemcpyAsync(span_tok_end + total, o_te, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+        VRAG_CUDA(cudaMemcpyAsync(span_score + total, o_sc, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+      }
+      VRAG_CUDA(cudaStreamSynchronize(_ctx->stream));
+    }
+    total += n_here;
+  }
+  *nspans_out = total;
+  if (total > cap) throw Error(VRAG_ERR_CAPACITY, "span_extract: output capacity too small; see *nspans_out");
   VRAG_API_END()
 }

@@ -43,6 +43,12 @@ void launch_bert_embed_ln(vrag_ctx* ctx, const int32_t* ids, const int32_t* pos,
                           const float* word_emb, const float* pos_emb, const float* type_emb0, const float* gamma,
                           const float* beta, float eps, float* x32, __half* h16, __half* h16_lo = nullptr,
                           int hidden = HIDDEN, const int32_t* type_ids = nullptr);
+// Device span post-processing: fill = false counts the spans of each sequence into counts[nseq] and
+// their exclusive prefix sums into offs[nseq + 1]; fill = true writes the spans at offs[seq].
+void launch_span_runs(vrag_ctx* ctx, const float* probs, const int32_t* cu, const int32_t* ctx_first, const int32_t* ctx_len,
+                      const int64_t* tok_base, const int32_t* tcs, const int32_t* tce, int nseq, float threshold,
+                      int min_span_chars, int merge_gap_chars, int32_t* counts, int32_t* offs, int32_t seq_base,
+                      int32_t* o_seq, int32_t* o_cs, int32_t* o_ce, float* o_score, int32_t* o_ts, int32_t* o_te, bool fill);
 // Cross-encoder head on the [CLS] rows: scores[s] = W_c tanh(W_p x_CLS + b_p) + b_c  (BertForSequenceClassification).
 void launch_cls_head(vrag_ctx* ctx, const float* x32, const int32_t* cu_seqlens_dev, int nseq, int hidden, const float* wp,
                      const float* bp, const float* wc, const float* bc, float* scores);

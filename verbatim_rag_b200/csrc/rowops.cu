@@ -275,6 +275,77 @@ head_finish_kernel(const float4* __restrict__ part, int T, int slots, float inv_
   probs[row] = e1 / (e0 + e1);
 }
 
+// ---- span post-processing on the device (the integer half of the highlighter contract, identical to
+// the host function vrag_spans_from_probs in api.cu / oracle/highlighter.py steps 4-8): one thread per sequence walks
+// its context tokens: keep = p > threshold; maximal runs -> char spans; merge gaps <= merge_gap_chars; drop spans
+// shorter than min_span_chars; score = mean kept p (accumulated in double, same order as the host function, so the
+// results are bit-identical).  FILL = false counts the spans of each sequence, FILL = true writes them at offs[seq].
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+span_runs_kernel(const float* __restrict__ probs, const int32_t* __restrict__ cu, const int32_t* __restrict__ ctx_first,
+                 const int32_t* __restrict__ ctx_len, const int64_t* __restrict__ tok_base,
+                 const int32_t* __restrict__ tcs, const int32_t* __restrict__ tce, int nseq, float threshold,
+                 int min_span_chars, int merge_gap_chars, int32_t* __restrict__ counts, const int32_t* __restrict__ offs,
+                 int32_t seq_base, int32_t* __restrict__ o_seq, int32_t* __restrict__ o_cs, int32_t* __restrict__ o_ce,
+                 float* __restrict__ o_score, int32_t* __restrict__ o_ts, int32_t* __restrict__ o_te) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseq) return;
+  const float* p = probs + cu[s] + ctx_first[s];
+  const int n = ctx_len[s];
+  const int32_t* cs_ = tcs + tok_base[s];
+  const int32_t* ce_ = tce + tok_base[s];
+  int count = 0;
+  int out = FILL ? offs[s] : 0;
+  bool open = false;
+  int32_t cs = 0, ce = 0, ts = 0, te = 0, cnt = 0;
+  double acc = 0.0;
+  auto flush = [&]() {
+    if (open && ce - cs >= min_span_chars) {
+      if (FILL) {
+        o_seq[out] = seq_base + s;
+        o_cs[out] = cs;
+        o_ce[out] = ce;
+        o_score[out] = static_cast<float>(acc / cnt);
+        o_ts[out] = ts;
+        o_te[out] = te;
+        ++out;
+      }
+      ++count;
+    }
+    open = false;
+  };
+  int i = 0;
+  while (i < n) {
+    if (!(p[i] > threshold)) { ++i; continue; }
+    int j = i;
+    double racc = 0.0;
+    while (j < n && p[j] > threshold) { racc += static_cast<double>(p[j]); ++j; }
+    const int32_t rs = cs_[i], re = ce_[j - 1];
+    if (open && rs - ce <= merge_gap_chars) {
+      ce = re;
+      te = j;
+      acc += racc;
+      cnt += j - i;
+    } else {
+      flush();
+      open = true;
+      cs = rs; ce = re; ts = i; te = j;
+      acc = racc;
+      cnt = j - i;
+    }
+    i = j;
+  }
+  flush();
+  if (!FILL) counts[s] = count;
+}
+__global__ void exclusive_scan_small_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out /*[n+1]*/) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int32_t acc = 0;
+    for (int i = 0; i < n; ++i) { out[i] = acc; acc += in[i]; }
+    out[n] = acc;
+  }
+}
+
 // ---- cross-encoder head (BertForSequenceClassification, num_labels = 1: the reference's SentenceTransformersReranker,
 // verbatim_rag/rerankers.py:109-134): score = W_c tanh(W_p h_CLS + b_p) + b_c.  One block per sequence; the pooler
 // matrix (H x H fp32) streams from L2.
@@ -522,6 +593,25 @@ void launch_head_finish(vrag_ctx* ctx, const float* head_part, int T, int slots,
   ProfScope prof(ctx, PROF_ROWOPS);
   head_finish_kernel<<<(T + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(head_part), T, slots,
                                                                 1.0f / H, eps, g0, g1, cls_b, logits, probs);
+  VRAG_LAUNCHED(ctx);
+}
+void launch_span_runs(vrag_ctx* ctx, const float* probs, const int32_t* cu, const int32_t* ctx_first, const int32_t* ctx_len,
+                      const int64_t* tok_base, const int32_t* tcs, const int32_t* tce, int nseq, float threshold,
+                      int min_span_chars, int merge_gap_chars, int32_t* counts, int32_t* offs, int32_t seq_base,
+                      int32_t* o_seq, int32_t* o_cs, int32_t* o_ce, float* o_score, int32_t* o_ts, int32_t* o_te, bool fill) {
+  ProfScope prof(ctx, PROF_ROWOPS);
+  const int blocks = (nseq + 127) / 128;
+  if (!fill) {
+    span_runs_kernel<false><<<blocks, 128, 0, ctx->stream>>>(probs, cu, ctx_first, ctx_len, tok_base, tcs, tce, nseq, threshold,
+                                                            min_span_chars, merge_gap_chars, counts, nullptr, seq_base,
+                                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    VRAG_LAUNCHED(ctx);
+    exclusive_scan_small_kernel<<<1, 32, 0, ctx->stream>>>(counts, nseq, offs);
+  } else {
+    span_runs_kernel<true><<<blocks, 128, 0, ctx->stream>>>(probs, cu, ctx_first, ctx_len, tok_base, tcs, tce, nseq, threshold,
+                                                           min_span_chars, merge_gap_chars, nullptr, offs, seq_base, o_seq,
+                                                           o_cs, o_ce, o_score, o_ts, o_te);
+  }
   VRAG_LAUNCHED(ctx);
 }
 void launch_cls_head(vrag_ctx* ctx, const float* x32, const int32_t* cu, int nseq, int hidden, const float* wp,

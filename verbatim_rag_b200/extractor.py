@@ -95,6 +95,7 @@ class B200SpanExtractor(SpanExtractor):
         # batches of >= worker_min_texts distinct contexts are tokenised by worker processes (_tokworker.py)
         self._workers = TokenizerWorkers(tokenizer.tok, tokenizer_workers)
         self.worker_min_texts = 256
+        self.device_spans = True       # span post-processing on the device when every context fits one window
 
     # -- reference interface -------------------------------------------------------------------------
     def extract_spans(self, question: str, search_results: List[Any]) -> Dict[str, List[str]]:
@@ -171,10 +172,23 @@ class B200SpanExtractor(SpanExtractor):
             out.extend(self._postprocess(pending[0], pending[1], pending[2].result()))
         return out
 
-    def _forward(self, plan: Dict[str, Any]) -> np.ndarray:
+    def _forward(self, plan: Dict[str, Any]):
+        """-> the spans dict of the device post-processing (single-window plans: one sequence per context)
+        or the per-token probabilities (documents split into overlapping windows: max over the windows on the host)."""
         if len(plan["cu"]) <= 1:
             return np.zeros(0, np.float32)
         with self._lock:
+            if plan["single_window"] and self.device_spans and hasattr(self._enc, "span_extract"):
+                wp = plan["win_pair"]
+                ip = plan["ctx_indptr"]
+                live = np.zeros(len(ip) - 1, bool)
+                live[wp] = True
+                # offsets of the live contexts only, in sequence order (contexts without a sequence have no tokens or failed)
+                sel = np.repeat(live, np.diff(ip))
+                sp = self._enc.span_extract(plan["ids"], plan["cu"], plan["win_c0"], plan["win_e"], plan["tok_cs"][sel],
+                                            plan["tok_ce"][sel], self.threshold, self.min_span_chars, self.merge_gap_chars)
+                sp["ctx"] = wp[sp["ctx"]]           # sequence index -> pair index
+                return sp
             return self._enc.span_forward(plan["ids"], plan["cu"])
 
     # -- internals -----------------------------------------------------------------------------------------
@@ -284,9 +298,12 @@ class B200SpanExtractor(SpanExtractor):
         return p_ctx
 
     def _postprocess(self, pairs, plan, probs) -> List[List[Dict[str, Any]]]:
-        p_ctx = self._context_probs(plan, probs)
-        sp = _native.spans_from_probs(p_ctx, plan["tok_cs"], plan["tok_ce"], plan["ctx_indptr"], self.threshold,
-                                      self.min_span_chars, self.merge_gap_chars)
+        if isinstance(probs, dict):
+            sp = probs
+        else:
+            p_ctx = self._context_probs(plan, probs)
+            sp = _native.spans_from_probs(p_ctx, plan["tok_cs"], plan["tok_ce"], plan["ctx_indptr"], self.threshold,
+                                          self.min_span_chars, self.merge_gap_chars)
         out: List[List[Dict[str, Any]]] = [[] for _ in pairs]
         for c, s, e, sc, ts, te in zip(sp["ctx"].tolist(), sp["start"].tolist(), sp["end"].tolist(),
                                        sp["score"].tolist(), sp["tok_start"].tolist(), sp["tok_end"].tolist()):
