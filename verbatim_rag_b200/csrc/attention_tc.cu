@@ -406,92 +406,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               s[32 + e] = (vm1 >> e) & 1u ? s[32 + e] : -INFINITY;
             }
           }
-          // The row-max pass (64 FMNMX + the reduction, a fifth of the block's instructions) only runs on the item's
-          // first block and while a row has not seen a key yet.  Later blocks are evaluated against the reference max the
-          // row already has -- any earlier block's max is a valid reference as long as no probability overflows fp16 --
-          // and are RE-DONE with the exact max only if that happened: the block's row sum bounds every term (p >= 0), so
-          // `sum <= 2^15` proves all 64 probabilities are representable.
-          bool need_max = (i == 0) || __any_sync(0xffffffffu, m_used == -INFINITY);
-          uint64_t sum2 = 0ull, sum2b = 0ull;
-#pragma unroll 1
-          for (int attempt = 0; attempt < 2; ++attempt) {
-            if (need_max) {
-              float mx8[8];  // independent max chains
+          float mx8[8];  // independent max chains
 #pragma unroll
-              for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(s[e], s[e + 8]);
+          for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(s[e], s[e + 8]);
 #pragma unroll
-              for (int e = 16; e < AK; e += 16)
+          for (int e = 16; e < AK; e += 16)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mx8[j] = fmaxf(mx8[j], fmaxf(s[e + j], s[e + j + 8]));
-              const float mx = scale_log2e * fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                                                   fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-              // scale > 0: max commutes with the scaling.  First key seen by this row: adopt its max, nothing to rescale
-              // (every earlier P of the row was 0, so its O row and sum are 0).
-              if (m_used == -INFINITY) m_used = mx;
-              if (__any_sync(0xffffffffu, mx > m_used + RESCALE_THRESHOLD)) {
-                // rare: raise the reference max of the rows that need it and rescale their O rows in TMEM.  PV_{G-1} must
-                // have completed; PV_G cannot start before this warp arrives on p_full.  i > 0 here: on the item's first
-                // block every row has m_used == mx or -inf.
-                mbar_wait_tagged(pv_done, (G - 1) & 1, 9);
-                tc_fence_after();
-                const float m_new = fmaxf(m_used, mx);
-                const float alpha = ex2(m_used - m_new);  // 1 for rows that keep their reference
-                const uint64_t a2 = f2_pack(alpha, alpha);
+            for (int j = 0; j < 8; ++j) mx8[j] = fmaxf(mx8[j], fmaxf(s[e + j], s[e + j + 8]));
+          const float mx = scale_log2e * fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+          // scale > 0: max commutes with the scaling.  First key seen by this row: adopt its max, nothing to rescale
+          // (every earlier P of the row was 0, so its O row and sum are 0).
+          if (m_used == -INFINITY) m_used = mx;
+          if (__any_sync(0xffffffffu, mx > m_used + RESCALE_THRESHOLD)) {
+            // rare: raise the reference max of the rows that need it and rescale their O rows in TMEM.  PV_{G-1} must
+            // have completed; PV_G cannot start before this warp arrives on p_full.  i > 0 here: on the item's first
+            // block every row has m_used == mx or -inf.
+            mbar_wait_tagged(pv_done, (G - 1) & 1, 9);
+            tc_fence_after();
+            const float m_new = fmaxf(m_used, mx);
+            const float alpha = ex2(m_used - m_new);  // 1 for rows that keep their reference
+            const uint64_t a2 = f2_pack(alpha, alpha);
 #pragma unroll
-                for (int c = 0; c < AD / 16; ++c) {
-                  uint32_t t[16];
-                  tmem_ld_32x32b_x16(t_lane + AK + c * 16, t);
-                  tmem_ld_wait();
+            for (int c = 0; c < AD / 16; ++c) {
+              uint32_t t[16];
+              tmem_ld_32x32b_x16(t_lane + AK + c * 16, t);
+              tmem_ld_wait();
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    float lo_, hi_;
-                    f2_unpack(f2_mul(f2_pack_bits(t[2 * e], t[2 * e + 1]), a2), lo_, hi_);
-                    t[2 * e] = __float_as_uint(lo_);
-                    t[2 * e + 1] = __float_as_uint(hi_);
-                  }
-                  tmem_st_32x32b_x16(t_lane + AK + c * 16, t);
-                }
-                tmem_st_wait();
-                l2 = f2_mul(l2, a2);
-                m_used = m_new;
+              for (int e = 0; e < 8; ++e) {
+                float lo_, hi_;
+                f2_unpack(f2_mul(f2_pack_bits(t[2 * e], t[2 * e + 1]), a2), lo_, hi_);
+                t[2 * e] = __float_as_uint(lo_);
+                t[2 * e + 1] = __float_as_uint(hi_);
               }
+              tmem_st_32x32b_x16(t_lane + AK + c * 16, t);
             }
-            const float mu = m_used == -INFINITY ? 0.f : m_used;
-            const uint64_t nmu2 = f2_pack(-mu, -mu);
-            sum2 = 0ull;
-            sum2b = 0ull;
-            if (i > 0) mbar_wait_tagged(pv_done, (G - 1) & 1, 7);  // (a second wait on a completed phase returns at once)
-            auto chunk = [&](auto cc) {  // 8 columns -> one 16-byte chunk of the P row, stored as it is produced
-              constexpr int c = decltype(cc)::value;
-              float pe[8];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0, x1;
-                f2_unpack(f2_fma(f2_pack(s[c * 8 + 2 * e], s[c * 8 + 2 * e + 1]), scale2, nmu2), x0, x1);
-                pe[2 * e] = ex2(x0);      // masked: fma(-inf, .) = -inf -> 0
-                pe[2 * e + 1] = ex2(x1);
-                if (e & 1) sum2b = f2_add(sum2b, f2_pack(pe[2 * e], pe[2 * e + 1]));
-                else sum2 = f2_add(sum2, f2_pack(pe[2 * e], pe[2 * e + 1]));
-              }
-              if constexpr (SPLIT) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split_half2(pe[2 * e], pe[2 * e + 1], h[e], l[e]);
-                st_p_chunk<c>(p_row_sw, h[0], h[1], h[2], h[3]);
-                st_p_chunk<c>(p_row_sw + SP_BYTES, l[0], l[1], l[2], l[3]);
-              } else {
-                st_p_chunk<c>(p_row_sw, pack_half2(pe[0], pe[1]), pack_half2(pe[2], pe[3]), pack_half2(pe[4], pe[5]),
-                              pack_half2(pe[6], pe[7]));
-              }
-            };
-            chunk(IntC<0>{}); chunk(IntC<1>{}); chunk(IntC<2>{}); chunk(IntC<3>{});
-            chunk(IntC<4>{}); chunk(IntC<5>{}); chunk(IntC<6>{}); chunk(IntC<7>{});
-            if (need_max) break;
-            float b0, b1;
-            f2_unpack(f2_add(sum2, sum2b), b0, b1);
-            if (!__any_sync(0xffffffffu, !(b0 + b1 <= 32768.f))) break;   // (also catches inf / NaN)
-            need_max = true;   // some probability may not fit fp16: redo this block against its exact max
+            tmem_st_wait();
+            l2 = f2_mul(l2, a2);
+            m_used = m_new;
           }
+          const float mu = m_used == -INFINITY ? 0.f : m_used;
+          const uint64_t nmu2 = f2_pack(-mu, -mu);
+          uint64_t sum2 = 0ull, sum2b = 0ull;
+          if (i > 0) mbar_wait_tagged(pv_done, (G - 1) & 1, 7);  // (a second wait on a completed phase returns at once)
+          auto chunk = [&](auto cc) {  // 8 columns -> one 16-byte chunk of the P row, stored as it is produced
+            constexpr int c = decltype(cc)::value;
+            float pe[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0, x1;
+              f2_unpack(f2_fma(f2_pack(s[c * 8 + 2 * e], s[c * 8 + 2 * e + 1]), scale2, nmu2), x0, x1);
+              pe[2 * e] = ex2(x0);      // masked: fma(-inf, .) = -inf -> 0
+              pe[2 * e + 1] = ex2(x1);
+              if (e & 1) sum2b = f2_add(sum2b, f2_pack(pe[2 * e], pe[2 * e + 1]));
+              else sum2 = f2_add(sum2, f2_pack(pe[2 * e], pe[2 * e + 1]));
+            }
+            if constexpr (SPLIT) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_half2(pe[2 * e], pe[2 * e + 1], h[e], l[e]);
+              st_p_chunk<c>(p_row_sw, h[0], h[1], h[2], h[3]);
+              st_p_chunk<c>(p_row_sw + SP_BYTES, l[0], l[1], l[2], l[3]);
+            } else {
+              st_p_chunk<c>(p_row_sw, pack_half2(pe[0], pe[1]), pack_half2(pe[2], pe[3]), pack_half2(pe[4], pe[5]),
+                            pack_half2(pe[6], pe[7]));
+            }
+          };
+          chunk(IntC<0>{}); chunk(IntC<1>{}); chunk(IntC<2>{}); chunk(IntC<3>{});
+          chunk(IntC<4>{}); chunk(IntC<5>{}); chunk(IntC<6>{}); chunk(IntC<7>{});
           l2 = f2_add(l2, f2_add(sum2, sum2b));
         }
         fence_proxy_async_smem();  // P written with st.shared must be visible to the tensor core (async proxy)
