@@ -540,41 +540,66 @@ __global__ void sparse_scatter_query_kernel(const int64_t* __restrict__ q_indptr
   }
 }
 
-__global__ void __launch_bounds__(256)
+// Warp per CSR row, lanes arranged 4 terms x 8 lanes.  The cost is the gather of the dense query table.  First version
+// (lane = term, each lane reading its term's 32 queries with 8 float4 loads): a warp-wide 16-byte load to 32 DIFFERENT table
+// rows is 32 L1 wavefronts of 16 useful bytes each -- 4.3 ms per pass over 128 M stored terms, L2 at 20 % and the SM at
+// 9 % of peak (ncu, profiles/r2_sparse_scan_full_raw.csv).  Here the 8 lanes of a group read ONE 128-byte table row
+// together (one wavefront, 4 queries per lane) and a warp-wide load covers 4 terms: 1.3 ms per pass.  What bounds it now
+// is the SM's 128 B/clk load-return path (l1tex data-pipe wavefronts 74 % of peak, profiles/r2b_sparse_scan_*): 128 bytes
+// of table per stored term have to reach registers, and the shuffles that hand out indices / values share that path.
+// Tried and dropped: tiles of 8 rows per warp with 32-byte score stores (same time at 1 M rows, slower at 10 k: the
+// 4-byte stores were not the limit).
+__global__ void __launch_bounds__(256, 4)
 sparse_scan_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                    const float* __restrict__ values, int64_t n, const float* __restrict__ qT, int nq,
                    const uint8_t* __restrict__ deleted, float* __restrict__ scores) {
+  static_assert(SQT == 32, "lane layout: 8 lanes x 4 queries per table row");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, j = lane & 7;   // group = term slot of a step, j = which 4 queries of the table row
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < n; row += nwarps) {
     const int64_t a = indptr[row], b = indptr[row + 1];
-    float acc[SQT];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = a + lane < b ? __ldg(indices + a + lane) : 0;       // padding terms: table row 0 with weight 0
+    float v = a + lane < b ? __ldg(values + a + lane) : 0.f;
+    for (int64_t base = a; base < b; base += 32) {
+      const int64_t next = base + 32 + lane;   // the next 32 terms are in flight while this block gathers
+      const int t_next = next < b ? __ldg(indices + next) : 0;
+      const float v_next = next < b ? __ldg(values + next) : 0.f;
+      // No branch on the tail: padding terms cost an L1 hit on table row 0, a branch per step would make the compiler
+      // wait for each gather before issuing the next (seen in the SASS of an earlier version).
+      float4 q[8];
+      float vv[8];
 #pragma unroll
-    for (int qi = 0; qi < SQT; ++qi) acc[qi] = 0.f;
-    for (int64_t j = a + lane; j < b; j += 32) {
-      const int t = __ldg(indices + j);
-      const float v = __ldg(values + j);
-      const float4* qrow = reinterpret_cast<const float4*>(qT + static_cast<size_t>(t) * SQT);
-#pragma unroll
-      for (int c = 0; c < SQT / 4; ++c) {
-        const float4 qv = __ldg(qrow + c);
-        acc[4 * c] += v * qv.x; acc[4 * c + 1] += v * qv.y; acc[4 * c + 2] += v * qv.z; acc[4 * c + 3] += v * qv.w;
+      for (int k = 0; k < 8; ++k) {
+        const int tt = __shfl_sync(0xffffffffu, t, 4 * k + g);
+        vv[k] = __shfl_sync(0xffffffffu, v, 4 * k + g);
+        q[k] = __ldg(reinterpret_cast<const float4*>(qT + static_cast<size_t>(tt) * SQT) + j);
       }
-    }
-    // transposing butterfly: lane l ends with the full sum of query l (31 shuffles instead of 5 per query)
 #pragma unroll
-    for (int off = 16, cnt = SQT / 2; off >= 1; off >>= 1, cnt >>= 1) {
-      const bool upper = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < cnt; ++i) {
-        const float send = upper ? acc[i] : acc[i + cnt];
-        const float keep = upper ? acc[i + cnt] : acc[i];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int k = 0; k < 8; ++k) {
+        acc.x = fmaf(vv[k], q[k].x, acc.x);
+        acc.y = fmaf(vv[k], q[k].y, acc.y);
+        acc.z = fmaf(vv[k], q[k].z, acc.z);
+        acc.w = fmaf(vv[k], q[k].w, acc.w);
       }
+      t = t_next;
+      v = v_next;
     }
-    // (the step with lane offset `off` keeps the half of the remaining queries selected by that bit of the lane index, so
-    // lane l is left with query l in acc[0])
-    if (lane < nq) scores[static_cast<size_t>(lane) * n + row] = deleted[row] ? -INFINITY : acc[0];
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {   // sum over the 4 term slots
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    if (lane < 8) {
+      const bool dead = deleted[row] != 0;
+      const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (4 * lane + e < nq) scores[static_cast<size_t>(4 * lane + e) * n + row] = dead ? -INFINITY : r[e];
+    }
   }
 }
 
