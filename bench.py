@@ -410,22 +410,24 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
     pr = timed.profiled(lambda: sx.search_sparse(qip, qix, qvl, 10))
     passes = pr["scan"]["launches"]
     bytes_pass = 8 * int(ip[-1]) + 8 * (len(ip))
-    # the scan gathers one 128-byte line of the dense query table (32 queries) per stored term from L2: that traffic, not
-    # the 8 bytes per term streamed from HBM, is what bounds it.  L2 peak: ~6300 B/clk full chip (B300_MICROARCH.md, LTS
-    # throughput cap) x the SM clock.
-    l2_peak = 6300 * 1.965e9 / 1e9
+    # the scan gathers one 128-byte row of the dense query table (32 queries) per stored term (L1 / L2 hits): what bounds
+    # it is the SMs' load-return path, 128 B/clk/SM (ncu: l1tex data-pipe wavefronts, profiles/r2b_sparse_scan_*), not the
+    # 8 bytes per term streamed from HBM.
+    import torch
+    l2_peak = torch.cuda.get_device_properties(0).multi_processor_count * 128 * 1.965e9 / 1e9
     gather_pass = (8 + 128) * int(ip[-1])
     out["docs10k_q1000"] = {
         "e2e": {"value": 1000 / dt, "unit": "queries/s", "us_per_query": dt / 1000 * 1e6,
                 "path": "vrag_index_search_sparse(host CSR queries) -> host ids + scores"},
         "nnz_corpus": int(ip[-1]), "scan_ms": pr["scan"]["ms"], "select_ms": pr["select"]["ms"], "corpus_passes": passes,
-        "roofline": {"bound": "l2", "kernel": "sparse_scan_kernel (32 queries per corpus pass)",
-                     "achieved": passes * gather_pass / pr["scan"]["ms"] / 1e6, "peak": l2_peak, "unit": "GB/s of L2 traffic",
+        "roofline": {"bound": "sm load-return path", "kernel": "sparse_scan_kernel (32 queries per corpus pass)",
+                     "achieved": passes * gather_pass / pr["scan"]["ms"] / 1e6, "peak": l2_peak,
+                     "unit": "GB/s into registers (8 B streamed + 128 B gathered per stored term)",
                      "frac": passes * gather_pass / pr["scan"]["ms"] / 1e6 / l2_peak,
-                     "peak_source": "6300 B/clk LTS cap (B300_MICROARCH.md) x 1965 MHz",
+                     "peak_source": "128 B/clk/SM x SMs x 1965 MHz",
                      "hbm_GBps": passes * bytes_pass / pr["scan"]["ms"] / 1e6,
-                     "note": "the 13.6 MB CSR corpus is L2-resident (SURVEY.md 8d): the bound is the gather of 128 B of the "
-                             "dense query table per stored term; see docs1M for the HBM-resident corpus"}}
+                     "note": "the 13.6 MB CSR corpus is L2-resident (SURVEY.md 8d) and a pass is a ~29 us launch: "
+                             "launch-bound at this size; see docs1M for the HBM-resident corpus"}}
     sx.close()
     if big_docs > 0:
         bip, bix, bvl = make_sparse_rows_device(big_docs, seed=1002, device=device)
@@ -447,9 +449,11 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
             "docs": big_docs, "nnz_corpus": int(bip[-1]), "queries": nq, "queries_per_pass": nq / max(passes, 1),
             "e2e": {"value": nq / dt, "unit": "queries/s", "path": "vrag_index_search_sparse(host CSR queries)"},
             "scan_ms": pr["scan"]["ms"], "select_ms": pr["select"]["ms"],
-            "roofline": {"bound": "l2", "kernel": "sparse_scan_kernel (32 queries per corpus pass)", "achieved": l2_gbs,
-                         "peak": l2_peak, "unit": "GB/s of L2 traffic (8 B streamed + 128 B gathered per stored term)",
-                         "frac": l2_gbs / l2_peak, "peak_source": "6300 B/clk LTS cap (B300_MICROARCH.md) x 1965 MHz",
+            "roofline": {"bound": "sm load-return path", "kernel": "sparse_scan_kernel (32 queries per corpus pass)",
+                         "achieved": l2_gbs, "peak": l2_peak,
+                         "unit": "GB/s into registers (8 B streamed + 128 B gathered per stored term)",
+                         "frac": l2_gbs / l2_peak, "peak_source": "128 B/clk/SM x SMs x 1965 MHz; ncu shows the l1tex data "
+                         "pipe at 74 % (the shuffles that distribute indices / values share it)",
                          "hbm_GBps": gbs, "hbm_frac": gbs / peaks["hbm_gbs"], "hbm_bytes_per_launch": bytes_pass,
                          "avg_launch_ms": pr["scan"]["ms"] / max(passes, 1)}}
         bx.close()
