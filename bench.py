@@ -408,7 +408,7 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
     sx.search_sparse(qip, qix, qvl, 10)
     dt = time.perf_counter() - t0
     pr = timed.profiled(lambda: sx.search_sparse(qip, qix, qvl, 10))
-    passes = pr["scan"]["launches"]
+    passes = (1000 + 31) // 32   # 32 queries per corpus pass (all passes of a selection group share one launch)
     bytes_pass = 8 * int(ip[-1]) + 8 * (len(ip))
     # the scan gathers one 128-byte row of the dense query table (32 queries) per stored term (L1 / L2 hits): what bounds
     # it is the SMs' load-return path, 128 B/clk/SM (ncu: l1tex data-pipe wavefronts, profiles/r2b_sparse_scan_*), not the
@@ -426,8 +426,8 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
                      "frac": passes * gather_pass / pr["scan"]["ms"] / 1e6 / l2_peak,
                      "peak_source": "128 B/clk/SM x SMs x 1965 MHz",
                      "hbm_GBps": passes * bytes_pass / pr["scan"]["ms"] / 1e6,
-                     "note": "the 13.6 MB CSR corpus is L2-resident (SURVEY.md 8d) and a pass is a ~29 us launch: "
-                             "launch-bound at this size; see docs1M for the HBM-resident corpus"}}
+                     "note": "the 13.6 MB CSR corpus is L2-resident (SURVEY.md 8d) and 32 passes take 0.6 ms: "
+                             "latency-bound at this size; see docs1M for the HBM-resident corpus"}}
     sx.close()
     if big_docs > 0:
         bip, bix, bvl = make_sparse_rows_device(big_docs, seed=1002, device=device)
@@ -441,7 +441,7 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
         bx.search_sparse(qip[:nq + 1], qix, qvl, 10)
         dt = time.perf_counter() - t0
         pr = timed.profiled(lambda: bx.search_sparse(qip[:nq + 1], qix, qvl, 10))
-        passes = pr["scan"]["launches"]
+        passes = (nq + 31) // 32
         bytes_pass = 8 * int(bip[-1]) + 8 * (big_docs + 1)
         gbs = passes * bytes_pass / pr["scan"]["ms"] / 1e6
         l2_gbs = passes * (8 + 128) * int(bip[-1]) / pr["scan"]["ms"] / 1e6
