@@ -292,10 +292,12 @@ def sec_dense(ctx, peaks, rank, world, device, cpu: bool):
         out[f"top{k}_q{nq}"] = rec
     # host-buffer e2e through the C ABI: queries H2D + search + ids / scores D2H inside the call
     qh = np.random.default_rng(2004).standard_normal((1000, dim), dtype=np.float32)
-    ix.search_dense(qh[:16], k)
-    t0 = time.perf_counter()
-    ix.search_dense(qh, k)
-    dt = time.perf_counter() - t0
+    ix.search_dense(qh, k)   # warm-up at the timed batch size: the first call of a size allocates its device buffers
+    dt = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ix.search_dense(qh, k)
+        dt = min(dt, time.perf_counter() - t0)
     out["e2e"] = {"value": 1000 / dt, "unit": "queries/s", "h2d_bytes": int(qh.nbytes), "d2h_bytes": 1000 * k * 12,
                   "path": "vrag_index_search_dense(host queries) -> host ids + scores, one call for 1000 queries"}
     if world > 1:
