@@ -301,23 +301,37 @@ def sec_dense(ctx, peaks, rank, world, device, cpu: bool):
     out["e2e"] = {"value": 1000 / dt, "unit": "queries/s", "h2d_bytes": int(qh.nbytes), "d2h_bytes": 1000 * k * 12,
                   "path": "vrag_index_search_dense(host queries) -> host ids + scores, one call for 1000 queries"}
     if world > 1:
-        # configs[3] as stated: queries replicated, per-rank top-k, ONE packed NCCL all_gather + device merge, no host sync
+        # configs[3] as stated: queries replicated, per-rank top-k, ONE exchange of the [1000, 10] blocks + device merge, no
+        # host sync: as stores into NVLink peer memory (PeerExchange) when the group has peer access, and as one packed
+        # NCCL all_gather (timed beside it)
+        from verbatim_rag_b200.distributed import make_peer_exchange
         q = torch.randn(1000, dim, device=device, generator=gq)
-        for _ in range(2):
-            sharded_search_dense(ix, q, k)
-        dist.barrier()
-        torch.cuda.synchronize(device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            gi, gs, _ = sharded_search_dense(ix, q, k)
-        e1.record()
-        torch.cuda.synchronize(device)
-        ms = _all_max(e0.elapsed_time(e1) / 3, device, world)
+        ex = make_peer_exchange(ctx, device)
+
+        def timed_global(exchange):
+            for _ in range(2):
+                sharded_search_dense(ix, q, k, exchange=exchange)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                gi, gs, _ = sharded_search_dense(ix, q, k, exchange=exchange)
+            e1.record()
+            torch.cuda.synchronize(device)
+            return _all_max(e0.elapsed_time(e1) / 3, device, world), gi, gs
+
+        ms_nccl, gi_n, gs = timed_global(None)
+        ms = ms_nccl
+        if ex is not None:
+            ms, gi_p, gs = timed_global(ex)
+            assert bool((gi_p == gi_n).all().item()), "peer exchange and NCCL all-gather disagree"
         out["top10_q1000_global"] = {
             "ms": ms, "queries_per_s": 1000 / ms * 1e3, "ranks": world, "rows_total": n_total,
-            "collective": "one all_gather of packed [1000, 10] x (f64 score, i64 id) per rank + vrag_topk_merge, "
-                          "device-ordered on the library stream (no host sync)",
+            "exchange": ("vrag_topk_publish: each rank stores its [1000, 10] x (f64 score, i64 id) block into every peer's "
+                         "symmetric buffer over NVLink + one device barrier + vrag_topk_merge_packed") if ex is not None else
+                        "one NCCL all_gather of packed [1000, 10] x (f64 score, i64 id) per rank + vrag_topk_merge",
+            "ms_with_nccl_all_gather": ms_nccl, "device_ordered": "everything on the library stream, no host sync",
             "ids_sorted_by_score": bool((gs[:, :-1] >= gs[:, 1:]).all().item())}
     ix.close()
     if cpu:

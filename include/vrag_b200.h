@@ -25,6 +25,7 @@
  *   vrag_index_search_sparse <- BaseMilvusStore.query sparse branch -> client.search milvus_base.py:250-259
  *   vrag_index_mark_deleted  <- BaseMilvusStore.delete -> client.delete         milvus_base.py:461-470
  *   vrag_topk_merge          <- (new) merge of per-shard top-k after the NCCL all-gather
+ *   vrag_topk_publish / vrag_topk_merge_packed <- (new) the same exchange as stores into NVLink peer memory
  *
  * Conventions: every call returns an int status (0 = VRAG_OK); vrag_last_error() gives the message.
  * The CALLER owns all data buffers; the library owns only handles, weights, corpora and workspaces.
@@ -246,6 +247,18 @@ int vrag_index_search_sparse(vrag_index* idx, const int64_t* q_indptr, const int
  * global top-k with the same order.  Device buffers on ctx's GPU. */
 int vrag_topk_merge(vrag_ctx* ctx, const double* scores64, const int64_t* ids, int nq, int m, int k, int64_t* ids_out,
                     float* scores_out, double* scores64_out);
+
+/* The same exchange over NVLink / NVSwitch peer memory instead of an NCCL all-gather (the one collective
+ * of the path).  peer_bufs: `world` device pointers (a host array) -- the SAME symmetric buffer of every rank as mapped
+ * into this process (cudaIpc / fabric handles; the Python host side uses torch's symmetric memory), each holding
+ * [world][nq][k] records of 16 bytes (fp64 score bits, int64 global id).  vrag_topk_publish stores this rank's block
+ * (device arrays scores64 / ids, [nq][k]) into slot `rank` of every peer's buffer; after a cross-rank barrier on the
+ * same stream, vrag_topk_merge_packed merges the `world` blocks of the LOCAL buffer into the global top-k
+ * ((score desc, id asc), id < 0 = empty slot: bit-identical to vrag_topk_merge on the gathered arrays). */
+int vrag_topk_publish(vrag_ctx* ctx, const double* scores64, const int64_t* ids, int nq, int k, void* const* peer_bufs,
+                      int world, int rank);
+int vrag_topk_merge_packed(vrag_ctx* ctx, const int64_t* packed, int world, int nq, int k, int64_t* ids_out,
+                           float* scores_out, double* scores64_out);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from verbatim_rag_b200 import _native  # noqa: E402
-from verbatim_rag_b200.distributed import shard_bounds, sharded_search_dense, sharded_search_sparse  # noqa: E402
+from verbatim_rag_b200.distributed import (make_peer_exchange, shard_bounds, sharded_search_dense,  # noqa: E402
+                                           sharded_search_sparse)
 from verbatim_rag_b200.synthetic import make_dense_corpus, make_dense_queries, make_sparse_rows  # noqa: E402
 
 
@@ -32,6 +33,17 @@ def main():
     fid, fs32, fs64 = full.search_dense(queries, k, want64=True)
     assert np.array_equal(ids.cpu().numpy(), fid), "dense ids differ"
     assert np.array_equal(s64.cpu().numpy(), fs64), "dense fp64 scores differ"
+    # the same exchange as stores into NVLink peer memory (symmetric buffer + device barrier) instead of NCCL
+    ex = make_peer_exchange(ctx, dev)
+    if ex is not None:
+        qd_dev = torch.from_numpy(queries).to(dev)
+        for rep in range(5):   # several calls: the two slots of the exchange buffer alternate
+            pid, _, ps64 = sharded_search_dense(shard, qd_dev if rep % 2 == 0 else qd_dev[:7], k, exchange=ex)
+            nq = pid.shape[0]
+            assert np.array_equal(pid.cpu().numpy(), fid[:nq]), "dense ids differ (peer exchange)"
+            assert np.array_equal(ps64.cpu().numpy(), fs64[:nq]), "dense fp64 scores differ (peer exchange)"
+    if rank == 0:
+        print("PEER_EXCHANGE", "on" if ex is not None else "unavailable", flush=True)
 
     ip, ix, vl = make_sparse_rows(8000, seed=1002)
     qip, qix, qvl = make_sparse_rows(16, seed=2002, query=True)
@@ -45,6 +57,10 @@ def main():
     rid, _, rd = fsx.search_sparse(qip, qix, qvl, k, want64=True)
     assert np.array_equal(sid.cpu().numpy(), rid), "sparse ids differ"
     assert np.array_equal(sd.cpu().numpy(), rd), "sparse fp64 scores differ"
+    if ex is not None:
+        sid, _, sd = sharded_search_sparse(ss, qip, qix, qvl, k, dev, exchange=ex)
+        assert np.array_equal(sid.cpu().numpy(), rid), "sparse ids differ (peer exchange)"
+        assert np.array_equal(sd.cpu().numpy(), rd), "sparse fp64 scores differ (peer exchange)"
     # the plugin-level store: vectors split over the ranks, payload replicated, one all-gather per search
     from verbatim_rag_b200 import B200VectorStore
     from verbatim_rag_b200.sharded_store import ShardedB200VectorStore

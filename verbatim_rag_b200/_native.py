@@ -30,6 +30,8 @@ EXPORTS = [
     "vrag_index_create", "vrag_index_destroy", "vrag_index_size", "vrag_index_add_dense", "vrag_index_add_sparse",
     "vrag_index_set_id_base", "vrag_index_mark_deleted", "vrag_index_set_filter", "vrag_index_search_dense", "vrag_index_search_sparse",
     "vrag_topk_merge",
+    "vrag_topk_publish",
+    "vrag_topk_merge_packed",
     "vrag_encoder_create_ex", "vrag_selftest_gemm_split", "vrag_bench_gemm_split", "vrag_selftest_attention_split",
     "vrag_bench_attention_split", "vrag_encoder_hidden", "vrag_rerank_forward", "vrag_sentence_forward",
     "vrag_span_extract",
@@ -114,6 +116,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "vrag_index_search_dense": (i32, [vp, vp, i32, i32, vp, vp, vp, i32]),
             "vrag_index_search_sparse": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
             "vrag_topk_merge": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+            "vrag_topk_publish": (i32, [vp, vp, vp, i32, i32, vp, i32, i32]),
+            "vrag_topk_merge_packed": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -245,6 +249,16 @@ class Context:
         """Device buffers (torch tensors or raw pointers)."""
         self.check(self.lib.vrag_topk_merge(self.h, _ptr(scores64), _ptr(ids), nq, m, k, _ptr(ids_out),
                                             _ptr(scores_out), _ptr(scores64_out)))
+
+    def topk_publish(self, scores64, ids, nq: int, k: int, peer_ptrs, rank: int):
+        """Store this rank's [nq, k] (score64, id) block into slot ``rank`` of every peer's exchange buffer
+        (``peer_ptrs``: one device address per rank, mapped into this process)."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self.check(self.lib.vrag_topk_publish(self.h, _ptr(scores64), _ptr(ids), nq, k, arr, len(peer_ptrs), rank))
+
+    def topk_merge_packed(self, packed, world: int, nq: int, k: int, ids_out, scores_out, scores64_out=None):
+        self.check(self.lib.vrag_topk_merge_packed(self.h, _ptr(packed), world, nq, k, _ptr(ids_out), _ptr(scores_out),
+                                                   _ptr(scores64_out)))
 
     def close(self):
         if getattr(self, "h", None):

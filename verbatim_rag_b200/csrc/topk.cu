@@ -1051,6 +1051,59 @@ void grow(vrag_ctx* ctx, DevBuf& b, size_t used_bytes, size_t need_bytes) {
 }
 
 // scores [nq_tile][n] on device -> final top-k for the tile written at out offsets
+// ---------------------------------------------------------------------------------- peer exchange (multi-GPU)
+// The all-gather of the per-shard top-k as plain stores into peer memory (NVLink / NVSwitch): every rank writes its
+// [nq][k] block of 16-byte (fp64 score bits, global id) records into slot `rank` of EVERY rank's exchange buffer
+// ([world][nq][k][2] int64, a symmetric allocation whose peer mappings the host passes in).  One block per peer x
+// chunk; 16-byte stores, coalesced.  After a cross-rank barrier each rank merges its own buffer (rank_packed_kernel).
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs {
+  unsigned long long p[MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+topk_publish_kernel(const double* __restrict__ score64, const int64_t* __restrict__ ids, int64_t n_rec, PeerPtrs peers,
+                    int rank) {
+  longlong2* dst = reinterpret_cast<longlong2*>(peers.p[blockIdx.y]) + static_cast<size_t>(rank) * n_rec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_rec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = make_longlong2(__double_as_longlong(score64[i]), ids[i]);
+  __threadfence_system();   // the records are performed system-wide before the kernel (and the barrier after it) ends
+}
+
+// rank_kernel on the exchange buffer: candidate j of query q = record (j / k of rank, q, j % k)
+__global__ void __launch_bounds__(256)
+rank_packed_kernel(const longlong2* __restrict__ packed, int world, int nq, int k, int64_t* __restrict__ ids_out,
+                   float* __restrict__ scores_out, double* __restrict__ scores64_out) {
+  extern __shared__ longlong2 rec[];   // [world * k]
+  const int q = blockIdx.x, m = world * k;
+  for (int j = threadIdx.x; j < m; j += blockDim.x)
+    rec[j] = packed[(static_cast<size_t>(j / k) * nq + q) * k + (j % k)];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {  // default fill
+    ids_out[static_cast<size_t>(q) * k + j] = -1;
+    scores_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+    if (scores64_out) scores64_out[static_cast<size_t>(q) * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int64_t idi = rec[i].y;
+    if (idi < 0) continue;
+    const double si = __longlong_as_double(rec[i].x);
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const int64_t idj = rec[j].y;
+      if (idj < 0 || j == i) continue;
+      const double sj = __longlong_as_double(rec[j].x);
+      rank += (sj > si) || (sj == si && (idj < idi || (idj == idi && j < i)));
+    }
+    if (rank < k) {
+      ids_out[static_cast<size_t>(q) * k + rank] = idi;
+      scores_out[static_cast<size_t>(q) * k + rank] = static_cast<float>(si);
+      if (scores64_out) scores64_out[static_cast<size_t>(q) * k + rank] = si;
+    }
+  }
+}
+
 void select_and_rank(vrag_index* ix, const float* scores, int nq_tile, int k, bool dense,
                      const float* queries_dev /*dense*/, int64_t* ids_out, float* s32_out,
                      double* s64_out /*device, tile offset applied*/, cudaStream_t st, int64_t stride = 0) {
@@ -1630,6 +1683,42 @@ extern "C" int vrag_topk_merge(vrag_ctx* ctx, const double* scores64, const int6
   VRAG_CHECK(nq >= 0 && m > 0 && k > 0 && scores64 && ids && ids_out && scores_out, VRAG_ERR_ARG, "topk_merge: bad argument");
   if (nq == 0) return VRAG_OK;
   rank_kernel<<<nq, 256, 0, ctx->stream>>>(scores64, ids, m, k, 0, ids_out, scores_out, scores64_out);
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  VRAG_API_END()
+}
+
+extern "C" int vrag_topk_publish(vrag_ctx* ctx, const double* scores64, const int64_t* ids, int nq, int k,
+                                 void* const* peer_bufs, int world, int rank) {
+  if (!ctx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(ctx)
+  VRAG_CHECK(nq >= 0 && k > 0 && scores64 && ids && peer_bufs && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world,
+             VRAG_ERR_ARG, "topk_publish: bad argument (at most 16 peers)");
+  if (nq == 0) return VRAG_OK;
+  PeerPtrs pp;
+  for (int i = 0; i < world; ++i) {
+    VRAG_CHECK(peer_bufs[i] != nullptr, VRAG_ERR_ARG, "topk_publish: null peer buffer");
+    pp.p[i] = reinterpret_cast<unsigned long long>(peer_bufs[i]);
+  }
+  const int64_t n_rec = static_cast<int64_t>(nq) * k;
+  const int bx = static_cast<int>(std::min<int64_t>((n_rec + 255) / 256, 32));
+  topk_publish_kernel<<<dim3(bx, world), 256, 0, ctx->stream>>>(scores64, ids, n_rec, pp, rank);
+  VRAG_CUDA(cudaGetLastError());
+  ctx->launches++;
+  VRAG_API_END()
+}
+
+extern "C" int vrag_topk_merge_packed(vrag_ctx* ctx, const int64_t* packed, int world, int nq, int k, int64_t* ids_out,
+                                      float* scores_out, double* scores64_out) {
+  if (!ctx) return VRAG_ERR_ARG;
+  VRAG_API_BEGIN(ctx)
+  VRAG_CHECK(nq >= 0 && k > 0 && k <= MAX_K && world >= 1 && world <= MAX_PEERS && packed && ids_out && scores_out,
+             VRAG_ERR_ARG, "topk_merge_packed: bad argument");
+  if (nq == 0) return VRAG_OK;
+  const size_t smem = static_cast<size_t>(world) * k * sizeof(longlong2);
+  VRAG_CHECK(smem <= 48 * 1024, VRAG_ERR_ARG, "topk_merge_packed: world * k too large for the merge kernel");
+  rank_packed_kernel<<<nq, 256, smem, ctx->stream>>>(reinterpret_cast<const longlong2*>(packed), world, nq, k, ids_out,
+                                                     scores_out, scores64_out);
   VRAG_CUDA(cudaGetLastError());
   ctx->launches++;
   VRAG_API_END()

@@ -21,7 +21,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .distributed import gather_and_merge, shard_bounds, sharded_search_dense, sharded_search_sparse
+from .distributed import (gather_and_merge, make_peer_exchange, shard_bounds, sharded_search_dense,
+                          sharded_search_sparse)
 from .vector_store import B200VectorStore, dicts_to_csr
 
 
@@ -37,6 +38,7 @@ class ShardedB200VectorStore(B200VectorStore):
         self._l2g = np.zeros(0, np.int64)      # local row -> global row (= position in the replicated payload lists)
         self._g2l: List[int] = []              # global row -> local row, -1 when another rank holds it
         self._l2g_dev: Optional[torch.Tensor] = None
+        self._exchange = False   # False = not set up yet; None = unavailable (NCCL all-gather); else a PeerExchange
         self._on_gpu = any(hasattr(ix, "search_dense_device") for ix in (self._dense, self._sparse) if ix is not None)
         self._device = torch.device("cuda", self._ctx.device) if self._on_gpu else torch.device("cpu")
 
@@ -105,6 +107,13 @@ class ShardedB200VectorStore(B200VectorStore):
                 for ix in live:
                     ix.set_filter(None)
 
+    def _peer_exchange(self):
+        """NVLink peer-memory exchange for the per-shard top-k (distributed.PeerExchange), set up collectively on the
+        first search; None (-> NCCL all-gather) when the group has no peer access."""
+        if self._exchange is False:
+            self._exchange = make_peer_exchange(self._ctx, self._device, self._group)
+        return self._exchange
+
     def _l2g_tensor(self) -> torch.Tensor:
         if self._l2g_dev is None or len(self._l2g_dev) != max(1, len(self._l2g)):
             a = self._l2g if len(self._l2g) else np.zeros(1, np.int64)
@@ -115,7 +124,7 @@ class ShardedB200VectorStore(B200VectorStore):
         q = np.ascontiguousarray(np.asarray(queries, np.float32).reshape(-1, self.dense_dim))
         if self._on_gpu:
             ids, s32, _ = sharded_search_dense(self._dense, torch.from_numpy(q).to(self._device), limit, self._group,
-                                               local_to_global=self._l2g_tensor())
+                                               local_to_global=self._l2g_tensor(), exchange=self._peer_exchange())
             ids, s32 = ids.cpu().numpy(), s32.cpu().numpy()
         else:
             lid, _, s64 = self._dense.search_dense(q, limit, want64=True)
@@ -135,7 +144,8 @@ class ShardedB200VectorStore(B200VectorStore):
             indptr[i + 1] = len(idx)
         l2g = self._l2g if len(self._l2g) else np.zeros(1, np.int64)
         ids, s32, _ = sharded_search_sparse(self._sparse, indptr, np.asarray(idx, np.int32), np.asarray(val, np.float32),
-                                            limit, self._device, self._group, local_to_global=l2g)
+                                            limit, self._device, self._group, local_to_global=l2g,
+                                            exchange=self._peer_exchange() if self._on_gpu else None)
         ids, s32 = ids.cpu().numpy(), s32.cpu().numpy()
         return [self._hits(ids[i], s32[i], drop_zero=True) for i in range(ids.shape[0])]
 
