@@ -491,6 +491,84 @@ def sec_sparse(ctx, peaks, device, cpu: bool, big_docs: int):
     return out
 
 
+def sec_heads(ctx, rank, world, device, cpu: bool):
+    """the reference's two further model heads on the same kernels.  Host ids in -> host scores out
+    through the C ABI (the calls are end to end by construction); every rank scores its own batch (no collective)."""
+    from verbatim_rag_b200 import _native
+    from verbatim_rag_b200.synthetic import (BertSpec, ModernBertSpec, make_cross_encoder_weights, make_qa_model_weights)
+    out = {}
+    rng = np.random.default_rng(1004 + rank)
+    # cross-encoder reranker (rerankers.py:109-134): BERT-base pair classifier, 2 048 (query, chunk) pairs of 256 tokens
+    bspec = BertSpec()
+    w = make_cross_encoder_weights(1004, bspec)
+    npairs, L, lq = 2048, 256, 32
+    ids = rng.integers(1000, bspec.vocab_size, size=(npairs, L), dtype=np.int32)
+    ids[:, 0], ids[:, lq - 1], ids[:, -1] = bspec.cls_id, bspec.sep_id, bspec.sep_id
+    types = np.zeros((npairs, L), np.int32)
+    types[:, lq:] = 1
+    cu = (np.arange(npairs + 1) * L).astype(np.int32)
+    for prec in ("fast", "precise"):
+        enc = _native.Encoder(ctx, _native.ENC_BERT_CLS, w, bspec.layers, bspec.vocab_size, max_tokens=65536, precision=prec)
+        enc.rerank_forward(ids.reshape(-1), types.reshape(-1), cu)
+        dt = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            sc = enc.rerank_forward(ids.reshape(-1), types.reshape(-1), cu)
+            dt = min(dt, time.perf_counter() - t0)
+        dt = _all_max(dt, device, world)
+        out.setdefault("reranker_bert_base_256tok", {})[prec] = {
+            "pairs_per_s": world * npairs / dt, "ms": dt * 1e3, "pairs_per_gpu": npairs, "n_gpus": world,
+            "path": "vrag_rerank_forward(host ids + token types) -> host logits", "score_std": float(sc.std())}
+        enc.close()
+    # legacy QAModel sentence classifier (extractor_models/model.py:59-117): ModernBERT-base + sentence mean-pool + Linear;
+    # 512 (question + document) sequences of 512 tokens, 12 sentences of 40 tokens each
+    mspec = ModernBertSpec()
+    wq = make_qa_model_weights(1001, mspec)
+    nseq, Ls, ns, sl = 512, 512, 12, 40
+    qids = rng.integers(1000, mspec.vocab_size, size=(nseq, Ls), dtype=np.int32)
+    qids[:, 0], qids[:, -1] = mspec.cls_id, mspec.sep_id
+    qcu = (np.arange(nseq + 1) * Ls).astype(np.int32)
+    sip = (np.arange(nseq + 1) * ns).astype(np.int32)
+    s0 = np.tile(30 + np.arange(ns) * sl, nseq).astype(np.int32)
+    s1 = (s0 + sl - 1).astype(np.int32)
+    for prec in ("fast", "precise"):
+        enc = _native.Encoder(ctx, _native.ENC_MODERNBERT_SENT, wq, mspec.layers, mspec.vocab_size, max_tokens=131072,
+                              precision=prec)
+        enc.sentence_forward(qids.reshape(-1), qcu, sip, s0, s1)
+        dt = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            lg = enc.sentence_forward(qids.reshape(-1), qcu, sip, s0, s1)
+            dt = min(dt, time.perf_counter() - t0)
+        dt = _all_max(dt, device, world)
+        out.setdefault("qa_model_sentences_512tok", {})[prec] = {
+            "documents_per_s": world * nseq / dt, "sentences_per_s": world * nseq * ns / dt, "ms": dt * 1e3,
+            "documents_per_gpu": nseq, "n_gpus": world,
+            "path": "vrag_sentence_forward(host ids + sentence boundaries) -> host logits [n_sentences, 2]",
+            "logit_std": float(lg.std())}
+        enc.close()
+    if cpu:
+        import torch as _t
+        _t.set_num_threads(_host_cores())
+        from oracle.heads import cross_encoder_scores, qa_sentence_logits
+        n1 = 16
+        t0 = time.perf_counter()
+        cross_encoder_scores(w, [ids[i] for i in range(n1)], [types[i] for i in range(n1)], bspec)
+        dt = time.perf_counter() - t0
+        out["reranker_bert_base_256tok"]["cpu_baseline"] = {
+            "value": n1 / dt, "unit": "pairs/s", "cores": _host_cores(), "kind": "port",
+            "sample": f"{n1} of {npairs} pairs, one fp32 forward per pair (CrossEncoder.predict order, rerankers.py:120-126)"}
+        n2 = 4
+        t0 = time.perf_counter()
+        for i in range(n2):
+            qa_sentence_logits(wq, qids[i], [(int(a), int(b)) for a, b in zip(s0[:ns], s1[:ns])], mspec)
+        dt = time.perf_counter() - t0
+        out["qa_model_sentences_512tok"]["cpu_baseline"] = {
+            "value": n2 / dt, "unit": "documents/s", "cores": _host_cores(), "kind": "port",
+            "sample": f"{n2} of {nseq} documents, one fp32 forward per document (extractors.py:246-268)"}
+    return out
+
+
 def sec_rag(ctx, rank, world, device, cpu: bool, n_chunks: int, n_queries: int):
     """BASELINE configs[4]: SPLADE retrieve top-20 + span extraction for ``n_queries`` questions over ``n_chunks`` chunks
     of 256 tokens, strings in / verbatim span strings out through the plugin classes.  N ranks: the index is built data-
@@ -760,7 +838,8 @@ def run_gpu_arm(args, out):
         for name, fn in (("cfg4_dense_1Mx768", lambda: sec_dense(ctx, peaks, rank, world, device, cpu)),
                          ("cfg2_splade_encode_256tok", lambda: sec_splade(ctx, peaks, rank, world, device, cpu, args.splade_chunks)),
                          ("cfg2_sparse_top10", lambda: sec_sparse(ctx, peaks, device, cpu, args.sparse_docs if world == 1 else 0)),
-                         ("cfg5_rag_e2e", lambda: sec_rag(ctx, rank, world, device, cpu, args.rag_chunks, args.rag_queries))):
+                         ("cfg5_rag_e2e", lambda: sec_rag(ctx, rank, world, device, cpu, args.rag_chunks, args.rag_queries)),
+                         ("f4_heads", lambda: sec_heads(ctx, rank, world, device, cpu))):
             try:
                 sec[name] = fn()
             except Exception as exc:  # noqa: BLE001 -- a secondary block must not take the headline line down
