@@ -770,12 +770,23 @@ def run_gpu_arm(args, out):
                                              / (p_prof["gemm"]["ms"] / 1e3) / 1e12 if p_prof["gemm"]["ms"] > 0 else None,
                             "share_of_step": {k: v["ms"] / (p_ms * max(1, args.steps // 2)) for k, v in p_prof.items() if v["launches"]}}
 
+    # ONE table of secondary blocks for every rank.  `collective` blocks synchronise / reduce across the ranks and must run
+    # on all of them, in this order; the others run on rank 0 only.  (A block that rank 0 alone entered with a collective
+    # inside would leave the job hanging in the final barrier -- tests/test_bench_contract.py checks the table.)
+    cpu = world == 1 and args.cpu_baseline
+    secondary_blocks = (
+        ("cfg4_dense_1Mx768", True, lambda: sec_dense(ctx, peaks, rank, world, device, cpu)),
+        ("cfg2_splade_encode_256tok", True, lambda: sec_splade(ctx, peaks, rank, world, device, cpu, args.splade_chunks)),
+        ("cfg2_sparse_top10", False, lambda: sec_sparse(ctx, peaks, device, cpu, args.sparse_docs if world == 1 else 0)),
+        ("cfg5_rag_e2e", True, lambda: sec_rag(ctx, rank, world, device, cpu, args.rag_chunks, args.rag_queries)),
+        ("f4_heads", True, lambda: sec_heads(ctx, rank, world, device, cpu)),
+    )
     if rank != 0:
         enc.close()
         if args.secondary:
-            sec_dense(ctx, peaks, rank, world, device, False)
-            sec_splade(ctx, peaks, rank, world, device, False, args.splade_chunks)
-            sec_rag(ctx, rank, world, device, False, args.rag_chunks, args.rag_queries)
+            for _, collective, fn in secondary_blocks:
+                if collective:
+                    fn()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -833,13 +844,8 @@ def run_gpu_arm(args, out):
         rate, dt, cores, _ = time_cpu_spans(args.cpu_sample, 1, 1)
         line["cpu_baseline"] = cpu_baseline_block(rate, cores, args.cpu_sample)
     if args.secondary:
-        cpu = world == 1 and args.cpu_baseline
         sec = {}
-        for name, fn in (("cfg4_dense_1Mx768", lambda: sec_dense(ctx, peaks, rank, world, device, cpu)),
-                         ("cfg2_splade_encode_256tok", lambda: sec_splade(ctx, peaks, rank, world, device, cpu, args.splade_chunks)),
-                         ("cfg2_sparse_top10", lambda: sec_sparse(ctx, peaks, device, cpu, args.sparse_docs if world == 1 else 0)),
-                         ("cfg5_rag_e2e", lambda: sec_rag(ctx, rank, world, device, cpu, args.rag_chunks, args.rag_queries)),
-                         ("f4_heads", lambda: sec_heads(ctx, rank, world, device, cpu))):
+        for name, _, fn in secondary_blocks:
             try:
                 sec[name] = fn()
             except Exception as exc:  # noqa: BLE001 -- a secondary block must not take the headline line down

@@ -38,3 +38,24 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr
+
+
+def test_secondary_blocks_with_collectives_run_on_every_rank():
+    """Multi-rank safety of bench.py: a secondary block that contains a collective (all-reduce of a time, barrier,
+    sharded search, peer exchange) must be flagged `collective` in the ONE table both rank branches iterate, so that
+    every rank enters it; a block rank 0 alone entered would leave the job hanging in the final barrier (this happened
+    once with a block added to the rank-0 list only)."""
+    import inspect
+    import re
+
+    import bench
+    src = inspect.getsource(bench.run_gpu_arm)
+    table = re.findall(r'\("([\w]+)",\s*(True|False),\s*lambda:\s*(sec_\w+)\(', src)
+    assert len(table) >= 5, table
+    assert src.count("secondary_blocks") >= 3          # defined once, iterated by the rank != 0 and the rank 0 branch
+    assert "if collective:" in src
+    for name, flag, fn_name in table:
+        body = inspect.getsource(getattr(bench, fn_name))
+        has_collective = bool(re.search(r"\bdist\.|_all_max\(|barrier\(|sharded_search_|make_peer_exchange|rag_query_batch|"
+                                        r"ShardedB200VectorStore", body))
+        assert has_collective == (flag == "True"), (name, fn_name, flag, has_collective)
