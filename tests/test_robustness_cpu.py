@@ -210,3 +210,35 @@ def _host_spans(probs, tok_cs, tok_ce, ctx_indptr, threshold, min_span_chars, me
             for k in ("start", "end", "score", "tok_start", "tok_end"):
                 out[k].append(sp[k])
     return {k: np.asarray(v) for k, v in out.items()}
+
+
+def test_tokenizer_workers_match_in_process_and_survive_a_broken_pool(caplog):
+    """The worker pool is an optimisation: same arrays as in-process tokenisation, and a pool that cannot start (e.g. a
+    caller script without the ``if __name__ == "__main__"`` guard, which makes ``spawn`` raise) costs ONE warning, after
+    which everything is tokenised in-process -- no batch is lost."""
+    from verbatim_rag_b200._tokworker import TokenizerWorkers, encode_with
+    from verbatim_rag_b200.synthetic import SyntheticTokenizer
+    tk = SyntheticTokenizer("modernbert")
+    rng = np.random.default_rng(3)
+    texts = [tk.make_text(rng, int(n)) for n in rng.integers(1, 60, size=23)]
+    ref = encode_with(tk.tok, texts)
+    w = TokenizerWorkers(tk.tok, 2)
+    try:
+        got = w.encode(texts)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+    finally:
+        w.close()
+    broken = TokenizerWorkers(tk.tok, 2)
+
+    def boom():
+        raise RuntimeError("An attempt has been made to start a new process before the current process has finished "
+                           "its bootstrapping phase.")
+    broken._ensure = boom
+    with caplog.at_level(logging.WARNING):
+        got = broken.encode(texts)
+        again = broken.encode(texts)
+    for a, b, c in zip(got, again, ref):
+        assert np.array_equal(a, c) and np.array_equal(b, c)
+    assert broken.n == 0
+    assert sum("tokenising in-process" in r.message for r in caplog.records) == 1

@@ -66,9 +66,20 @@ class TokenizerWorkers:
         texts = list(texts)
         if self.n <= 0 or len(texts) < 2 * self.n:
             return encode_with(self._tok, texts)
-        pool = self._ensure()
         step = (len(texts) + self.n - 1) // self.n
-        parts = [f.result() for f in [pool.submit(encode, texts[a:a + step]) for a in range(0, len(texts), step)]]
+        try:
+            pool = self._ensure()
+            parts = [f.result() for f in [pool.submit(encode, texts[a:a + step]) for a in range(0, len(texts), step)]]
+        except Exception as exc:  # noqa: BLE001 -- the pool is an optimisation, never a reason to lose a batch
+            # Typical cause: the calling script spawns at import time (no ``if __name__ == "__main__":`` guard), or the
+            # host forbids new processes.  Tokenise in-process from now on -- same result, one warning.
+            import logging
+            logging.getLogger(__name__).warning(
+                "tokenizer worker processes unavailable (%s: %s); tokenising in-process from now on",
+                type(exc).__name__, str(exc).strip().splitlines()[0] if str(exc).strip() else "")
+            self.close()
+            self.n = 0
+            return encode_with(self._tok, texts)
         return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]),
                 np.concatenate([p[2] for p in parts], axis=0))
 
